@@ -1,0 +1,736 @@
+// als_api.cu -- host side of the B200 ALS hot path: work plans, the resident solver
+// handle, the doALS driver and the C ABI declared in include/cumf_als.h.
+//
+// Mirrors the reference's driver doALS (als.cu:662-1035) for the path
+//   per-row Gram (+RHS) formation -> batched f x f solve -> RMSE observable,
+// re-designed for one B200: CSR/CSC/COO are uploaded once and stay resident (the
+// reference re-uploads CSR every iteration, als.cu:734-739), the X_BATCH /
+// THETA_BATCH loop that bounded a 12 GB card's Gram buffer (als.cu:768-777) is
+// replaced by an internal workspace cap (unfused path) or by never materialising
+// A at all (fused path), and long rows are split deterministically across CTAs.
+#include <cublas_v2.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cumf {
+
+// ---------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int DevBuf::alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_last_error(std::string("cudaMalloc(") + std::to_string(n) + "): " + cudaGetErrorString(e));
+        return CUMF_ECUDA;
+    }
+    bytes = n;
+    return CUMF_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+static long env_long(const char* name, long dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return atol(v);
+}
+static int env_choice(const char* name, const char* a, int va, const char* b, int vb, const char* c, int vc, int dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    if (a && !strcasecmp(v, a)) return va;
+    if (b && !strcasecmp(v, b)) return vb;
+    if (c && !strcasecmp(v, c)) return vc;
+    return dflt;
+}
+
+static int check_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_last_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+        return CUMF_ENOGPU;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (major != 10) {
+        set_last_error("this library contains sm_100a code only; found compute capability major " +
+                       std::to_string(major));
+        return CUMF_ENOGPU;
+    }
+    return CUMF_OK;
+}
+
+static int check_f(int f) {
+    // main.cpp:33-36 rejects f % 10 != 0; the kernels additionally view rows as float2 (als.cu:805)
+    CUMF_REQUIRE(f >= 10 && f <= 200 && f % 10 == 0, "f must be a multiple of 10 in [10, 200]");
+    return CUMF_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// LU oracle mode: cuBLAS batched LU without pivoting (als.cu:58-122).
+// ---------------------------------------------------------------------------------
+namespace {
+__global__ void fill_ptrs_kernel(float** Ap, float** bp, float* A, float* b, int batch, int f) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < batch) {
+        Ap[k] = A + (size_t)k * f * f;   // devPtrTTHost[k] = &tt[k*f*f]            (als.cu:70-74)
+        bp[k] = b + (size_t)k * f;       // devPtrYthetaTHost[k] = &ythetaT[... k*f] (als.cu:91-95)
+    }
+}
+cublasHandle_t g_cublas = nullptr;
+std::mutex g_cublas_mu;
+}  // namespace
+
+int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t st) {
+    if (batch <= 0) return CUMF_OK;
+    std::lock_guard<std::mutex> lk(g_cublas_mu);
+    if (!g_cublas && cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
+        set_last_error("cublasCreate failed");
+        return CUMF_ECUDA;
+    }
+    cublasSetStream(g_cublas, st);
+    DevBuf ptrs, info;
+    CUMF_TRY(ptrs.alloc(sizeof(float*) * 2 * (size_t)batch));
+    CUMF_TRY(info.alloc(sizeof(int) * (size_t)batch));
+    float** Ap = ptrs.as<float*>();
+    float** bp = Ap + batch;
+    fill_ptrs_kernel<<<(batch + 255) / 256, 256, 0, st>>>(Ap, bp, d_A, d_b, batch, f);
+    CUMF_CUDA_TRY(cudaGetLastError());
+    // A is symmetric, so its row-major storage is also its column-major storage.
+    if (cublasSgetrfBatched(g_cublas, f, Ap, f, nullptr, info.as<int>(), batch) != CUBLAS_STATUS_SUCCESS) {
+        set_last_error("cublasSgetrfBatched failed");
+        return CUMF_ECUDA;
+    }
+    int info2 = 0;
+    if (cublasSgetrsBatched(g_cublas, CUBLAS_OP_N, f, 1, (const float**)Ap, f, nullptr, bp, f, &info2, batch) !=
+        CUBLAS_STATUS_SUCCESS) {
+        set_last_error("cublasSgetrsBatched failed");
+        return CUMF_ECUDA;
+    }
+    // als.cu:108: the solution (left in the RHS) is copied into the factor
+    CUMF_CUDA_TRY(cudaMemcpyAsync(d_x, d_b, sizeof(float) * (size_t)batch * f, cudaMemcpyDeviceToDevice, st));
+    CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+    ptrs.release();
+    info.release();
+    return CUMF_OK;
+}
+
+}  // namespace cumf
+
+using namespace cumf;
+
+// ---------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------
+struct cumf_plan {
+    int rows = 0, row_begin = 0, row_end = 0, f = 0, path = CUMF_PATH_SIMT;
+    long long base = 0;                 // h_rowptr[row_begin]: chunk offsets are relative to it
+    std::vector<Chunk> chunks;
+    std::vector<SplitRow> splits;
+    std::vector<int> row_chunk_ptr;     // first chunk of each owned row (+1 sentinel)
+    DevBuf d_chunks, d_splits;
+    DevBuf scratchA, scratchB;          // split partials
+    DevBuf tt, rhs;                     // materialised batch workspace (unfused path)
+    int batch_rows = 0;
+    int last_launches = 0;
+    TcWork* tc = nullptr;
+    // optional timing of the dominant (Gram) kernel
+    bool time_kernel = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+    double kernel_ms_total = 0.0;
+};
+
+static void plan_free(cumf_plan* p) {
+    if (!p) return;
+    p->d_chunks.release(); p->d_splits.release();
+    p->scratchA.release(); p->scratchB.release(); p->tt.release(); p->rhs.release();
+    if (p->tc) tc_plan_destroy(p->tc);
+    for (auto& e : p->kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    delete p;
+}
+
+static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
+                            int path, bool alloc_workspace) {
+    CUMF_REQUIRE(out && h_rowptr, "null pointer");
+    CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
+    CUMF_TRY(check_f(f));
+    CUMF_TRY(check_device());
+    cumf_plan* p = new cumf_plan();
+    p->rows = rows; p->row_begin = row_begin; p->row_end = row_end; p->f = f;
+    if (path == CUMF_PATH_AUTO) path = tc_path_supports(f) ? CUMF_PATH_TC : CUMF_PATH_SIMT;
+    if (path == CUMF_PATH_TC && !tc_path_supports(f)) {
+        delete p;
+        set_last_error("the fused tcgen05 path does not handle f = " + std::to_string(f));
+        return CUMF_EUNSUPPORTED;
+    }
+    p->path = path;
+    p->base = h_rowptr[row_begin];
+
+    const int max_chunk = (int)env_long("CUMF_SPLIT_NNZ", path == CUMF_PATH_TC ? 8192 : 4096);
+    const int owned = row_end - row_begin;
+    p->row_chunk_ptr.resize(owned + 1);
+    int slot = 0;
+    for (int r = row_begin; r < row_end; ++r) {
+        p->row_chunk_ptr[r - row_begin] = (int)p->chunks.size();
+        const long long s = (long long)h_rowptr[r] - p->base, e = (long long)h_rowptr[r + 1] - p->base;
+        const long long n = e - s;
+        if (n < 0 || e > 0x7fffffffLL) {
+            plan_free(p);
+            set_last_error("row pointers must be non-decreasing and a shard must hold < 2^31 ratings");
+            return CUMF_EINVAL;
+        }
+        if (n <= max_chunk) {
+            p->chunks.push_back(Chunk{r, (int)s, (int)e, -1});
+        } else {
+            const int parts = (int)((n + max_chunk - 1) / max_chunk);
+            const long long per = (n + parts - 1) / parts;
+            p->splits.push_back(SplitRow{r, slot, parts, (int)n});
+            for (int q = 0; q < parts; ++q) {
+                const long long b = s + q * per, en = std::min(e, b + per);
+                p->chunks.push_back(Chunk{r, (int)b, (int)en, slot++});
+            }
+        }
+    }
+    p->row_chunk_ptr[owned] = (int)p->chunks.size();
+
+    int rc = p->d_chunks.alloc(sizeof(Chunk) * std::max<size_t>(1, p->chunks.size()));
+    if (rc == CUMF_OK && !p->chunks.empty())
+        if (cudaMemcpy(p->d_chunks.p, p->chunks.data(), sizeof(Chunk) * p->chunks.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = CUMF_ECUDA;
+    if (rc == CUMF_OK) rc = p->d_splits.alloc(sizeof(SplitRow) * std::max<size_t>(1, p->splits.size()));
+    if (rc == CUMF_OK && !p->splits.empty())
+        if (cudaMemcpy(p->d_splits.p, p->splits.data(), sizeof(SplitRow) * p->splits.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = CUMF_ECUDA;
+    const size_t ff = (size_t)f * f;
+    if (rc == CUMF_OK && slot > 0) {
+        rc = p->scratchA.alloc(sizeof(float) * ff * slot);
+        if (rc == CUMF_OK) rc = p->scratchB.alloc(sizeof(float) * (size_t)f * slot);
+    }
+    if (rc == CUMF_OK && path == CUMF_PATH_SIMT && alloc_workspace) {
+        const size_t cap = (size_t)env_long("CUMF_WORKSPACE_MB", 8192) << 20;
+        long long br = (long long)(cap / (ff * sizeof(float)));
+        if (br < 1) br = 1;
+        p->batch_rows = (int)std::min<long long>(br, std::max(1, owned));
+        rc = p->tt.alloc(sizeof(float) * ff * p->batch_rows);
+        if (rc == CUMF_OK) rc = p->rhs.alloc(sizeof(float) * (size_t)f * p->batch_rows);
+    }
+    if (rc == CUMF_OK && path == CUMF_PATH_TC) {
+        rc = tc_plan_create(&p->tc, p->chunks, p->splits, owned, f);
+        // rows split across CTAs are reduced and solved through the materialised path
+        if (rc == CUMF_OK && !p->splits.empty()) {
+            p->batch_rows = (int)p->splits.size();
+            rc = p->tt.alloc(sizeof(float) * ff * p->batch_rows);
+            if (rc == CUMF_OK) rc = p->rhs.alloc(sizeof(float) * (size_t)f * p->batch_rows);
+        }
+    }
+    if (rc != CUMF_OK) {
+        if (rc == CUMF_ECUDA && g_last_error.empty()) set_last_error("plan upload failed");
+        plan_free(p);
+        return rc;
+    }
+    *out = p;
+    return CUMF_OK;
+}
+
+extern "C" int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
+                                int path) {
+    return plan_create_impl(out, h_rowptr, rows, row_begin, row_end, f, path, true);
+}
+
+extern "C" int cumf_plan_destroy(cumf_plan* plan) {
+    plan_free(plan);
+    return CUMF_OK;
+}
+extern "C" int cumf_plan_last_launches(const cumf_plan* plan) { return plan ? plan->last_launches : 0; }
+
+static void plan_time_begin(cumf_plan* p, cudaStream_t st, cudaEvent_t* e0, cudaEvent_t* e1) {
+    *e0 = *e1 = nullptr;
+    if (!p->time_kernel) return;
+    cudaEventCreate(e0);
+    cudaEventCreate(e1);
+    cudaEventRecord(*e0, st);
+}
+static void plan_time_end(cumf_plan* p, cudaStream_t st, cudaEvent_t e0, cudaEvent_t e1) {
+    if (!p->time_kernel || !e0) return;
+    cudaEventRecord(e1, st);
+    p->kernel_events.emplace_back(e0, e1);
+}
+static double plan_collect_kernel_ms(cumf_plan* p) {
+    for (auto& e : p->kernel_events) {
+        float ms = 0.f;
+        cudaEventSynchronize(e.second);
+        if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) p->kernel_ms_total += ms;
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    p->kernel_events.clear();
+    return p->kernel_ms_total;
+}
+
+static int solve_batch(float* tt, float* x, float* rhs, int batch, int f, int solver, float cg_iter, cudaStream_t st,
+                       int* launches) {
+    if (solver == CUMF_SOLVER_LU) {
+        CUMF_TRY(launch_lu(tt, x, rhs, batch, f, st));
+        *launches += 1;   // our pointer-fill kernel; the cuBLAS kernels are library code
+    } else {
+        CUMF_TRY(launch_cg(tt, x, rhs, batch, f, cg_iter, nullptr, st));
+        *launches += 1;
+    }
+    return CUMF_OK;
+}
+
+extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
+                                  float* d_out, float lambda, int solver, float cgIter, void* stream) {
+    CUMF_REQUIRE(p && d_colidx && d_val && d_factor && d_out, "null pointer");
+    CUMF_REQUIRE(solver == CUMF_SOLVER_CG || solver == CUMF_SOLVER_LU, "unknown solver");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int f = p->f;
+    int launches = 0;
+    const Chunk* d_chunks = p->d_chunks.as<Chunk>();
+    const SplitRow* d_splits = p->d_splits.as<SplitRow>();
+
+    if (p->path == CUMF_PATH_TC && solver == CUMF_SOLVER_CG) {
+        cudaEvent_t e0, e1;
+        plan_time_begin(p, st, &e0, &e1);
+        CUMF_TRY(tc_update_factor(p->tc, d_chunks, (int)p->chunks.size(), d_colidx, d_val, d_factor, d_out,
+                                  f, lambda, cgIter, p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches));
+        plan_time_end(p, st, e0, e1);
+        // rows that were split across CTAs: reduce their partials into a compact batch, solve it
+        const int ns = (int)p->splits.size();
+        if (ns > 0) {
+            CUMF_TRY(launch_split_reduce(d_splits, 0, ns, f, lambda, /*compact=*/1, 0, p->tt.as<float>(),
+                                         p->rhs.as<float>(), p->scratchA.as<float>(), p->scratchB.as<float>(), st));
+            CUMF_TRY(launch_cg(p->tt.as<float>(), d_out, p->rhs.as<float>(), ns, f, cgIter, d_splits, st));
+            launches += 2;
+        }
+        p->last_launches = launches;
+        return CUMF_OK;
+    }
+
+    // unfused path: materialise A for a batch of rows, then solve the batch
+    if (p->path != CUMF_PATH_SIMT || p->batch_rows <= 0) {
+        set_last_error("this plan was built for the fused path; the LU oracle needs a CUMF_PATH_SIMT plan");
+        return CUMF_EUNSUPPORTED;
+    }
+    const int owned = p->row_end - p->row_begin;
+    size_t s_lo = 0;
+    for (int b0 = 0; b0 < owned; b0 += p->batch_rows) {
+        const int b1 = std::min(owned, b0 + p->batch_rows);
+        const int c0 = p->row_chunk_ptr[b0], c1 = p->row_chunk_ptr[b1];
+        const int row_base = p->row_begin + b0;
+        cudaEvent_t e0, e1;
+        plan_time_begin(p, st, &e0, &e1);
+        CUMF_TRY(launch_gram_simt(d_chunks, c0, c1, d_colidx, d_val, d_factor, f, lambda, row_base, p->tt.as<float>(),
+                                  p->rhs.as<float>(), p->scratchA.as<float>(), p->scratchB.as<float>(), st));
+        plan_time_end(p, st, e0, e1);
+        launches += (c1 > c0);
+        // split rows inside this batch
+        size_t s_hi = s_lo;
+        while (s_hi < p->splits.size() && p->splits[s_hi].row < p->row_begin + b1) ++s_hi;
+        if (s_hi > s_lo) {
+            CUMF_TRY(launch_split_reduce(d_splits, (int)s_lo, (int)s_hi, f, lambda, /*compact=*/0, row_base,
+                                         p->tt.as<float>(), p->rhs.as<float>(), p->scratchA.as<float>(),
+                                         p->scratchB.as<float>(), st));
+            launches += 1;
+        }
+        s_lo = s_hi;
+        CUMF_TRY(solve_batch(p->tt.as<float>(), d_out + (size_t)row_base * f, p->rhs.as<float>(), b1 - b0, f, solver,
+                             cgIter, st, &launches));
+    }
+    p->last_launches = launches;
+    return CUMF_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// misc C ABI
+// ---------------------------------------------------------------------------------
+extern "C" const char* cumf_last_error(void) { return g_last_error.c_str(); }
+extern "C" int cumf_version(void) { return 100; }
+
+// ---------------------------------------------------------------------------------
+// b4 seams
+// ---------------------------------------------------------------------------------
+extern "C" int cumf_gram(int batch_offset, int batch_size, float* d_tt, float* d_rhs, const int* d_rowptr,
+                         const int* d_colidx, const float* d_val, float lambda, int m, int f, const float* d_factor,
+                         int path, void* stream) {
+    CUMF_REQUIRE(d_tt && d_rowptr && d_colidx && d_factor, "null pointer");
+    CUMF_REQUIRE(!d_rhs || d_val, "d_val is required when d_rhs is requested");
+    CUMF_REQUIRE(batch_offset >= 0 && batch_size >= 0, "negative batch");
+    CUMF_TRY(check_f(f));
+    CUMF_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    // rows beyond m are skipped like `if (row < m)` in the reference kernels (als.cu:449-450)
+    const int row_end = std::min(m, batch_offset + batch_size);
+    if (row_end <= batch_offset) return CUMF_OK;
+    std::vector<int> h_rowptr(m + 1);
+    CUMF_CUDA_TRY(cudaMemcpyAsync(h_rowptr.data(), d_rowptr, sizeof(int) * (m + 1), cudaMemcpyDeviceToHost, st));
+    CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (path == CUMF_PATH_AUTO) path = CUMF_PATH_SIMT;
+    if (path != CUMF_PATH_SIMT) {
+        set_last_error("cumf_gram materialises A with the SIMT kernel; the fused path has no A to return "
+                       "(use cumf_update_factor)");
+        return CUMF_EUNSUPPORTED;
+    }
+    cumf_plan* p = nullptr;
+    // the plan's own workspace is not needed here: build it with a tiny cap, then aim the
+    // kernel at the caller's buffers.
+    CUMF_TRY(plan_create_impl(&p, h_rowptr.data(), m, batch_offset, row_end, f, CUMF_PATH_SIMT, false));
+    const long long base = p->base;
+    int rc = launch_gram_simt(p->d_chunks.as<Chunk>(), 0, (int)p->chunks.size(), d_colidx + base,
+                              d_val ? d_val + base : nullptr, d_factor, f, lambda, batch_offset, d_tt, d_rhs,
+                              p->scratchA.as<float>(), p->scratchB.as<float>(), st);
+    if (rc == CUMF_OK && !p->splits.empty())
+        rc = launch_split_reduce(p->d_splits.as<SplitRow>(), 0, (int)p->splits.size(), f, lambda, 0, batch_offset, d_tt,
+                                 d_rhs, p->scratchA.as<float>(), p->scratchB.as<float>(), st);
+    if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_last_error(std::string("cumf_gram: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = CUMF_ECUDA;
+    }
+    plan_free(p);
+    return rc;
+}
+
+extern "C" int cumf_cg(const float* d_A, float* d_x, const float* d_b, int batchSize, int f, float cgIter,
+                       void* stream) {
+    CUMF_REQUIRE(d_A && d_x && d_b, "null pointer");
+    CUMF_TRY(check_f(f));
+    CUMF_TRY(check_device());
+    CUMF_TRY(launch_cg(d_A, d_x, d_b, batchSize, f, cgIter, nullptr, (cudaStream_t)stream));
+    // updateXWithCGHost synchronises and checks (cg.cu:686-687)
+    CUMF_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return CUMF_OK;
+}
+
+extern "C" int cumf_lu(float* d_A, float* d_x, float* d_b, int batchSize, int f, void* stream) {
+    CUMF_REQUIRE(d_A && d_x && d_b, "null pointer");
+    CUMF_REQUIRE(f >= 1, "f");
+    CUMF_TRY(check_device());
+    return launch_lu(d_A, d_x, d_b, batchSize, f, (cudaStream_t)stream);
+}
+
+extern "C" int cumf_rmse(const float* d_val, const int* d_row, const int* d_col, const float* d_thetaT,
+                         const float* d_XT, long count, int f, int drop_tail, float* rmse_out, double* sse_out,
+                         void* stream) {
+    CUMF_REQUIRE(d_val && d_row && d_col && d_thetaT && d_XT, "null pointer");
+    CUMF_REQUIRE(f >= 2 && f % 2 == 0, "f must be even");
+    CUMF_TRY(check_device());
+    cudaStream_t st = (cudaStream_t)stream;
+    // the test-set launch has (count-1)/256 blocks of 256 threads (als.cu:1006)
+    long launched = drop_tail ? ((count - 1) / 256) * 256 : count;
+    if (launched < 0) launched = 0;
+    DevBuf part, out;
+    CUMF_TRY(part.alloc(sizeof(double) * sse_partial_capacity()));
+    CUMF_TRY(out.alloc(sizeof(double)));
+    int rc = launch_sse(d_val, d_row, d_col, d_thetaT, d_XT, launched, f, out.as<double>(), part.as<double>(),
+                        sse_partial_capacity(), st);
+    double sse = 0.0;
+    if (rc == CUMF_OK && cudaMemcpyAsync(&sse, out.p, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = CUMF_ECUDA;
+    if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = CUMF_ECUDA;
+    part.release();
+    out.release();
+    if (rc != CUMF_OK) return rc;
+    if (sse_out) *sse_out = sse;
+    if (rmse_out) *rmse_out = sqrtf((float)sse / (float)count);   // als.cu:991, 1018
+    return CUMF_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// resident solver handle
+// ---------------------------------------------------------------------------------
+struct cumf_als_solver {
+    int m = 0, n = 0, f = 0;
+    long nnz = 0, nnz_test = 0;
+    float lambda = 0.f;
+    int xb = 0, xe = 0, tb = 0, te = 0;
+    int device = 0, solver = CUMF_SOLVER_CG, path = CUMF_PATH_AUTO;
+    float cg_iter = 6.0f;               // CG_ITER, als.cu:32
+    // owned slices (rebased): CSR rows [xb,xe), CSC columns [tb,te)
+    DevBuf csr_col, csr_val, csc_row, csc_val;
+    DevBuf coo_row;                     // cooRowIndex for the owned CSR slice (train RMSE pairing, als.cu:979-980)
+    DevBuf test_row, test_col, test_val;
+    long train_cnt = 0, test_cnt = 0;
+    DevBuf theta, x;                    // full replicas
+    DevBuf sse, partials;
+    cumf_plan* px = nullptr;
+    cumf_plan* pt = nullptr;
+    // timers
+    double ms_x = 0, ms_theta = 0;
+    long launches = 0, iterations = 0;
+};
+
+extern "C" int cumf_als_destroy(cumf_als_solver* s) {
+    if (!s) return CUMF_OK;
+    cudaSetDevice(s->device);
+    s->csr_col.release(); s->csr_val.release(); s->csc_row.release(); s->csc_val.release();
+    s->coo_row.release(); s->test_row.release(); s->test_col.release(); s->test_val.release();
+    s->theta.release(); s->x.release(); s->sse.release(); s->partials.release();
+    plan_free(s->px);
+    plan_free(s->pt);
+    delete s;
+    return CUMF_OK;
+}
+
+template <typename T>
+static int upload(DevBuf& buf, const T* host, size_t count) {
+    CUMF_TRY(buf.alloc(sizeof(T) * count));
+    if (count) CUMF_CUDA_TRY(cudaMemcpy(buf.p, host, sizeof(T) * count, cudaMemcpyHostToDevice));
+    return CUMF_OK;
+}
+
+extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                               const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                               const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                               const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                               const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                               long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                               int device, int solver, int path) {
+    CUMF_REQUIRE(out && csrRowIndexHostPtr && csrColIndexHostPtr && csrValHostPtr && cscRowIndexHostPtr &&
+                     cscColIndexHostPtr && cscValHostPtr, "null pointer");
+    CUMF_REQUIRE(m > 0 && n > 0 && nnz >= 0 && nnz_test >= 0, "bad sizes");
+    CUMF_REQUIRE(0 <= x_begin && x_begin <= x_end && x_end <= m, "bad X row range");
+    CUMF_REQUIRE(0 <= t_begin && t_begin <= t_end && t_end <= n, "bad theta row range");
+    CUMF_TRY(check_f(f));
+    CUMF_CUDA_TRY(cudaSetDevice(device));
+    CUMF_TRY(check_device());
+    if (solver == CUMF_SOLVER_LU) path = CUMF_PATH_SIMT;   // the LU oracle needs a materialised A
+    cumf_als_solver* s = new cumf_als_solver();
+    s->m = m; s->n = n; s->f = f; s->nnz = nnz; s->nnz_test = nnz_test; s->lambda = lambda;
+    s->xb = x_begin; s->xe = x_end; s->tb = t_begin; s->te = t_end;
+    s->device = device; s->solver = solver; s->path = path;
+    int rc = CUMF_OK;
+    auto fail = [&](int code) { cumf_als_destroy(s); return code; };
+
+    // note the reference's argument order for CSC (main.cpp:99-101, als.cu:867-869):
+    // cscColIndex is the pointer array (n+1), cscRowIndex the row ids (nnz).
+    const long long xo = csrRowIndexHostPtr[x_begin], xn = (long long)csrRowIndexHostPtr[x_end] - xo;
+    const long long to = cscColIndexHostPtr[t_begin], tn = (long long)cscColIndexHostPtr[t_end] - to;
+    if ((rc = upload(s->csr_col, csrColIndexHostPtr + xo, (size_t)xn)) != CUMF_OK) return fail(rc);
+    if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn)) != CUMF_OK) return fail(rc);
+    if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn)) != CUMF_OK) return fail(rc);
+    if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn)) != CUMF_OK) return fail(rc);
+    if (cooRowIndexHostPtr) {
+        if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn)) != CUMF_OK) return fail(rc);
+        s->train_cnt = (long)xn;
+    }
+    if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
+        // samples the reference's launch covers: 256*((nnz_test-1)/256) (als.cu:1006); this
+        // shard's share is the contiguous slice proportional to its X row range.
+        const long long eff = ((long long)(nnz_test - 1) / 256) * 256;
+        const long long t0 = eff * x_begin / m, t1 = eff * x_end / m;
+        if ((rc = upload(s->test_row, cooRowIndexTestHostPtr + t0, (size_t)(t1 - t0))) != CUMF_OK) return fail(rc);
+        if ((rc = upload(s->test_col, cooColIndexTestHostPtr + t0, (size_t)(t1 - t0))) != CUMF_OK) return fail(rc);
+        if ((rc = upload(s->test_val, cooValHostTestPtr + t0, (size_t)(t1 - t0))) != CUMF_OK) return fail(rc);
+        s->test_cnt = (long)(t1 - t0);
+    }
+    if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
+    if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
+    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
+    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
+    s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
+    *out = s;
+    return CUMF_OK;
+}
+
+extern "C" int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost, const float* XTHost) {
+    CUMF_REQUIRE(s && thetaTHost && XTHost, "null pointer");
+    CUMF_CUDA_TRY(cudaSetDevice(s->device));
+    CUMF_CUDA_TRY(cudaMemcpy(s->theta.p, thetaTHost, sizeof(float) * (size_t)s->n * s->f, cudaMemcpyHostToDevice));
+    CUMF_CUDA_TRY(cudaMemcpy(s->x.p, XTHost, sizeof(float) * (size_t)s->m * s->f, cudaMemcpyHostToDevice));
+    return CUMF_OK;
+}
+extern "C" int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float* XTHost) {
+    CUMF_REQUIRE(s, "null pointer");
+    CUMF_CUDA_TRY(cudaSetDevice(s->device));
+    if (thetaTHost) CUMF_CUDA_TRY(cudaMemcpy(thetaTHost, s->theta.p, sizeof(float) * (size_t)s->n * s->f, cudaMemcpyDeviceToHost));
+    if (XTHost) CUMF_CUDA_TRY(cudaMemcpy(XTHost, s->x.p, sizeof(float) * (size_t)s->m * s->f, cudaMemcpyDeviceToHost));
+    return CUMF_OK;
+}
+extern "C" float* cumf_als_theta_ptr(cumf_als_solver* s) { return s ? s->theta.as<float>() : nullptr; }
+extern "C" float* cumf_als_x_ptr(cumf_als_solver* s) { return s ? s->x.as<float>() : nullptr; }
+
+extern "C" int cumf_als_update_x(cumf_als_solver* s, void* stream) {
+    CUMF_REQUIRE(s, "null pointer");
+    CUMF_TRY(cumf_update_factor(s->px, s->csr_col.as<int>(), s->csr_val.as<float>(), s->theta.as<float>(),
+                                s->x.as<float>(), s->lambda, s->solver, s->cg_iter, stream));
+    s->launches += s->px->last_launches;
+    return CUMF_OK;
+}
+extern "C" int cumf_als_update_theta(cumf_als_solver* s, void* stream) {
+    CUMF_REQUIRE(s, "null pointer");
+    CUMF_TRY(cumf_update_factor(s->pt, s->csc_row.as<int>(), s->csc_val.as<float>(), s->x.as<float>(),
+                                s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream));
+    s->launches += s->pt->last_launches;
+    return CUMF_OK;
+}
+
+extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_sse, void* stream) {
+    CUMF_REQUIRE(s, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    double h[2] = {0.0, 0.0};
+    double* d = s->sse.as<double>();
+    CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
+    if (train_sse && s->train_cnt > 0) {
+        // pairs cooRowIndex[i] with csrColIndex[i], csrVal[i] (als.cu:979-980)
+        CUMF_TRY(launch_sse(s->csr_val.as<float>(), s->coo_row.as<int>(), s->csr_col.as<int>(), s->theta.as<float>(),
+                            s->x.as<float>(), s->train_cnt, s->f, d, s->partials.as<double>(), sse_partial_capacity(), st));
+        s->launches += 2;
+    }
+    if (test_sse && s->test_cnt > 0) {
+        CUMF_TRY(launch_sse(s->test_val.as<float>(), s->test_row.as<int>(), s->test_col.as<int>(), s->theta.as<float>(),
+                            s->x.as<float>(), s->test_cnt, s->f, d + 1, s->partials.as<double>(), sse_partial_capacity(), st));
+        s->launches += 2;
+    }
+    CUMF_CUDA_TRY(cudaMemcpyAsync(h, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (train_sse) *train_sse = h[0];
+    if (test_sse) *test_sse = h[1];
+    return CUMF_OK;
+}
+
+extern "C" int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, void* stream) {
+    CUMF_REQUIRE(s && iters >= 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<cudaEvent_t> ev(2 * (size_t)iters + 1);
+    for (auto& e : ev) CUMF_CUDA_TRY(cudaEventCreate(&e));
+    CUMF_CUDA_TRY(cudaEventRecord(ev[0], st));
+    int rc = CUMF_OK;
+    for (int it = 0; it < iters && rc == CUMF_OK; ++it) {
+        rc = cumf_als_update_x(s, stream);
+        if (rc == CUMF_OK && cudaEventRecord(ev[2 * it + 1], st) != cudaSuccess) rc = CUMF_ECUDA;
+        if (rc == CUMF_OK) rc = cumf_als_update_theta(s, stream);
+        if (rc == CUMF_OK && cudaEventRecord(ev[2 * it + 2], st) != cudaSuccess) rc = CUMF_ECUDA;
+    }
+    if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_last_error(std::string("cumf_als_iterate: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = CUMF_ECUDA;
+    }
+    if (rc == CUMF_OK) {
+        float total = 0.f;
+        for (int it = 0; it < iters; ++it) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, ev[2 * it], ev[2 * it + 1]);
+            cudaEventElapsedTime(&b, ev[2 * it + 1], ev[2 * it + 2]);
+            s->ms_x += a; s->ms_theta += b; total += a + b;
+        }
+        s->iterations += iters;
+        if (ms_out) *ms_out = total;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+extern "C" int cumf_als_timers(cumf_als_solver* s, double* out6, int reset) {
+    CUMF_REQUIRE(s && out6, "null pointer");
+    out6[0] = s->ms_x; out6[1] = s->ms_theta;
+    out6[2] = plan_collect_kernel_ms(s->px);
+    out6[3] = plan_collect_kernel_ms(s->pt);
+    out6[4] = (double)s->launches; out6[5] = (double)s->iterations;
+    if (reset) {
+        s->ms_x = s->ms_theta = 0; s->launches = 0; s->iterations = 0;
+        s->px->kernel_ms_total = s->pt->kernel_ms_total = 0;
+    }
+    return CUMF_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// b1: doALS.  Same signature and observable behaviour as als.cu:662-1035: blocking,
+// host pointers in, factors written back, last test RMSE returned, progress on stdout
+// in the line formats the reference's scripts parse (print-test-result.sh:8-12).
+// On an unrecoverable error it prints and exits like the cudacall macro (als.h:628-640).
+// ---------------------------------------------------------------------------------
+[[noreturn]] static void die(const char* where) {
+    fprintf(stderr, "cumf_als_b200 error in %s: %s\n", where, cumf_last_error());
+    cudaDeviceReset();
+    exit(EXIT_FAILURE);
+}
+
+static double wall_seconds() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
+            const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
+            const int* cooRowIndexHostPtr, float* thetaTHost, float* XTHost, const int* cooRowIndexTestHostPtr,
+            const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, const int m, const int n, const int f,
+            const long nnz, const long nnz_test, const float lambda, const int ITERS, const int X_BATCH,
+            const int THETA_BATCH, const int DEVICEID) {
+    const bool quiet = env_long("CUMF_QUIET", 0) != 0;
+    const bool debug = env_long("CUMF_DEBUG", 0) != 0;
+    const int solver = env_choice("CUMF_SOLVER", "cg", CUMF_SOLVER_CG, "lu", CUMF_SOLVER_LU, nullptr, 0, CUMF_SOLVER_CG);
+    const int path = env_choice("CUMF_PATH", "auto", CUMF_PATH_AUTO, "simt", CUMF_PATH_SIMT, "tc", CUMF_PATH_TC, CUMF_PATH_AUTO);
+    (void)X_BATCH; (void)THETA_BATCH;   // advisory: nothing is batched to fit a 12 GB card any more
+    if (!quiet) {
+        printf("*******parameters: m: %d, n:  %d, f: %d, nnz: %ld \n", m, n, f, nnz);
+        printf("*******B200 path: solver %s, kernels %s; uploading CSR/CSC/COO once (resident)...\n",
+               solver == CUMF_SOLVER_CG ? "CG" : "LU(cuBLAS oracle)",
+               path == CUMF_PATH_SIMT ? "simt" : (path == CUMF_PATH_TC ? "tcgen05" : "auto"));
+    }
+    cumf_als_solver* s = nullptr;
+    if (cumf_als_create(&s, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
+                        cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
+                        cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, 0, m, 0, n,
+                        DEVICEID, solver, path) != CUMF_OK)
+        die("cumf_als_create");
+    if (cumf_als_set_factors(s, thetaTHost, XTHost) != CUMF_OK) die("cumf_als_set_factors");
+    if (!quiet) printf("*******start iterations...\n");
+    float final_rmse = 0.f;
+    for (int iter = 0; iter < ITERS; ++iter) {
+        double t0 = wall_seconds();
+        if (debug) printf("---------------------------ALS iteration %d, update X.----------------------------------\n", iter);
+        if (cumf_als_update_x(s, nullptr) != CUMF_OK) die("update X");
+        if (debug) {
+            cudaDeviceSynchronize();
+            if (solver == CUMF_SOLVER_CG) printf("\tCG solver with fp32.\n");
+            printf("update X run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, m, f);
+            t0 = wall_seconds();
+            printf("---------------------------------- ALS iteration %d, update theta ----------------------------------\n", iter);
+        }
+        if (cumf_als_update_theta(s, nullptr) != CUMF_OK) die("update theta");
+        if (debug) {
+            cudaDeviceSynchronize();
+            if (solver == CUMF_SOLVER_CG) printf("\tCG solver with fp32.\n");
+            printf("update theta run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, n, f);
+            printf("Calculate RMSE.\n");
+        }
+        double tr = 0.0, te = 0.0;
+        if (cumf_als_sse(s, cooRowIndexHostPtr ? &tr : nullptr, &te, nullptr) != CUMF_OK) die("RMSE");
+        const float rmse_train = sqrtf((float)tr / (float)nnz);          // als.cu:991
+        final_rmse = sqrtf((float)te / (float)nnz_test);                  // als.cu:1018
+        if (!quiet) {
+            printf("--------- Train RMSE in iter %d: %f\n", iter, rmse_train);
+            printf("--------- Test RMSE in iter %d: %f\n", iter, final_rmse);
+        }
+    }
+    if (cumf_als_get_factors(s, thetaTHost, XTHost) != CUMF_OK) die("cumf_als_get_factors");   // als.cu:1024-1025
+    cumf_als_destroy(s);
+    // like the reference, do NOT cudaDeviceReset here: the caller owns the context (als.cu:1031-1033)
+    return final_rmse;
+}
+
+extern "C" float cumf_doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
+                            const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                            const int* cooRowIndexHostPtr, float* thetaTHost, float* XTHost,
+                            const int* cooRowIndexTestHostPtr, const int* cooColIndexTestHostPtr,
+                            const float* cooValHostTestPtr, const int m, const int n, const int f, const long nnz,
+                            const long nnz_test, const float lambda, const int ITERS, const int X_BATCH,
+                            const int THETA_BATCH, const int DEVICEID) {
+    return doALS(csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr, cscColIndexHostPtr,
+                 cscValHostPtr, cooRowIndexHostPtr, thetaTHost, XTHost, cooRowIndexTestHostPtr, cooColIndexTestHostPtr,
+                 cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, ITERS, X_BATCH, THETA_BATCH, DEVICEID);
+}

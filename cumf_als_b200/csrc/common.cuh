@@ -1,0 +1,110 @@
+// common.cuh -- shared declarations of the B200 ALS hot path (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/cumf_als.h"
+
+namespace cumf {
+
+// ---------------------------------------------------------------------------
+// error plumbing: C-ABI functions return codes, doALS mirrors the reference's
+// print-and-exit convention (als.h:628-665).
+// ---------------------------------------------------------------------------
+void set_last_error(const std::string& msg);
+
+#define CUMF_CUDA_TRY(call)                                                                        \
+    do {                                                                                           \
+        cudaError_t err__ = (call);                                                                \
+        if (err__ != cudaSuccess) {                                                                \
+            ::cumf::set_last_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + \
+                                   cudaGetErrorString(err__));                                     \
+            return CUMF_ECUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+#define CUMF_TRY(call)                      \
+    do {                                    \
+        int rc__ = (call);                  \
+        if (rc__ != CUMF_OK) return rc__;   \
+    } while (0)
+
+#define CUMF_REQUIRE(cond, msg)                                   \
+    do {                                                          \
+        if (!(cond)) {                                            \
+            ::cumf::set_last_error(std::string("invalid argument: ") + (msg)); \
+            return CUMF_EINVAL;                                   \
+        }                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Work decomposition of one half-step.
+//   A "chunk" is a contiguous run of one row's ratings.  Rows longer than the
+//   split threshold are cut into equal chunks whose partial Grams are summed
+//   in a fixed order afterwards (deterministic split-K), so a 200k-rating
+//   movie does not serialise one CTA at the tail of the kernel.
+// ---------------------------------------------------------------------------
+struct Chunk {
+    int row;        // absolute row index
+    int begin;      // first rating (absolute offset into colidx/val; < 2^31 per shard)
+    int end;        // one past the last rating
+    int slot;       // -1: sole chunk of its row (written straight to the output);
+                    // >= 0: index of the partial [A|b] slot in the split scratch
+};
+
+struct SplitRow {
+    int row;        // absolute row index
+    int first_slot; // first partial slot
+    int count;      // number of partials
+    int nnz;        // ratings in the whole row (for the lambda*n_u term)
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Launch helpers implemented in the .cu files -------------------------------------
+// SIMT Gram (+RHS) over chunk range [c0,c1): direct rows go to tt/rhs at
+// (row - out_row_base), split chunks to scratchA/scratchB[slot].
+int launch_gram_simt(const Chunk* d_chunks, int c0, int c1, const int* d_colidx, const float* d_val,
+                     const float* d_factor, int f, float lambda, int out_row_base, float* d_tt,
+                     float* d_rhs, float* d_scratchA, float* d_scratchB, cudaStream_t st);
+// Sum split-row partials in slot order, add lambda*n_u, write to tt/rhs.
+// compact != 0: split row number i (index into d_rows) is written to slot i of tt/rhs;
+// otherwise to slot (row - out_row_base).
+int launch_split_reduce(const SplitRow* d_rows, int r0, int r1, int f, float lambda, int compact,
+                        int out_row_base, float* d_tt, float* d_rhs, const float* d_scratchA,
+                        const float* d_scratchB, cudaStream_t st);
+// Batched CG, one CTA per system, A row held in registers.
+// d_sys_rows (optional): system s reads/writes x at row d_sys_rows[s].row of d_x instead of row s
+// (used for the compact batch of split rows).
+int launch_cg(const float* d_A, float* d_x, const float* d_b, int batch, int f, float cg_iter,
+              const SplitRow* d_sys_rows, cudaStream_t st);
+// cuBLAS batched LU oracle.
+int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t st);
+// RMSE partial sums.
+int launch_sse(const float* d_val, const int* d_row, const int* d_col, const float* d_thetaT,
+               const float* d_XT, long count, int f, double* d_sse_out, double* d_partials,
+               int partial_capacity, cudaStream_t st);
+int sse_partial_capacity();
+
+// Fused tcgen05 path (gram_tc.cu).  Returns CUMF_EUNSUPPORTED when f is not handled.
+bool tc_path_supports(int f);
+struct TcWork;  // opaque per-plan state of the fused kernel
+int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const std::vector<SplitRow>& splits,
+                   int rows_total, int f);
+void tc_plan_destroy(TcWork* w);
+int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,
+                     const int* d_colidx, const float* d_val, const float* d_factor, float* d_out,
+                     int f, float lambda, float cg_iter, float* d_scratchA, float* d_scratchB,
+                     cudaStream_t st, int* launches);
+
+}  // namespace cumf

@@ -1,0 +1,175 @@
+/*
+ * include/cumf_als.h -- C ABI of the B200-native ALS factor-update path.
+ *
+ * This is the drop-in boundary for cuMF/cumf_als's one hot path (per-row Gram
+ * formation + batched f x f solve).  Plain pointers and sizes only; no torch,
+ * no C++ types.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference tree).  The library is
+ * cumf_als_b200/libcumf_als_b200.so; it additionally exports the C++-mangled
+ * symbol `doALS` (_Z5doALSPKiS0_PKfS0_S0_S2_S0_PfS3_S0_S0_S2_iiillfiiii) so
+ * the reference's unmodified main.cpp and tensorflow/als_tf.cc link against it
+ * (als.h:676-681, als_tf.cc:33-38), and the four loaders of host_utilities.h.
+ *
+ * Conventions
+ *   - "d_" arguments are DEVICE pointers on the current CUDA device, "h_"/
+ *     "...HostPtr" arguments are HOST pointers.
+ *   - Factor matrices are row-major [rows][f] fp32 (thetaT: n x f, XT: m x f),
+ *     exactly the reference's layout (als.cu:805, 1024-1025).
+ *   - Functions returning int return CUMF_OK (0) or a negative CUMF_E* code and
+ *     leave a message retrievable with cumf_last_error().  cumf_doALS mirrors
+ *     the reference instead: on a CUDA error it prints and exit(EXIT_FAILURE)s
+ *     (als.h:628-665).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - There is NO CPU fallback anywhere behind this header.
+ */
+#ifndef CUMF_ALS_H_
+#define CUMF_ALS_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUMF_OK 0
+#define CUMF_EINVAL (-1)   /* bad argument (f odd / f%10 != 0 where required, null pointer, ...) */
+#define CUMF_ECUDA (-2)    /* a CUDA runtime / cuBLAS call failed                                   */
+#define CUMF_ENOGPU (-3)   /* no sm_100 device visible                                              */
+#define CUMF_EUNSUPPORTED (-4)
+
+/* solver selection: the reference chooses at compile time (`#define USE_CG`, als.cu:28) */
+#define CUMF_SOLVER_CG 0   /* batched CG, CG_ITER = 6 (als.cu:32), break at rsnew < 1e-4 (cg.cu:31,195) */
+#define CUMF_SOLVER_LU 1   /* cuBLAS getrf/getrsBatched without pivoting (als.cu:58-189): oracle mode   */
+
+/* kernel family selection for the Gram + solve half-step */
+#define CUMF_PATH_AUTO 0   /* fused tcgen05 kernel where it applies, else SIMT                       */
+#define CUMF_PATH_SIMT 1   /* exact-fp32 FFMA Gram (materialised A) + register-resident CG kernel    */
+#define CUMF_PATH_TC   2   /* fused TMA-gather + tcgen05 split-fp16 Gram + in-register CG            */
+
+const char* cumf_last_error(void);
+int cumf_version(void);
+
+/* ---- b1: doALS -------------------------------------------------------------
+ * Replaces  float doALS(...)  als.h:676-681 / als.cu:662-1035 (same argument
+ * order and meaning).  All pointers are host memory owned by the caller;
+ * thetaTHost (n*f) and XTHost (m*f) are in/out (initial guess in -- CG warm
+ * starts from XTHost, main.cpp:76-78 -- final factors out).  Returns the last
+ * iteration's test RMSE (als.cu:1018, 1034).  X_BATCH / THETA_BATCH are
+ * accepted and advisory: results do not depend on them.
+ * Environment knobs (all optional): CUMF_SOLVER=cg|lu, CUMF_PATH=auto|simt|tc,
+ * CUMF_DEBUG=1 (prints the reference's -DDEBUG timing lines, als.cu:821-963),
+ * CUMF_QUIET=1 (no stdout).                                                  */
+float cumf_doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
+                 const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                 const int* cooRowIndexHostPtr, float* thetaTHost, float* XTHost,
+                 const int* cooRowIndexTestHostPtr, const int* cooColIndexTestHostPtr,
+                 const float* cooValHostTestPtr, const int m, const int n, const int f, const long nnz,
+                 const long nnz_test, const float lambda, const int ITERS, const int X_BATCH,
+                 const int THETA_BATCH, const int DEVICEID);
+
+/* ---- b2: the .bin loaders of the CLI ---------------------------------------
+ * Replace host_utilities.h:31-40 / host_utilities.cpp:19-98 (same file format:
+ * headerless little-endian int32 / float32).  Return 0, or -1 if a file cannot
+ * be opened or is short (the reference prints "Unable to open file!" and
+ * carries on with garbage, host_utilities.cpp:27-31; the C++-linkage symbols
+ * with the reference's names keep that void signature).                      */
+int cumf_load_csr_bin(const char* dataFile, const char* rowFile, const char* colFile, float* data,
+                      int* row, int* col, int m, long nnz);
+int cumf_load_csc_bin(const char* dataFile, const char* rowFile, const char* colFile, float* data,
+                      int* row, int* col, int n, long nnz);
+int cumf_load_coo_row_bin(const char* rowFile, int* row, long nnz);
+int cumf_load_coo_bin(const char* dataFile, const char* rowFile, const char* colFile, float* data,
+                      int* row, int* col, long nnz);
+
+/* ---- b4: stage-level seams (device pointers) --------------------------------
+ * cumf_gram replaces the launches
+ *   get_hermitian100 / get_hermitianT10 <<<batch_size, ...>>>(batch_offset, tt,
+ *       rowPtr, colIdx, lambda, m, F, factor)          als.cu:445-447, 576-578, 804, 816
+ * and (when d_rhs != NULL) the RHS pass cusparseScsrmm2 + cublasSgeam als.cu:750-757:
+ *   d_tt  [batch_size][f][f] full symmetric fp32,  A_u = sum theta theta^T + lambda*nnz_u*I
+ *   d_rhs [batch_size][f]   b_u = sum val * theta   (rows batch_offset .. +batch_size)
+ * d_rowptr has m+1 entries, indices are absolute (not rebased).  f must be even
+ * and a multiple of 10 (main.cpp:33-36), 10 <= f <= 200.                      */
+int cumf_gram(int batch_offset, int batch_size, float* d_tt, float* d_rhs, const int* d_rowptr,
+              const int* d_colidx, const float* d_val, float lambda, int m, int f,
+              const float* d_factor, int path, void* stream);
+
+/* Replaces  void updateXWithCGHost(float* A, float* x, float* b, const int
+ * batchSize, const int f, const float cgIter)  cg.h:30 / cg.cu:682-686.
+ * x is in/out (warm start, cg.cu:48).                                         */
+int cumf_cg(const float* d_A, float* d_x, const float* d_b, int batchSize, int f, float cgIter,
+            void* stream);
+
+/* Replaces updateX / updateTheta with the LU solver, als.cu:58-122 / 124-189
+ * (cublasSgetrfBatched + cublasSgetrsBatched, NULL pivot).  d_A is overwritten
+ * with its LU factors, d_b with the solution, which is also copied to d_x.    */
+int cumf_lu(float* d_A, float* d_x, float* d_b, int batchSize, int f, void* stream);
+
+/* Replaces the RMSE kernel + cublasSasum + sqrt, als.cu:191-219, 979-991,
+ * 1006-1019.  drop_tail != 0 reproduces the test-set launch (nnz_test-1)/256
+ * blocks (als.cu:1006): only the first 256*((count-1)/256) samples are summed
+ * while the divisor stays `count`.  *sse_out (optional) receives the sum of
+ * squared errors in double; returns via *rmse_out = sqrtf(sse/count).         */
+int cumf_rmse(const float* d_val, const int* d_row, const int* d_col, const float* d_thetaT,
+              const float* d_XT, long count, int f, int drop_tail, float* rmse_out, double* sse_out,
+              void* stream);
+
+/* ---- the hot path as one call: a half-step plan -------------------------------
+ * A plan holds the work decomposition (row chunks, split-row partial slots,
+ * workspace) for updating rows [row_begin,row_end) of one factor from a CSR-like
+ * structure.  h_rowptr (rows+1 ints) is read on the host once; the plan keeps a
+ * device copy of what it needs.  One plan per side (CSR for X, CSC for theta).  */
+typedef struct cumf_plan cumf_plan;
+int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end,
+                     int f, int path);
+int cumf_plan_destroy(cumf_plan* plan);
+/* number of kernels launched by the last cumf_update_factor on this plan */
+int cumf_plan_last_launches(const cumf_plan* plan);
+
+/* One half-step of ALS for the plan's rows: for every row u in the plan
+ *   A_u, b_u  as in cumf_gram;  d_out[u] <- solve(A_u, b_u, x0 = d_out[u])
+ * = the body of the iteration loop als.cu:727-853 (X) / 858-961 (theta).
+ * d_colidx/d_val: device pointers to the first rating of row_begin (i.e. the
+ * CSR index/value arrays offset by h_rowptr[row_begin]; the plan keeps the row
+ * structure); d_factor: the opposing factor [*, f]; d_out: the factor being
+ * updated, full [rows][f] array (in/out, rows addressed absolutely).          */
+int cumf_update_factor(cumf_plan* plan, const int* d_colidx, const float* d_val,
+                       const float* d_factor, float* d_out, float lambda, int solver, float cgIter,
+                       void* stream);
+
+/* ---- resident solver handle (what cumf_doALS is built from) -------------------
+ * Uploads CSR/CSC/COO once (the reference re-uploads CSR every iteration,
+ * als.cu:734-739) and keeps the factors on the device.  Row ranges select the
+ * shard this process updates (one process per GPU: rank g owns X rows
+ * [x_begin,x_end) and theta rows [t_begin,t_end)); pass 0,m / 0,n for a single
+ * GPU.  Only the owned CSR/CSC slices are uploaded (64-bit offsets inside).   */
+typedef struct cumf_als_solver cumf_als_solver;
+int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                    const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                    const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                    const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                    const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                    long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                    int device, int solver, int path);
+int cumf_als_destroy(cumf_als_solver* s);
+int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost, const float* XTHost);
+int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float* XTHost);
+/* device pointers of the resident full factor replicas (for NCCL all-gather by the caller) */
+float* cumf_als_theta_ptr(cumf_als_solver* s);
+float* cumf_als_x_ptr(cumf_als_solver* s);
+int cumf_als_update_x(cumf_als_solver* s, void* stream);       /* als.cu:727-853 for the owned rows  */
+int cumf_als_update_theta(cumf_als_solver* s, void* stream);   /* als.cu:858-961 for the owned rows  */
+/* sum of squared errors over this shard's share of the train / test samples
+ * (all of them on a single GPU); the caller all-reduces and takes
+ * sqrt(sse/count) (als.cu:991, 1018).                                          */
+int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_sse, void* stream);
+/* `iters` full iterations (X step then theta step), device-timed with CUDA
+ * events on `stream`; *ms_out = elapsed milliseconds for the iters.            */
+int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, void* stream);
+/* per-phase device time (ms) accumulated since the last call with reset != 0:
+ * out[0] = X step, out[1] = theta step, out[2] = dominant Gram kernel X side,
+ * out[3] = dominant Gram kernel theta side, out[4] = kernel launches, out[5] = iterations */
+int cumf_als_timers(cumf_als_solver* s, double* out6, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUMF_ALS_H_ */
