@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- ALS iterations/sec on the BASELINE.json workload (Netflix-shaped, f=100).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload netflix]
+
+One "step" = one ALS iteration = update-X half-step + update-theta half-step (Gram + RHS
+formation and the batched CG solve for every row and every column), the span the reference's
+`update X run` + `update theta run` timers cover (als.cu:730-850, 858-963).
+
+Prints ONE JSON line (rank 0):
+  value      iterations/sec with CSR/CSC/factors already resident in HBM, timed with CUDA events
+             (max over ranks), W warm-up iterations first; inputs (theta 192 MB, ratings 1.2 GB
+             per orientation) exceed the 126 MB L2, so no flush is needed between iterations.
+  e2e        the same metric through the reference-facing call doALS(host pointers): uploads,
+             K iterations, per-iteration train/test RMSE, factor download -- wall clock / K.
+  roofline   Gram(+fused solve) kernel: algorithmic bytes / CUDA-event kernel time.
+  cpu_baseline  the CPU oracle (oracle/als_cpu.c port) timed on a bounded row sample, scaled.
+`--impl reference` runs the UNMODIFIED reference (oracle/_ref, its Kepler-era kernels recompiled
+for sm_100a + cuBLAS/cuSPARSE) through its own doALS on the same inputs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: m, n, nnz, nnz_test, f, lambda, seed, reference (X_BATCH, THETA_BATCH) (test_als.sh:5-28)
+    "netflix": dict(m=17770, n=480189, nnz=99072112, nnz_test=1408395, f=100, lam=0.048, seed=1002, ref_batches=(1, 3)),
+    "netflix_f200": dict(m=17770, n=480189, nnz=99072112, nnz_test=1408395, f=200, lam=0.048, seed=1002, ref_batches=(1, 10)),
+    "ml10m": dict(m=71567, n=65133, nnz=9000048, nnz_test=1000006, f=10, lam=0.05, seed=1001, ref_batches=(1, 1)),
+    "tiny": dict(m=2000, n=5000, nnz=400000, nnz_test=20000, f=100, lam=0.048, seed=1, ref_batches=(1, 1)),
+}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def make_inputs(w, scale: float, device: str):
+    from cumf_als_b200.data import init_factors, synth_ratings
+    m, n = w["m"], w["n"]
+    nnz, nnz_test = int(w["nnz"] * scale), max(1024, int(w["nnz_test"] * scale))
+    nnz = max(nnz, m + n)
+    r = synth_ratings(m, n, nnz, nnz_test, seed=w["seed"], device=device, alpha_row=0.5, alpha_col=0.6)
+    theta0, X0 = init_factors(m, n, w["f"], seed=w["seed"])
+    return r, theta0, X0
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.tmp = gpu_index, None, None
+
+    def __enter__(self):
+        try:
+            self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.tmp is None:
+            return out
+        try:
+            self.tmp.flush()
+            rows = [l.split(",") for l in open(self.tmp.name).read().strip().splitlines() if l.strip()]
+            os.unlink(self.tmp.name)
+        except Exception:
+            return out
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        if not sm:
+            return out
+        out["samples"] = len(sm)
+        out["sm_mhz"] = float(np.median(sm))
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows if len(r) >= 9):
+                out["reasons"].append(nm)
+        return out
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def gram_bytes(rows, nnz, f, fused: bool):
+    """Algorithmic bytes of one half-step's Gram formation."""
+    if fused:
+        return nnz * (4 * f + 4 + 4) + (rows + 1) * 4 + 2 * rows * f * 4
+    return nnz * (4 * f + 4) + (rows + 1) * 4 + rows * f * f * 4
+
+
+def cpu_baseline(r, theta0, X0, w, budget_s: float = 15.0):
+    """CPU oracle on a bounded sample of rows of both half-steps, scaled by rating share."""
+    from oracle import oracle as O
+    f, lam = w["f"], w["lam"]
+    cores = os.cpu_count() or 1
+    est = {}
+    sample_desc = []
+    for side, (ptr, idx, val, fac, out, rows) in {
+        "x": (r.csr_indptr, r.csr_indices, r.csr_data, theta0, X0.copy(), r.m),
+        "theta": (r.csc_indptr, r.csc_indices, r.csc_data, np.ascontiguousarray(
+            np.random.default_rng(0).random((r.m, f), dtype=np.float32) * 0.2), theta0.copy(), r.n),
+    }.items():
+        # grow the sample until it costs ~budget/2 seconds
+        share_rows = max(8, rows // 2000)
+        t, k = 0.0, 0
+        while True:
+            lo = (rows // 3)
+            hi = min(rows, lo + share_rows)
+            t0 = time.perf_counter()
+            O.half_step(ptr, idx, val, fac, out, f, lam, 0, 6.0, lo, hi)
+            t = time.perf_counter() - t0
+            k = int(ptr[hi] - ptr[lo])
+            if t > budget_s / 4 or hi - lo >= rows - lo:
+                break
+            share_rows = int(share_rows * max(2.0, min(16.0, (budget_s / 2) / max(t, 1e-3))))
+        est[side] = t * (int(ptr[-1]) / max(k, 1))
+        sample_desc.append(f"{side}: rows [{lo},{hi}) = {k} ratings in {t:.2f} s")
+    per_iter = est["x"] + est["theta"]
+    return {"value": 1.0 / per_iter, "unit": "iterations/s", "cores": cores, "kind": "port",
+            "sample": "oracle/als_cpu.c (OpenMP) on " + "; ".join(sample_desc) + "; scaled by rating share"}
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+    import cumf_als_b200 as c
+    from cumf_als_b200.data import nnz_balanced_ranges
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    r, theta0, X0 = make_inputs(w, args.scale, "cuda")
+    f, lam = w["f"], w["lam"]
+    path = {"auto": c.PATH_AUTO, "simt": c.PATH_SIMT, "tc": c.PATH_TC}[args.path]
+    os.environ["CUMF_TIME_KERNELS"] = "1"
+
+    if world == 1:
+        xr, tr_ = (0, r.m), (0, r.n)
+    else:
+        xr = nnz_balanced_ranges(r.csr_indptr, world)[rank]
+        tr_ = nnz_balanced_ranges(r.csc_indptr, world)[rank]
+    solver = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
+                         r.test_row, r.test_col, r.test_val, r.m, r.n, f, lam, x_range=xr, theta_range=tr_,
+                         device=local_rank, path=path)
+    solver.set_factors(theta0, X0)
+
+    if world > 1:
+        from cumf_als_b200.dist import ShardedAls
+        sharded = ShardedAls(solver, r, world, rank)
+        step = sharded.iterate
+    else:
+        step = lambda k: solver.iterate(k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step(args.warmup)
+    solver.timers(reset=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ms = step(args.steps)
+        barrier()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    tm = solver.timers()
+    train_rmse, test_rmse = (sharded.rmse() if world > 1 else solver.rmse())
+    iters_per_s = args.steps / (ms / 1e3)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        fused = args.path != "simt" and _tc_active(c, f)
+        xs, ts = xr[1] - xr[0], tr_[1] - tr_[0]
+        nnz_x = int(r.csr_indptr[xr[1]] - r.csr_indptr[xr[0]])
+        nnz_t = int(r.csc_indptr[tr_[1]] - r.csc_indptr[tr_[0]])
+        gb = (gram_bytes(xs, nnz_x, f, fused) + gram_bytes(ts, nnz_t, f, fused)) / 1e9   # per iteration, this rank
+        gram_ms = (tm["gram_x_ms"] + tm["gram_theta_ms"]) / max(tm["iterations"], 1)
+        achieved = gb / (gram_ms / 1e3) if gram_ms > 0 else None
+        line = {
+            "metric": "ALS iterations/sec (Netflix-shaped f=100, CG solver)", "value": iters_per_s,
+            "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
+                       "lambda": lam, "solver": "cg6", "path": "tcgen05-fused" if fused else "simt-unfused",
+                       "sharding": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, all-gather",
+                       "l2": "inputs exceed L2 (theta 192 MB, ratings 1.2 GB per orientation): no flush"},
+            "x_ms": tm["x_ms"] / max(tm["iterations"], 1), "theta_ms": tm["theta_ms"] / max(tm["iterations"], 1),
+            "train_rmse": train_rmse, "test_rmse": test_rmse,
+            "gpu_launches": int(tm["launches"]),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "gram (+rhs" + (" + fused CG)" if fused else ")") + " X side + theta side",
+                         "bytes_per_iteration_gb": gb, "kernel_ms_per_iteration": gram_ms,
+                         "gram_x_ms": tm["gram_x_ms"] / max(tm["iterations"], 1),
+                         "gram_theta_ms": tm["gram_theta_ms"] / max(tm["iterations"], 1),
+                         "formula": "B_gram_fused" if fused else "B_gram (materialised A)", "peak_source": peak_src},
+        }
+    solver.close()
+
+    # e2e: the reference-facing call with host buffers (rank 0 of a single-GPU run; under
+    # torchrun every rank would repeat the same whole-job call, so it is only timed at N=1)
+    if rank == 0 and world == 1 and not args.no_e2e:
+        os.environ["CUMF_QUIET"] = "1"
+        os.environ["CUMF_PATH"] = args.path
+        th, X = theta0.copy(), X0.copy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fin = c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz, r.nnz_test, lam,
+                       args.steps, 1, 1, local_rank)
+        wall = time.perf_counter() - t0
+        h2d = (r.csr_indices.nbytes + r.csr_data.nbytes + r.csc_indices.nbytes + r.csc_data.nbytes + r.coo_row.nbytes +
+               r.test_row.nbytes + r.test_col.nbytes + r.test_val.nbytes + th.nbytes + X.nbytes)
+        line["e2e"] = {"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": h2d // args.steps,
+                       "d2h_bytes_per_step": (th.nbytes + X.nbytes) // args.steps, "wall_s": wall,
+                       "final_test_rmse": fin,
+                       "what": "doALS(host pointers, ITERS=steps): upload + iterations + per-iteration RMSE + download"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(r, theta0, X0, w)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _tc_active(c, f):
+    try:
+        import ctypes
+        h = ctypes.c_void_p()
+        rp = np.array([0, 1], np.int32)
+        rc = c.api.load_library().cumf_plan_create(ctypes.byref(h), rp.ctypes.data_as(ctypes.c_void_p), 1, 0, 1, f, c.PATH_TC)
+        if rc == 0:
+            c.api.load_library().cumf_plan_destroy(h)
+        return rc == 0
+    except Exception:
+        return False
+
+
+def run_reference(args, w):
+    """The unmodified reference (oracle/_ref) through its own doALS, rank 0 only."""
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as O
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    torch.cuda.set_device(local_rank)
+    r, theta0, X0 = make_inputs(w, args.scale, "cuda")
+    f, lam = w["f"], w["lam"]
+    xb, tb = w["ref_batches"]
+    variant = args.ref_variant
+    if not O.ref_available(variant):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_als_%s.so not built" % variant}))
+        return
+    from make_golden import CaptureStdout
+    if args.warmup > 0:   # context / cuBLAS / cuSPARSE initialisation outside the timed call
+        with CaptureStdout():
+            O.ref_do_als(r, theta0.copy(), X0.copy(), f, lam, 1, xb, tb, variant, local_rank)
+    th, X = theta0.copy(), X0.copy()
+    iters = args.steps
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        with CaptureStdout() as cap:
+            fin = O.ref_do_als(r, th, X, f, lam, iters, xb, tb, variant, local_rank)
+        wall = time.perf_counter() - t0
+    xs = [float(v) for v in re.findall(r"^update X run ([0-9.]+) seconds", cap.text, flags=re.M)]
+    ts = [float(v) for v in re.findall(r"^update theta run ([0-9.]+) seconds", cap.text, flags=re.M)]
+    kx = [float(v) for v in re.findall(r"update X kernel run ([0-9.]+) seconds", cap.text)]
+    kt = [float(v) for v in re.findall(r"update Theta kernel run ([0-9.]+) seconds", cap.text)]
+    sv = [float(v) for v in re.findall(r"solver run seconds: ([0-9.]+)", cap.text)]
+    als_s = sum(xs) + sum(ts)
+    value = iters / als_s if als_s > 0 else iters / wall
+    peak, peak_src = measured_peaks()
+    gb = (gram_bytes(r.m, r.nnz, f, False) + gram_bytes(r.n, r.nnz, f, False)) / 1e9
+    gram_s = (sum(kx) + sum(kt)) / iters if kx else None
+    line = {
+        "impl": "reference", "metric": "ALS iterations/sec (Netflix-shaped f=100, CG solver)", "value": value,
+        "unit": "iterations/s", "n_gpus": 1, "steps": iters, "warmup": 0, "ms_per_step": 1e3 * als_s / iters,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
+                   "lambda": lam, "solver": "cg6" if variant == "cg" else "cublas-lu", "X_BATCH": xb, "THETA_BATCH": tb,
+                   "what": "unmodified reference sources (oracle/_ref), Kepler-era kernels recompiled for sm_100a; value = "
+                           "iterations / sum of its own `update X run`+`update theta run` timers (als.cu:850, 963)"},
+        "e2e": {"value": iters / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "wall_s": wall},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "reference",
+                         "sample": f"reference doALS ({variant}) single host thread driving GPU kernels, {iters} iterations"},
+        "final_test_rmse": fin, "clocks": clocks.summary(), "gpu_launches": 0,
+        "roofline": {"bound": "hbm", "achieved": (gb / gram_s) if gram_s else None, "peak": peak, "unit": "GB/s",
+                     "frac": (gb / gram_s / peak) if gram_s else None, "traffic": None,
+                     "kernel": "get_hermitian100 X+theta (reference timers)", "peak_source": peak_src},
+        "ref_timers": {"update_x_s": sum(xs) / max(len(xs), 1), "update_theta_s": sum(ts) / max(len(ts), 1),
+                       "gram_kernels_s_per_iter": gram_s, "solver_s_per_iter": sum(sv) / iters if sv else None},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="netflix", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink nnz (debug only; 1.0 = the BASELINE workload)")
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--ref-variant", default="cg", choices=["cg", "lu"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,10 +35,12 @@ obj "$REF/host_utilities.cpp"  "$TMP/hu.o" &
 obj "$REF/main.cpp"            "$TMP/main.o" &
 "$NVCC" -O3 -std=c++14 -Xcompiler -fPIC -gencode arch=compute_100a,code=sm_100a -w \
     -c "$HERE/ref_shim/csrmm2_shim.cu" -o "$TMP/shim.o" &
-obj "$REF/als.cu"              "$TMP/als_cg.o" &
+# als.cu is compiled through ref_shim/ref_hooks.cu, which #includes it verbatim from where it
+# lies and appends extern "C" launchers for the stage-level golden vectors.
+obj "$HERE/ref_shim/ref_hooks.cu" "$TMP/als_cg.o" -DREF_ALS_SOURCE="\"$REF/als.cu\"" &
 # LU oracle: als.cu with its line-28 `#define USE_CG` commented out, nothing else.
 sed 's|^#define USE_CG|//#define USE_CG|' "$REF/als.cu" > "$TMP/als_lu.cu"
-obj "$TMP/als_lu.cu"           "$TMP/als_lu.o" &
+obj "$HERE/ref_shim/ref_hooks.cu" "$TMP/als_lu.o" -DREF_ALS_SOURCE="\"$TMP/als_lu.cu\"" &
 wait
 LIBS=(-lcublas -lcusparse)
 for v in cg lu; do

@@ -1,0 +1,257 @@
+"""Parity tests proper: the CUDA path through the C ABI (ctypes -> libcumf_als_b200.so)
+against the oracle (CPU restatement), the golden vectors recorded from the reference, and
+-- when oracle/_ref travelled to the box -- the live reference library.  Run with -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+import cumf_als_b200 as c
+from conftest import golden, rel_fro
+from cumf_als_b200.data import Ratings, init_factors, synth_ratings
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # north_star: factors and per-iteration RMSE within 1e-4 relative (fp32)
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def run_gram(torch, rowptr, colidx, val, factor, f, lam, batch_offset=0, batch_size=None, path=c.PATH_SIMT):
+    m = rowptr.size - 1
+    bs = m - batch_offset if batch_size is None else batch_size
+    tt = torch.full((bs, f, f), float("nan"), dtype=torch.float32, device="cuda")
+    rhs = torch.full((bs, f), float("nan"), dtype=torch.float32, device="cuda")
+    c.gram(batch_offset, bs, tt, dev(torch, rowptr), dev(torch, colidx), lam, m, f, dev(torch, factor), rhs=rhs,
+           val=dev(torch, val), path=path)
+    torch.cuda.synchronize()
+    return tt.cpu().numpy(), rhs.cpu().numpy()
+
+
+def random_csr(rng, lengths, n):
+    rowptr = np.zeros(len(lengths) + 1, np.int32)
+    rowptr[1:] = np.cumsum(lengths)
+    cols = [np.sort(rng.choice(n, size=k, replace=False)) for k in lengths]
+    colidx = np.concatenate(cols + [np.zeros(0, np.int64)]).astype(np.int32)
+    val = rng.integers(1, 6, colidx.size).astype(np.float32)
+    return rowptr, colidx, val
+
+
+# ---- Gram + RHS -----------------------------------------------------------------------------
+@pytest.mark.parametrize("f", [10, 20, 50, 100, 130, 200])
+def test_gram_bit_exact_vs_oracle(cuda, f):
+    rng = np.random.default_rng(f)
+    lengths = [1, 2, 31, 32, 33, 64, 65, 0, 100, 7, 250, 3]     # ragged, empty, stage boundaries (KC = 32)
+    n = 400
+    rowptr, colidx, val = random_csr(rng, lengths, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    tt, rhs = run_gram(cuda, rowptr, colidx, val, factor, f, 0.05)
+    ref = O.gram(rowptr, colidx, factor, f, 0.05)
+    assert np.array_equal(tt, ref), f"max abs diff {np.abs(tt - ref).max()}"      # same FMA chain: bit-exact
+    assert np.array_equal(rhs, O.rhs(rowptr, colidx, val, factor, f))
+
+
+def test_gram_batch_window_and_rows_beyond_m(cuda):
+    rng = np.random.default_rng(5)
+    rowptr, colidx, val = random_csr(rng, [4, 9, 40, 2, 17, 33, 5], 90)
+    factor = rng.standard_normal((90, 20)).astype(np.float32)
+    full, _ = run_gram(cuda, rowptr, colidx, val, factor, 20, 0.1)
+    sub, _ = run_gram(cuda, rowptr, colidx, val, factor, 20, 0.1, batch_offset=2, batch_size=3)
+    assert np.array_equal(sub, full[2:5])
+    # a window hanging over the end only touches rows < m (als.cu:449-450)
+    over, _ = run_gram(cuda, rowptr, colidx, val, factor, 20, 0.1, batch_offset=5, batch_size=4)
+    assert np.array_equal(over[:2], full[5:7]) and np.isnan(over[2:]).all()
+
+
+def test_gram_split_rows_deterministic(cuda, monkeypatch):
+    """Rows longer than the split threshold are cut up and reduced in a fixed order."""
+    monkeypatch.setenv("CUMF_SPLIT_NNZ", "64")
+    rng = np.random.default_rng(6)
+    rowptr, colidx, val = random_csr(rng, [300, 64, 65, 1000, 5], 1200)
+    factor = (0.3 * rng.standard_normal((1200, 100))).astype(np.float32)
+    a, ra = run_gram(cuda, rowptr, colidx, val, factor, 100, 0.05)
+    b, rb = run_gram(cuda, rowptr, colidx, val, factor, 100, 0.05)
+    assert np.array_equal(a, b) and np.array_equal(ra, rb)          # run-to-run bit-exact
+    ref = O.gram(rowptr, colidx, factor, 100, 0.05)
+    assert rel_fro(a, ref) < 1e-6 and np.allclose(a, ref, rtol=1e-5, atol=1e-5)
+    assert np.array_equal(a[[1, 4]], ref[[1, 4]])                    # unsplit rows stay bit-exact
+    assert rel_fro(ra, O.rhs(rowptr, colidx, val, factor, 100)) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["gram_f100.npz", "gram_f20.npz", "gram_f200.npz"])
+def test_gram_vs_reference_golden(cuda, name):
+    g = golden(name)
+    f, lam = int(g["f"]), float(g["lam"])
+    tt, rhs = run_gram(cuda, g["rowptr"], g["colidx"], g["val"], g["factor"], f, lam)
+    assert np.array_equal(tt, g["tt"]), f"max abs diff {np.abs(tt - g['tt']).max()}"
+    assert np.allclose(rhs, g["rhs"], rtol=2e-5, atol=2e-5)
+
+
+# ---- solvers --------------------------------------------------------------------------------
+def spd_batch(rng, batch, f, k=None):
+    k = k or 3 * f
+    T = (0.3 * rng.standard_normal((batch, k, f))).astype(np.float32)
+    A = np.einsum("bki,bkj->bij", T, T).astype(np.float32) + 0.05 * k * np.eye(f, dtype=np.float32)
+    A = (A + A.transpose(0, 2, 1)) / 2
+    return A.astype(np.float32)
+
+
+@pytest.mark.parametrize("f", [10, 30, 100, 130, 200])
+def test_cg_vs_oracle(cuda, f):
+    rng = np.random.default_rng(100 + f)
+    batch = 37
+    A = spd_batch(rng, batch, f)
+    b = rng.standard_normal((batch, f)).astype(np.float32)
+    x0 = (0.1 * rng.standard_normal((batch, f))).astype(np.float32)
+    for it in (6.0, 1.0, 0.0, 50.0):
+        dA, dx, db = dev(cuda, A), dev(cuda, x0), dev(cuda, b)
+        c.cg(dA, dx, db, batch, f, it)
+        got = dx.cpu().numpy()
+        want = O.cg(A, x0, b, f, it)
+        assert rel_fro(got, want) < TOL, (f, it, rel_fro(got, want))
+    assert np.array_equal(dA.cpu().numpy(), A)   # A is read-only for the CG
+
+
+def test_cg_empty_row_gives_nan_like_reference(cuda):
+    # A = 0, b = 0 -> alpha = 0/0 (cg.cu:128): NaN stays confined to that system
+    f = 20
+    A = np.zeros((2, f, f), np.float32)
+    A[1] = np.eye(f)
+    b = np.zeros((2, f), np.float32)
+    b[1] = 1
+    dx = dev(cuda, np.zeros((2, f), np.float32))
+    c.cg(dev(cuda, A), dx, dev(cuda, b), 2, f, 6.0)
+    x = dx.cpu().numpy()
+    assert np.isnan(x[0]).all() and np.allclose(x[1], 1.0)
+
+
+@pytest.mark.parametrize("name", ["solve_f100.npz", "solve_f20.npz"])
+def test_solvers_vs_reference_golden(cuda, name):
+    g = golden(name)
+    f, batch = int(g["f"]), g["b"].shape[0]
+    for it in (6, 2):
+        dx = dev(cuda, g["x0"])
+        c.cg(dev(cuda, g["A"]), dx, dev(cuda, g["b"]), batch, f, float(it))
+        assert rel_fro(dx.cpu().numpy(), g[f"x_cg{it}"]) < TOL
+    dx = dev(cuda, np.zeros_like(g["b"]))
+    c.lu(dev(cuda, g["A"]), dx, dev(cuda, g["b"]), batch, f)
+    assert rel_fro(dx.cpu().numpy(), g["x_lu"]) < TOL
+
+
+# ---- RMSE -----------------------------------------------------------------------------------
+def test_rmse_vs_oracle_and_golden(cuda):
+    g = golden("rmse.npz")
+    f, cnt = int(g["f"]), g["val"].size
+    args = [dev(cuda, g[k]) for k in ("val", "row", "col", "thetaT", "XT")]
+    tr, sse = c.rmse(*args, cnt, f, drop_tail=False)
+    te, _ = c.rmse(*args, cnt, f, drop_tail=True)
+    assert tr == pytest.approx(float(g["rmse_train"]), rel=1e-5)
+    assert te == pytest.approx(float(g["rmse_test"]), rel=1e-5)
+    assert tr == pytest.approx(O.rmse(g["val"], g["row"], g["col"], g["thetaT"], g["XT"], f, False), rel=1e-5)
+    # the sample set is an integer path: 256*((count-1)/256) samples, bit-exact
+    e = g["val"] - np.einsum("ij,ij->i", g["thetaT"][g["col"]].astype(np.float64), g["XT"][g["row"]].astype(np.float64))
+    assert sse == pytest.approx(float((e ** 2).sum()), rel=1e-5)
+    _, sse_t = c.rmse(*args, cnt, f, drop_tail=True)
+    assert sse_t == pytest.approx(float((e[:256 * ((cnt - 1) // 256)] ** 2).sum()), rel=1e-5)
+
+
+# ---- the whole path: doALS ------------------------------------------------------------------
+def run_doals(r, theta0, f, lam, iters, solver="cg", path="simt"):
+    os.environ["CUMF_SOLVER"], os.environ["CUMF_PATH"], os.environ["CUMF_QUIET"] = solver, path, "1"
+    th, X = theta0.copy(), np.zeros((r.m, f), np.float32)
+    fin = c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz, r.nnz_test, lam,
+                   iters, 1, 1, 0)
+    return fin, th, X
+
+
+def ratings_from(g):
+    return Ratings(m=int(g["m"]), n=int(g["n"]),
+                   **{k: g[k] for k in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices",
+                                        "csc_data", "coo_row", "test_row", "test_col", "test_val")})
+
+
+@pytest.mark.parametrize("name", ["doals_f20.npz", "doals_f100.npz"])
+@pytest.mark.parametrize("solver", ["cg", "lu"])
+def test_doals_vs_reference_golden(cuda, name, solver):
+    g = golden(name)
+    r = ratings_from(g)
+    f, lam, iters = int(g["f"]), float(g["lam"]), int(g["iters"])
+    fin, th, X = run_doals(r, g["theta0"], f, lam, iters, solver)
+    assert fin == pytest.approx(float(g[f"final_{solver}"]), rel=TOL)
+    assert rel_fro(X, g[f"x_{solver}"]) < 10 * TOL, rel_fro(X, g[f"x_{solver}"])
+    assert rel_fro(th, g[f"theta_{solver}"]) < 10 * TOL
+
+
+@pytest.mark.parametrize("f,solver", [(10, "lu"), (10, "cg"), (100, "cg"), (200, "cg")])
+def test_doals_vs_oracle(cuda, f, solver):
+    r = synth_ratings(300, 420, 16000, 1500, seed=40 + f)
+    theta0, _ = init_factors(r.m, r.n, f, seed=f)
+    fin, th, X = run_doals(r, theta0, f, 0.05, 3, solver)
+    th_o, X_o = theta0.copy(), np.zeros((r.m, f), np.float32)
+    fin_o, hist = O.do_als(r, th_o, X_o, f, 0.05, 3, 0 if solver == "cg" else 1)
+    assert fin == pytest.approx(fin_o, rel=TOL)
+    assert rel_fro(X, X_o) < 10 * TOL and rel_fro(th, th_o) < 10 * TOL
+
+
+def test_doals_batches_are_advisory(cuda):
+    """Results do not depend on X_BATCH / THETA_BATCH (rows are independent)."""
+    r = synth_ratings(200, 300, 9000, 800, seed=77)
+    theta0, _ = init_factors(r.m, r.n, 20, seed=1)
+    os.environ["CUMF_QUIET"] = "1"
+    outs = []
+    for xb, tb in ((1, 1), (3, 7)):
+        th, X = theta0.copy(), np.zeros((r.m, 20), np.float32)
+        c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, 20, r.nnz, r.nnz_test, 0.05, 2,
+                 xb, tb, 0)
+        outs.append((th, X))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+def test_row_shard_equals_full_update(cuda):
+    """E1 sharding: updating a row range touches exactly those rows and gives the
+    same bits as the full update."""
+    r = synth_ratings(240, 360, 12000, 900, seed=12)
+    f = 100
+    theta0, X0 = init_factors(r.m, r.n, f, seed=3)
+    args = (r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row, r.test_row,
+            r.test_col, r.test_val, r.m, r.n, f, 0.05)
+    full = c.AlsSolver(*args, path=c.PATH_SIMT)
+    full.set_factors(theta0, X0)
+    full.update_x()
+    _, X_full = full.get_factors()
+    lo, hi = 60, 150
+    part = c.AlsSolver(*args, x_range=(lo, hi), theta_range=(0, r.n), path=c.PATH_SIMT)
+    part.set_factors(theta0, X0)
+    part.update_x()
+    _, X_part = part.get_factors()
+    assert np.array_equal(X_part[lo:hi], X_full[lo:hi])
+    assert np.array_equal(X_part[:lo], X0[:lo]) and np.array_equal(X_part[hi:], X0[hi:])
+    # sse over shards adds up to the whole (integer partition of the sample set)
+    tr_full, te_full = full.sse()
+    part2 = c.AlsSolver(*args, x_range=(0, lo), theta_range=(0, r.n), path=c.PATH_SIMT)
+    part3 = c.AlsSolver(*args, x_range=(hi, r.m), theta_range=(0, r.n), path=c.PATH_SIMT)
+    th_f, X_f = full.get_factors()
+    sums = np.zeros(2)
+    for p in (part, part2, part3):
+        p.set_factors(th_f, X_f)
+        sums += np.array(p.sse())
+    assert sums[0] == pytest.approx(tr_full, rel=1e-9) and sums[1] == pytest.approx(te_full, rel=1e-9)
+
+
+# ---- live reference (oracle/_ref shipped to the box) ---------------------------------------
+@pytest.mark.parametrize("f,theta_batch", [(100, 1), (20, 2)])
+def test_doals_vs_live_reference(cuda, f, theta_batch):
+    if not O.ref_available("cg"):
+        pytest.skip("oracle/_ref not present")
+    r = synth_ratings(1500, 2600, 180000, 9000, seed=90 + f)
+    theta0, _ = init_factors(r.m, r.n, f, seed=5)
+    iters = 3
+    fin, th, X = run_doals(r, theta0, f, 0.048, iters, "cg")
+    th_r, X_r = theta0.copy(), np.zeros((r.m, f), np.float32)
+    fin_r = O.ref_do_als(r, th_r, X_r, f, 0.048, iters, 1, theta_batch, "cg")
+    print(f"f={f}: final rmse ours {fin} ref {fin_r}; rel X {rel_fro(X, X_r):.2e} theta {rel_fro(th, th_r):.2e}")
+    assert fin == pytest.approx(fin_r, rel=TOL)
+    assert rel_fro(X, X_r) < 10 * TOL and rel_fro(th, th_r) < 10 * TOL

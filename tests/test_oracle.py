@@ -1,0 +1,137 @@
+"""The CPU restatement (oracle/als_cpu.c) against (a) float64 numpy math, (b) the golden
+vectors recorded from the REAL reference kernels on a B200 (tests/golden/make_golden.py).
+CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_fro
+from oracle import oracle as O
+from cumf_als_b200.data import init_factors, synth_ratings
+
+
+# ---- (a) math -------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def small():
+    r = synth_ratings(90, 140, 4000, 600, seed=21)
+    th, X = init_factors(r.m, r.n, 20, seed=2)
+    return r, th, X
+
+
+def test_gram_matches_float64(small):
+    r, th, _ = small
+    f, lam = 20, 0.05
+    tt = O.gram(r.csr_indptr, r.csr_indices, th, f, lam)
+    for u in (0, 7, 33, 89):
+        idx = r.csr_indices[r.csr_indptr[u]:r.csr_indptr[u + 1]]
+        T = th[idx].astype(np.float64)
+        A = T.T @ T + lam * len(idx) * np.eye(f)   # weighted-lambda: lambda * nnz_row (als.cu:546)
+        assert np.abs(tt[u] - A).max() <= 2e-6 * np.abs(A).max()
+        assert (tt[u] == tt[u].T).all()
+
+
+def test_gram_batch_window(small):
+    r, th, _ = small
+    full = O.gram(r.csr_indptr, r.csr_indices, th, 20, 0.05)
+    sub = O.gram(r.csr_indptr, r.csr_indices, th, 20, 0.05, batch_offset=30, batch_size=12)
+    assert (sub == full[30:42]).all()
+
+
+def test_rhs_and_solvers(small):
+    r, th, _ = small
+    f, lam = 20, 0.05
+    tt = O.gram(r.csr_indptr, r.csr_indices, th, f, lam)
+    b = O.rhs(r.csr_indptr, r.csr_indices, r.csr_data, th, f)
+    exact = np.stack([np.linalg.solve(tt[u].astype(np.float64), b[u].astype(np.float64)) for u in range(r.m)])
+    assert rel_fro(O.lu(tt, b, f), exact) < 1e-4
+    # CG stops at rsnew < 1e-4 (absolute): the residual bound, not the solution, is the contract
+    x = O.cg(tt, np.zeros_like(b), b, f, 200.0)
+    res = np.einsum("uij,uj->ui", tt.astype(np.float64), x) - b
+    assert (np.square(res).sum(1) < 1.05e-4).all()
+    # fused-fma and plain variants agree to rounding
+    assert rel_fro(O.cg(tt, np.zeros_like(b), b, f, 6.0, fused_fma=False), O.cg(tt, np.zeros_like(b), b, f, 6.0)) < 1e-5
+
+
+def test_batch_arithmetic_bit_exact():
+    # als.cu:768-777: last batch takes the remainder
+    for rows, nb in ((17770, 1), (480189, 3), (480189, 10), (71567, 4), (7, 3)):
+        sizes = [O.batch_range(rows, nb, i) for i in range(nb)]
+        assert sum(s for s, _ in sizes) == rows
+        assert [o for _, o in sizes] == [i * (rows // nb) for i in range(nb)]
+        assert all(s == rows // nb for s, _ in sizes[:-1])
+
+
+def test_rmse_tail_drop_quirk():
+    # the test launch has (count-1)/256 blocks (als.cu:1006): samples past 256*floor((count-1)/256)
+    # are ignored while the divisor stays `count`
+    rng = np.random.default_rng(0)
+    f, cnt = 10, 700
+    th = rng.standard_normal((30, f)).astype(np.float32)
+    X = rng.standard_normal((20, f)).astype(np.float32)
+    row = rng.integers(0, 20, cnt).astype(np.int32)
+    col = rng.integers(0, 30, cnt).astype(np.int32)
+    val = rng.integers(1, 6, cnt).astype(np.float32)
+    e = val - np.einsum("ij,ij->i", th[col].astype(np.float64), X[row].astype(np.float64))
+    assert abs(O.rmse(val, row, col, th, X, f, False) - np.sqrt((e ** 2).sum() / cnt)) < 1e-5
+    assert abs(O.rmse(val, row, col, th, X, f, True) - np.sqrt((e[:512] ** 2).sum() / cnt)) < 1e-5
+
+
+def test_doals_converges_and_lu_cg_agree(small):
+    r, _, _ = small
+    f, lam = 20, 0.05
+    hist = {}
+    for solver in (0, 1):
+        th, X = init_factors(r.m, r.n, f, seed=2)
+        fin, h = O.do_als(r, th, X, f, lam, 4, solver)
+        assert np.isfinite(h).all() and h[-1, 0] < h[0, 0]
+        assert fin == pytest.approx(h[-1, 1])
+        hist[solver] = h
+    assert np.abs(hist[0] - hist[1]).max() < 5e-3
+
+
+# ---- (b) pinned against the real reference ---------------------------------------------------
+@pytest.mark.parametrize("name", ["gram_f100.npz", "gram_f20.npz", "gram_f200.npz"])
+def test_gram_vs_reference_kernels(name):
+    g = golden(name)
+    f, lam = int(g["f"]), float(g["lam"])
+    tt = O.gram(g["rowptr"], g["colidx"], g["factor"], f, lam)
+    # same fp32 FMA chain in CSR order as als.h:39-143: expected bit-exact
+    assert np.array_equal(tt, g["tt"]), f"max abs diff {np.abs(tt - g['tt']).max()}"
+    sub = O.gram(g["rowptr"], g["colidx"], g["factor"], f, lam, batch_offset=2, batch_size=3)
+    assert np.array_equal(sub, g["tt_sub"])
+    rhs = O.rhs(g["rowptr"], g["colidx"], g["val"], g["factor"], f)
+    assert np.allclose(rhs, g["rhs"], rtol=2e-5, atol=2e-5)    # cuSPARSE order is unspecified
+
+
+@pytest.mark.parametrize("name", ["solve_f100.npz", "solve_f20.npz"])
+def test_solvers_vs_reference(name):
+    g = golden(name)
+    f = int(g["f"])
+    for it in (6, 2):
+        x = O.cg(g["A"], g["x0"], g["b"], f, float(it))
+        assert rel_fro(x, g[f"x_cg{it}"]) < 1e-4, (it, rel_fro(x, g[f"x_cg{it}"]))
+    assert rel_fro(O.lu(g["A"], g["b"], f), g["x_lu"]) < 1e-4
+
+
+def test_rmse_vs_reference():
+    g = golden("rmse.npz")
+    f = int(g["f"])
+    assert O.rmse(g["val"], g["row"], g["col"], g["thetaT"], g["XT"], f, False) == pytest.approx(float(g["rmse_train"]), rel=1e-5)
+    assert O.rmse(g["val"], g["row"], g["col"], g["thetaT"], g["XT"], f, True) == pytest.approx(float(g["rmse_test"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("name", ["doals_f20.npz", "doals_f100.npz"])
+@pytest.mark.parametrize("variant,solver", [("cg", 0), ("lu", 1)])
+def test_doals_vs_reference(name, variant, solver):
+    from cumf_als_b200.data import Ratings
+    g = golden(name)
+    m, n, f, lam, iters = int(g["m"]), int(g["n"]), int(g["f"]), float(g["lam"]), int(g["iters"])
+    r = Ratings(m=m, n=n, **{k: g[k] for k in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices",
+                                                "csc_data", "coo_row", "test_row", "test_col", "test_val")})
+    th, X = g["theta0"].copy(), np.zeros((m, f), np.float32)
+    fin, hist = O.do_als(r, th, X, f, lam, iters, solver)
+    # the reference prints RMSE with %f (6 decimals): compare at that resolution + 1e-4 relative
+    assert np.allclose(hist[:, 0], g[f"train_{variant}"], rtol=1e-4, atol=2e-6)
+    assert np.allclose(hist[:, 1], g[f"test_{variant}"], rtol=1e-4, atol=2e-6)
+    assert fin == pytest.approx(float(g[f"final_{variant}"]), rel=1e-4)
+    assert rel_fro(X, g[f"x_{variant}"]) < 1e-3
+    assert rel_fro(th, g[f"theta_{variant}"]) < 1e-3
