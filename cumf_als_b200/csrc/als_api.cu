@@ -163,8 +163,10 @@ static void plan_free(cumf_plan* p) {
     delete p;
 }
 
+// force_slots: treat every row as "split" (each chunk stores its partial [A|b]); used by cumf_gram
+// to materialise A through the fused kernel.
 static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
-                            int path, bool alloc_workspace) {
+                            int path, bool alloc_workspace, bool force_slots = false) {
     CUMF_REQUIRE(out && h_rowptr, "null pointer");
     CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
     CUMF_TRY(check_f(f));
@@ -193,8 +195,11 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
             set_last_error("row pointers must be non-decreasing and a shard must hold < 2^31 ratings");
             return CUMF_EINVAL;
         }
-        if (n <= max_chunk) {
+        if (n <= max_chunk && !force_slots) {
             p->chunks.push_back(Chunk{r, (int)s, (int)e, -1});
+        } else if (n <= max_chunk) {
+            p->splits.push_back(SplitRow{r, slot, 1, (int)n});
+            p->chunks.push_back(Chunk{r, (int)s, (int)e, slot++});
         } else {
             const int parts = (int)((n + max_chunk - 1) / max_chunk);
             const long long per = (n + parts - 1) / parts;
@@ -229,7 +234,7 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
     if (rc == CUMF_OK && path == CUMF_PATH_TC) {
         rc = tc_plan_create(&p->tc, p->chunks, p->splits, owned, f);
         // rows split across CTAs are reduced and solved through the materialised path
-        if (rc == CUMF_OK && !p->splits.empty()) {
+        if (rc == CUMF_OK && !p->splits.empty() && alloc_workspace) {
             p->batch_rows = (int)p->splits.size();
             rc = p->tt.alloc(sizeof(float) * ff * p->batch_rows);
             if (rc == CUMF_OK) rc = p->rhs.alloc(sizeof(float) * (size_t)f * p->batch_rows);
@@ -367,6 +372,7 @@ extern "C" int cumf_gram(int batch_offset, int batch_size, float* d_tt, float* d
                          int path, void* stream) {
     CUMF_REQUIRE(d_tt && d_rowptr && d_colidx && d_factor, "null pointer");
     CUMF_REQUIRE(!d_rhs || d_val, "d_val is required when d_rhs is requested");
+    CUMF_REQUIRE(path != CUMF_PATH_TC || (d_rhs && d_val), "the fused path always forms the RHS: pass d_rhs and d_val");
     CUMF_REQUIRE(batch_offset >= 0 && batch_size >= 0, "negative batch");
     CUMF_TRY(check_f(f));
     CUMF_TRY(check_device());
@@ -378,22 +384,31 @@ extern "C" int cumf_gram(int batch_offset, int batch_size, float* d_tt, float* d
     CUMF_CUDA_TRY(cudaMemcpyAsync(h_rowptr.data(), d_rowptr, sizeof(int) * (m + 1), cudaMemcpyDeviceToHost, st));
     CUMF_CUDA_TRY(cudaStreamSynchronize(st));
     if (path == CUMF_PATH_AUTO) path = CUMF_PATH_SIMT;
-    if (path != CUMF_PATH_SIMT) {
-        set_last_error("cumf_gram materialises A with the SIMT kernel; the fused path has no A to return "
-                       "(use cumf_update_factor)");
-        return CUMF_EUNSUPPORTED;
-    }
     cumf_plan* p = nullptr;
-    // the plan's own workspace is not needed here: build it with a tiny cap, then aim the
-    // kernel at the caller's buffers.
-    CUMF_TRY(plan_create_impl(&p, h_rowptr.data(), m, batch_offset, row_end, f, CUMF_PATH_SIMT, false));
-    const long long base = p->base;
-    int rc = launch_gram_simt(p->d_chunks.as<Chunk>(), 0, (int)p->chunks.size(), d_colidx + base,
+    int rc = CUMF_OK;
+    if (path == CUMF_PATH_TC) {
+        // materialise A through the fused tensor-core kernel: every chunk stores its partial
+        // [A|b] (split-row mode), then the deterministic reduce adds lambda*n_u and writes tt/rhs.
+        CUMF_TRY(plan_create_impl(&p, h_rowptr.data(), m, batch_offset, row_end, f, CUMF_PATH_TC, false, true));
+        const long long base = p->base;
+        int launches = 0;
+        rc = tc_update_factor(p->tc, p->d_chunks.as<Chunk>(), (int)p->chunks.size(), d_colidx + base,
+                              d_val ? d_val + base : nullptr, d_factor, nullptr, f, lambda, 0.f,
+                              p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches);
+        if (rc == CUMF_OK)
+            rc = launch_split_reduce(p->d_splits.as<SplitRow>(), 0, (int)p->splits.size(), f, lambda, 0, batch_offset,
+                                     d_tt, d_rhs, p->scratchA.as<float>(), p->scratchB.as<float>(), st);
+    } else {
+        // the plan's own workspace is not needed here: aim the kernel at the caller's buffers
+        CUMF_TRY(plan_create_impl(&p, h_rowptr.data(), m, batch_offset, row_end, f, CUMF_PATH_SIMT, false));
+        const long long base = p->base;
+        rc = launch_gram_simt(p->d_chunks.as<Chunk>(), 0, (int)p->chunks.size(), d_colidx + base,
                               d_val ? d_val + base : nullptr, d_factor, f, lambda, batch_offset, d_tt, d_rhs,
                               p->scratchA.as<float>(), p->scratchB.as<float>(), st);
-    if (rc == CUMF_OK && !p->splits.empty())
-        rc = launch_split_reduce(p->d_splits.as<SplitRow>(), 0, (int)p->splits.size(), f, lambda, 0, batch_offset, d_tt,
-                                 d_rhs, p->scratchA.as<float>(), p->scratchB.as<float>(), st);
+        if (rc == CUMF_OK && !p->splits.empty())
+            rc = launch_split_reduce(p->d_splits.as<SplitRow>(), 0, (int)p->splits.size(), f, lambda, 0, batch_offset,
+                                     d_tt, d_rhs, p->scratchA.as<float>(), p->scratchB.as<float>(), st);
+    }
     if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) {
         set_last_error(std::string("cumf_gram: ") + cudaGetErrorString(cudaGetLastError()));
         rc = CUMF_ECUDA;

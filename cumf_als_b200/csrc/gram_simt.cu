@@ -128,10 +128,10 @@ __global__ void gram_simt_kernel(const Chunk* __restrict__ chunks, int c0, const
                          : (scratchB ? scratchB + (size_t)ch.slot * f : nullptr);
     if (has_tile) {
         if (direct && tx == ty) {
-            // weighted-lambda regularisation: (end-start)*lambda on the diagonal (als.cu:546, 655)
-            const float reg = (float)total * lambda;
+            // weighted-lambda regularisation: (end-start)*lambda on the diagonal (als.cu:546, 655);
+            // the reference binary executes it as one FFMA (pinned by tests/golden/gram_*.npz)
 #pragma unroll
-            for (int i = 0; i < TS; ++i) acc[i][i] += reg;
+            for (int i = 0; i < TS; ++i) acc[i][i] = fmaf((float)total, lambda, acc[i][i]);
         }
 #pragma unroll
         for (int i = 0; i < TS; ++i) {
@@ -166,14 +166,13 @@ __global__ void split_reduce_kernel(const SplitRow* __restrict__ rows, int r0, i
                                     const float* __restrict__ scratchB) {
     const SplitRow sr = rows[r0 + blockIdx.x];
     const int ff = f * f;
-    const float reg = (float)sr.nnz * lambda;
     const size_t oidx = compact ? (size_t)(r0 + blockIdx.x) : (size_t)(sr.row - out_row_base);
     float* Aout = tt + oidx * ff;
     for (int e = threadIdx.x; e < ff; e += blockDim.x) {
         float s = 0.f;
         for (int k = 0; k < sr.count; ++k) s += scratchA[(size_t)(sr.first_slot + k) * ff + e];
         const int i = e / f, j = e - i * f;
-        if (i == j) s += reg;
+        if (i == j) s = fmaf((float)sr.nnz, lambda, s);
         Aout[e] = s;
     }
     if (rhs && scratchB) {

@@ -1,19 +1,599 @@
-// gram_tc.cu -- fused TMA-gather + tcgen05 Gram + in-register CG (placeholder until the
-// kernel lands: the planner then never selects this path).
+// gram_tc.cu -- the fused B200 half-step kernel:
+//   TMA row gather -> split-fp16 operand staging -> tcgen05.mma (accumulators in TMEM)
+//   -> epilogue straight into an in-register conjugate-gradient solve.
+// A_u is never written to HBM; per rating the kernel moves one f-wide fp32 factor row,
+// one int32 column index and one fp32 value (B_gram_fused).
+//
+// What it replaces in the reference: get_hermitian100 (als.cu:443-569) + the cuSPARSE RHS
+// pass (als.cu:750-757) + updateXWithCGKernel (cg.cu:36-231) for f = 100, i.e. the body of
+// the iteration loop als.cu:727-853 / 858-961.  The disabled fused kernel
+// alsUpdateFeature100 (cg.cu:726-1189, "register pressure and low occupancy", als.cu:809)
+// is the precedent; here the Gram tile lives in TMEM instead of 100 registers x 55 threads.
+//
+// Numerics.  The reference accumulates theta_j theta_j^T in fp32.  Tensor cores have no fp32
+// input mode, so every gathered fp32 value v is split as  v = hi + lo,
+//   hi = v with the low 13 mantissa bits cleared (exactly representable in fp16),
+//   lo' = fp16( (v - hi) * 2048 )                      (scaled so it stays a normal fp16)
+// and  A = hi^T hi + (hi^T lo' + lo'^T hi) / 2048  is accumulated in fp32 in TMEM with three
+// kind::f16 MMAs per 16 gathered rows (the dropped lo^T lo term is < 2^-20 relative).  The
+// RHS  b = sum r_uj theta_j  is accumulated in exact fp32 FMAs in CSR order by the staging
+// warps (bit-identical to the SIMT path), and the CG is the fp32 register-resident solve of
+// cg.cu with identical semantics (cg.cu:47-230).
+//
+// CTA = 16 warps, persistent, one per SM, each owning a contiguous, cost-balanced range of
+// row chunks (so its ratings are one contiguous stream):
+//   warps 0-2     producers: warp 0 keeps a cp.async-prefetched window of colidx/val in
+//                 smem rings; all three issue one cp.async.bulk (TMA, SASS UBLKCP) per
+//                 gathered 400-byte factor row into an 8-stage fp32 ring (rows of a stage
+//                 interleaved over the warps: UBLKCP takes uniform-register operands, so a
+//                 warp issues its rows one at a time), completion on mbarriers (expect_tx)
+//   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=224 and N=112,
+//                 K=16, smem descriptors (K-major, no swizzle); tcgen05.commit frees
+//                 operand stages / publishes accumulators; owns the TMEM allocation
+//   warps 4-7     staging: fp32 tile -> (hi | lo') fp16 K-major core-matrix layout,
+//                 fence.proxy.async, RHS accumulation
+//   warps 8-11 /  two epilogue+solver warpgroups (one per TMEM accumulator buffer):
+//   warps 12-15   tcgen05.ld of row i of A into registers, + lambda*n_u, 6-step CG with
+//                 named-barrier reductions, x written back; chunks of split rows store
+//                 their partial [A|b] instead (reduced + solved by the unfused kernels).
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 namespace cumf {
-bool tc_path_supports(int) { return false; }
-struct TcWork {};
-int tc_plan_create(TcWork** out, const std::vector<Chunk>&, const std::vector<SplitRow>&, int, int) {
-    *out = nullptr;
-    set_last_error("fused tcgen05 path not built");
-    return CUMF_EUNSUPPORTED;
+namespace {
+
+// ---- compile-time geometry (f = 100) ---------------------------------------------------
+constexpr int F = 100;                    // rank handled by this kernel
+constexpr int FP = 112;                   // rank padded to a multiple of 16 (UMMA N granularity at M=128)
+constexpr int KT = 16;                    // gathered rows per MMA k-step (fp16 UMMA K)
+constexpr int S1 = 8;                     // fp32 staging ring depth (8 x 6.4 KB in flight per SM)
+constexpr int S2 = 4;                     // fp16 operand ring depth
+constexpr int ROW_BYTES = F * 4;          // one factor row
+constexpr int STAGE_F32_BYTES = KT * ROW_BYTES;
+constexpr int OP_ROWS = 2 * FP + 16;      // hi rows [0,112), lo' rows [112,224), 16 don't-care rows
+constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B): SBO
+constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
+constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 7680
+constexpr int IDX_RING = 2048;            // prefetched colidx / val window (ratings)
+constexpr int IDX_BATCH = 256;            // ratings per cp.async group
+constexpr int IDX_GROUPS = 4;             // groups kept in flight
+constexpr int CHUNK_RING = 128;
+constexpr int NUM_THREADS = 512;
+constexpr int PROD_WARPS = 3;             // producer warps (warp ids 0..2)
+constexpr int MMA_WARP = 3;
+constexpr int PROD_BAR = 3;               // named barrier id of the producer warps (1, 2: solver warpgroups)
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COLS = 256;             // column stride between the two accumulators
+constexpr int N1 = 2 * FP;                // 224: [hi | lo'] as B operand
+constexpr int N2 = FP;                    // 112: hi as B operand (lo' as A)
+constexpr float kLoScale = 2048.0f;
+constexpr float kLoInv = 1.0f / 2048.0f;
+constexpr double kCgError = 1e-4;         // cg.cu:31
+
+constexpr uint32_t FLAG_FIRST = 1u, FLAG_LAST = 2u;
+
+struct StageMeta {   // written by the producer (f32 ring) / staging warps (operand ring)
+    uint32_t ring_off;   // offset of the stage's first rating in the idx/val rings
+    uint32_t cnt;        // valid gathered rows (0..16)
+    uint32_t chunk_slot; // index into chunk_ring
+    uint32_t flags;
+};
+
+struct __align__(128) Smem {
+    unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 51200
+    unsigned char op_stage[S2][OP_STAGE_BYTES];     // 30720
+    int idx_ring[IDX_RING];
+    float val_ring[IDX_RING];
+    Chunk chunk_ring[CHUNK_RING];
+    StageMeta meta_f32[S1];
+    StageMeta meta_op[S2];
+    Chunk acc_chunk[2];
+    float bsm[2][FP];
+    float sp[2][128];            // CG direction vector per solver warpgroup
+    float red[2][3][4];          // cross-warp partial sums
+    unsigned long long full_f32[S1], empty_f32[S1], full_op[S2], empty_op[S2];
+    unsigned long long acc_full[2], acc_empty[2], b_full[2], b_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-void tc_plan_destroy(TcWork*) {}
-int tc_update_factor(TcWork*, const Chunk*, int, const int*, const float*, const float*, float*, int, float, float,
-                     float*, float*, cudaStream_t, int*) {
-    set_last_error("fused tcgen05 path not built");
-    return CUMF_EUNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_row_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading (K-direction core-matrix) byte offset >> 4,
+//   [32,46) stride (8-row group) byte offset >> 4, [46,48) version = 1, [61,64) layout = 0.
+__host__ __device__ constexpr uint64_t smem_desc_template(bool swap_lbo_sbo) {
+    return ((uint64_t)((swap_lbo_sbo ? OP_GROUP_BYTES : OP_KCORE_BYTES) >> 4) << 16) |
+           ((uint64_t)((swap_lbo_sbo ? OP_KCORE_BYTES : OP_GROUP_BYTES) >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t tmpl) {
+    return tmpl | (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format F16 (0),
+// K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct Ring {   // stage index + phase bit of an mbarrier ring
+    int s = 0;
+    uint32_t ph = 0;
+    int n;
+    __device__ explicit Ring(int n_) : n(n_) {}
+    __device__ void next() { if (++s == n) { s = 0; ph ^= 1u; } }
+};
+
+// ---- solver warpgroup: fp32 CG with A row i in registers (cg.cu:36-231) ---------------------
+__device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, int lane, int bar_id) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) red4[warp_in_wg] = v;
+    named_bar_sync(bar_id, 128);
+    return (red4[0] + red4[1]) + (red4[2] + red4[3]);
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
+                      const int* __restrict__ colidx, const float* __restrict__ val,
+                      const float* __restrict__ factor, float* __restrict__ out, float lambda, float cg_iter,
+                      float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl) {
+    extern __shared__ unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int c_begin = cta_chunk_ptr[blockIdx.x], c_end = cta_chunk_ptr[blockIdx.x + 1];
+    const int n_chunks = c_end - c_begin;
+
+    // ---- one-time setup --------------------------------------------------------------------
+    {   // zero the operand ring: padded feature rows and don't-care rows stay zero for ever
+        uint4* p = reinterpret_cast<uint4*>(&sm.op_stage[0][0]);
+        for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], 4); }
+        for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], 4); mbar_init(&sm.empty_op[s], 1); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 4);
+            mbar_init(&sm.b_full[b], 4);   mbar_init(&sm.b_empty[b], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, TMEM_COLS);
+    fence_proxy_async();      // the zero fill above must be visible to the tensor-core (async) proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (n_chunks > 0) {
+        if (warp < PROD_WARPS) {
+            // ================================ producers =========================================
+            const int pos0 = chunks[c_begin].begin;
+            const int pos_end = chunks[c_end - 1].end;
+            int fetched = pos0;       // next rating to prefetch
+            int ready = pos0;         // ratings [pos0, ready) are in the rings
+            int groups_in_flight = 0;
+            // every producer warp replays the same bookkeeping; only warp 0 moves the data
+            auto prefetch = [&]() {
+                if (warp == 0) {
+#pragma unroll
+                    for (int j = 0; j < IDX_BATCH / 32; ++j) {
+                        const int p = fetched + j * 32 + lane;
+                        if (p < pos_end) {
+                            cp_async_4(&sm.idx_ring[(p - pos0) & (IDX_RING - 1)], colidx + p);
+                            cp_async_4(&sm.val_ring[(p - pos0) & (IDX_RING - 1)], val + p);
+                        }
+                    }
+                    cp_async_commit();
+                }
+                fetched += IDX_BATCH;
+                ++groups_in_flight;
+            };
+            for (int g = 0; g < IDX_GROUPS; ++g) prefetch();
+
+            Ring st(S1);
+            Chunk next_ck = (c_begin + lane < c_end) ? chunks[c_begin + lane] : Chunk{0, 0, 0, -1};
+            int pos = pos0;
+            for (int cb = c_begin; cb < c_end; cb += 32) {
+                const Chunk my_ck = next_ck;
+                if (cb + 32 + lane < c_end) next_ck = chunks[cb + 32 + lane];     // register prefetch of the next 32
+                if (warp == 0 && cb + lane < c_end) sm.chunk_ring[(cb - c_begin + lane) & (CHUNK_RING - 1)] = my_ck;
+                __syncwarp();
+                const int nb = min(32, c_end - cb);
+                for (int ci = 0; ci < nb; ++ci) {
+                    const int cend = __shfl_sync(0xffffffffu, my_ck.end, ci);
+                    const uint32_t slot = (uint32_t)((cb - c_begin + ci) & (CHUNK_RING - 1));
+                    bool first = true;
+                    do {   // at least one (possibly empty) stage per chunk
+                        const int cnt = min(KT, cend - pos);
+                        // make sure the indices of this stage have landed in the ring
+                        while (pos + cnt > ready) {
+                            // oldest group complete <=> at most (groups_in_flight-1) pending
+                            if (warp == 0) {
+                                if (groups_in_flight >= 4) cp_async_wait<3>();
+                                else if (groups_in_flight == 3) cp_async_wait<2>();
+                                else if (groups_in_flight == 2) cp_async_wait<1>();
+                                else cp_async_wait<0>();
+                            }
+                            --groups_in_flight;
+                            named_bar_sync(PROD_BAR, PROD_WARPS * 32);      // ring contents visible to all producers
+                            ready += IDX_BATCH;
+                            if (fetched < pos_end) prefetch();
+                        }
+                        mbar_wait(&sm.empty_f32[st.s], st.ph ^ 1u);
+                        const bool last = (pos + cnt >= cend);
+                        if (warp == 0 && lane == 0) {
+                            sm.meta_f32[st.s] = StageMeta{(uint32_t)((pos - pos0) & (IDX_RING - 1)), (uint32_t)cnt, slot,
+                                                          (first ? FLAG_FIRST : 0u) | (last ? FLAG_LAST : 0u)};
+                            // the single pending arrival keeps the phase open until this executes, so
+                            // complete_tx from the other warps' rows may land before or after it
+                            mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)cnt * ROW_BYTES);
+                        }
+                        const int row_in_stage = warp + PROD_WARPS * lane;     // rows interleaved over the producer warps
+                        if (row_in_stage < cnt) {
+                            const int col = sm.idx_ring[(pos - pos0 + row_in_stage) & (IDX_RING - 1)];
+                            tma_row_g2s(&sm.f32_stage[st.s][row_in_stage * ROW_BYTES], factor + (size_t)col * F, ROW_BYTES,
+                                        &sm.full_f32[st.s]);
+                        }
+                        pos += cnt;
+                        first = false;
+                        st.next();
+                    } while (pos < cend);
+                }
+            }
+            cp_async_wait<0>();
+        } else if (warp == MMA_WARP) {
+            // ================================ MMA issuer ========================================
+            if (lane == 0) {
+                constexpr uint32_t idesc1 = make_idesc(128, N1);
+                constexpr uint32_t idesc2 = make_idesc(128, N2);
+                Ring op(S2);
+                int q = 0;
+                while (q < n_chunks) {
+                    mbar_wait(&sm.full_op[op.s], op.ph);
+                    const uint32_t flags = sm.meta_op[op.s].flags;
+                    const int buf = q & 1;
+                    if (flags & FLAG_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(&sm.op_stage[op.s][0]);
+                    const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                   // rows 0.. : hi (| lo')
+                    const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);       // rows 112.. : lo'
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+                    // cols [0,112): hi^T hi ; cols [112,224): hi^T lo'
+                    umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_FIRST) ? 0u : 1u);
+                    // cols [112,224) += lo'^T hi
+                    umma_f16(d_tmem + FP, d_lo, d_hi, idesc2, 1u);
+                    umma_commit(&sm.empty_op[op.s]);          // operand stage reusable once both MMAs retire
+                    if (flags & FLAG_LAST) { umma_commit(&sm.acc_full[buf]); ++q; }
+                    op.next();
+                }
+            }
+            __syncwarp();
+        } else if (warp < 8) {
+            // ================================ staging warps =====================================
+            const int t = tid - 128;                  // feature handled by this thread
+            const bool active = t < F;
+            const int wl = lane;
+            Ring st(S1), op(S2);
+            int q = 0;
+            float bacc = 0.f;
+            const int g = t >> 3, r8 = t & 7;
+            while (q < n_chunks) {
+                mbar_wait(&sm.full_f32[st.s], st.ph);
+                const StageMeta meta = sm.meta_f32[st.s];
+                mbar_wait(&sm.empty_op[op.s], op.ph ^ 1u);
+                if (meta.flags & FLAG_FIRST) bacc = 0.f;
+                if (active) {
+                    const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t;
+                    uint32_t hi2[8], lo2[8];
+#pragma unroll
+                    for (int k = 0; k < KT; k += 2) {
+                        float v0 = 0.f, v1 = 0.f, r0 = 0.f, r1 = 0.f;
+                        if ((uint32_t)k < meta.cnt) { v0 = src[k * F]; r0 = sm.val_ring[(meta.ring_off + k) & (IDX_RING - 1)]; }
+                        if ((uint32_t)(k + 1) < meta.cnt) { v1 = src[(k + 1) * F]; r1 = sm.val_ring[(meta.ring_off + k + 1) & (IDX_RING - 1)]; }
+                        bacc = fmaf(r0, v0, bacc);          // b_u += r_uj * theta_j[t], CSR order (als.cu:750)
+                        bacc = fmaf(r1, v1, bacc);
+                        const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);
+                        const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+                        const __half2 hh = __floats2half2_rn(h0, h1);                       // exact
+                        const __half2 ll = __floats2half2_rn((v0 - h0) * kLoScale, (v1 - h1) * kLoScale);
+                        hi2[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                        lo2[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+                    }
+                    unsigned char* ob = &sm.op_stage[op.s][0];
+                    uint4* hi_dst = reinterpret_cast<uint4*>(ob + g * OP_GROUP_BYTES + r8 * 16);
+                    uint4* lo_dst = reinterpret_cast<uint4*>(ob + (FP / 8 + g) * OP_GROUP_BYTES + r8 * 16);
+                    hi_dst[0] = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);                       // k 0..7
+                    hi_dst[OP_KCORE_BYTES / 16] = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);     // k 8..15
+                    lo_dst[0] = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+                    lo_dst[OP_KCORE_BYTES / 16] = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+                }
+                if (t == 0) sm.meta_op[op.s] = meta;
+                fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05.mma
+                __syncwarp();
+                if (wl == 0) {
+                    mbar_arrive(&sm.full_op[op.s]);
+                    mbar_arrive(&sm.empty_f32[st.s]);
+                }
+                if (meta.flags & FLAG_LAST) {
+                    const int buf = q & 1;
+                    mbar_wait(&sm.b_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                    if (active) sm.bsm[buf][t] = bacc;
+                    if (t == 0) sm.acc_chunk[buf] = sm.chunk_ring[meta.chunk_slot];
+                    __syncwarp();
+                    if (wl == 0) mbar_arrive(&sm.b_full[buf]);
+                    ++q;
+                }
+                st.next();
+                op.next();
+            }
+        } else {
+            // ========================= epilogue + solver warpgroups =============================
+            const int wg = (warp - 8) >> 2;               // 0: warps 8-11, 1: warps 12-15
+            const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
+            const int wiw = quad;                         // warp index inside the warpgroup
+            const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
+            const bool active = i < F;
+            const int bar_id = 1 + wg;
+            float* sp = sm.sp[wg];
+            for (int q = wg; q < n_chunks; q += 2) {
+                const int buf = wg;
+                const uint32_t ph = ((uint32_t)q >> 1) & 1u;
+                mbar_wait(&sm.acc_full[buf], ph);
+                mbar_wait(&sm.b_full[buf], ph);
+                tc_fence_after();
+                const Chunk ck = sm.acc_chunk[buf];
+                const float bi = active ? sm.bsm[buf][i] : 0.f;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
+                // row i of hi^T hi straight into the registers that will hold A, then fold in the
+                // cross terms 16 columns at a time (keeps the live temporaries at 16)
+                uint32_t au[F];
+#pragma unroll
+                for (int c = 0; c < 96; c += 16) tmem_ld16(taddr + c, reinterpret_cast<uint32_t(&)[16]>(au[c]));
+                tmem_ld4(taddr + 96, reinterpret_cast<uint32_t(&)[4]>(au[96]));
+                tmem_ld_wait();
+                float a[F];
+#pragma unroll
+                for (int c = 0; c < 96; c += 16) {
+                    uint32_t s[16];
+                    tmem_ld16(taddr + FP + c, s);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) a[c + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(au[c + j]));
+                }
+                {
+                    uint32_t s[4];
+                    tmem_ld4(taddr + FP + 96, s);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a[96 + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(au[96 + j]));
+                }
+                // accumulator and b buffer are drained: hand them back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&sm.acc_empty[buf]); mbar_arrive(&sm.b_empty[buf]); }
+
+                if (ck.slot >= 0) {
+                    // chunk of a row split across CTAs: store the partial [A | b]; reduced and solved later
+                    if (active) {
+                        float4* dst = reinterpret_cast<float4*>(scratchA + (size_t)ck.slot * F * F + (size_t)i * F);
+#pragma unroll
+                        for (int j = 0; j < F; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                        scratchB[(size_t)ck.slot * F + i] = bi;
+                    }
+                    continue;
+                }
+                // weighted-lambda regularisation on the diagonal (als.cu:546): (end-start)*lambda
+                const float nu = (float)(ck.end - ck.begin);
+#pragma unroll
+                for (int j = 0; j < F; ++j) if (j == i) a[j] = fmaf(nu, lambda, a[j]);
+
+                // ---- CG (cg.cu:47-230), A row i in registers, p broadcast from shared memory ----
+                float* xrow = out + (size_t)ck.row * F;
+                float xi = active ? xrow[i] : 0.f;
+                auto spmv = [&]() -> float {
+                    float y = 0.f;
+#pragma unroll
+                    for (int j = 0; j < F; j += 4) {
+                        const float4 pv = *reinterpret_cast<const float4*>(sp + j);
+                        y = fmaf(a[j], pv.x, y); y = fmaf(a[j + 1], pv.y, y);
+                        y = fmaf(a[j + 2], pv.z, y); y = fmaf(a[j + 3], pv.w, y);
+                    }
+                    return y;
+                };
+                const float own = active ? 1.f : 0.f;
+                named_bar_sync(bar_id, 128);                       // previous row's readers of sp are done
+                if (active) sp[i] = xi;
+                named_bar_sync(bar_id, 128);
+                float r = active ? bi - spmv() : 0.f;              // r = b - A x
+                float p = r;
+                float rsold = wg_sum(own * r * r, sm.red[wg][0], wiw, lane, bar_id);
+                for (int it = 0; (float)it < cg_iter; ++it) {
+                    named_bar_sync(bar_id, 128);
+                    if (active) sp[i] = p;
+                    named_bar_sync(bar_id, 128);
+                    const float ap = active ? spmv() : 0.f;
+                    const float pap = wg_sum(own * p * ap, sm.red[wg][1], wiw, lane, bar_id);
+                    const float alpha = rsold / pap;               // cg.cu:128 (no guard)
+                    xi = fmaf(alpha, p, xi);
+                    r = fmaf(-alpha, ap, r);
+                    const float rsnew = wg_sum(own * r * r, sm.red[wg][2], wiw, lane, bar_id);
+                    if ((double)rsnew < kCgError) break;           // cg.cu:195
+                    const float beta = rsnew / rsold;
+                    rsold = rsnew;
+                    p = fmaf(beta, p, r);
+                }
+                if (active) xrow[i] = xi;
+            }
+        }
+    }
+
+    // ---- teardown ----------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace
+
+// ---- host side -----------------------------------------------------------------------------
+struct TcWork {
+    DevBuf cta_ptr;
+    int grid = 0;
+    int nchunks = 0;
+};
+
+bool tc_path_supports(int f) {
+    const char* off = getenv("CUMF_DISABLE_TC");
+    if (off && *off == '1') return false;
+    return f == F;
+}
+
+int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const std::vector<SplitRow>&, int, int f) {
+    if (f != F) {
+        set_last_error("fused tcgen05 kernel handles f = 100 only");
+        return CUMF_EUNSUPPORTED;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* g = getenv("CUMF_TC_CTAS");
+    int grid = (g && *g) ? atoi(g) : sms;
+    if (grid < 1) grid = 1;
+    const int n = (int)chunks.size();
+    if (grid > n) grid = std::max(1, n);
+    // contiguous, cost-balanced partition of the (row-ordered) chunk list: cost = MMA k-steps
+    // plus a per-chunk epilogue/solve term, so every CTA streams one contiguous rating range.
+    const long long per_chunk = 96;
+    std::vector<long long> prefix(n + 1, 0);
+    for (int c = 0; c < n; ++c) {
+        const long long nnz = chunks[c].end - chunks[c].begin;
+        prefix[c + 1] = prefix[c] + ((nnz + KT - 1) / KT) * KT + per_chunk;
+    }
+    std::vector<int> ptr(grid + 1, 0);
+    for (int b = 1; b < grid; ++b) {
+        const long long target = prefix[n] * b / grid;
+        int c = (int)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        c = std::min(std::max(c, ptr[b - 1]), n);
+        ptr[b] = c;
+    }
+    ptr[grid] = n;
+    TcWork* w = new TcWork();
+    w->grid = grid;
+    w->nchunks = n;
+    int rc = w->cta_ptr.alloc(sizeof(int) * (grid + 1));
+    if (rc == CUMF_OK && cudaMemcpy(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_last_error("tc_plan_create: upload failed");
+        rc = CUMF_ECUDA;
+    }
+    if (rc != CUMF_OK) { w->cta_ptr.release(); delete w; return rc; }
+    *out = w;
+    return CUMF_OK;
+}
+
+void tc_plan_destroy(TcWork* w) {
+    if (!w) return;
+    w->cta_ptr.release();
+    delete w;
+}
+
+int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d_colidx, const float* d_val,
+                     const float* d_factor, float* d_out, int f, float lambda, float cg_iter, float* d_scratchA,
+                     float* d_scratchB, cudaStream_t st, int* launches) {
+    if (!w || f != F) {
+        set_last_error("tc_update_factor: bad plan");
+        return CUMF_EINVAL;
+    }
+    if (nchunks == 0) return CUMF_OK;
+    const size_t smem = sizeof(Smem) + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
+    const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
+    als_fused_f100_kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), d_colidx, d_val, d_factor,
+                                                            d_out, lambda, cg_iter, d_scratchA, d_scratchB, desc_tmpl);
+    CUMF_CUDA_TRY(cudaGetLastError());
+    *launches += 1;
+    return CUMF_OK;
+}
+
 }  // namespace cumf

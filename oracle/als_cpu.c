@@ -39,8 +39,9 @@
  * als.cu:575-659 (get_hermitianT10) and als.cu:443-569 (get_hermitian100) +
  * als.h:39-143 (accumulate_in_registers): every element (i,j) is
  *     acc = 0;  for k in CSR order: acc = fma(theta[col_k][i], theta[col_k][j], acc)
- * then the diagonal gets  (end-start)*lambda  added (als.cu:546-558, 653-656):
- * an int->float conversion, one fp32 multiply, one fp32 add.
+ * then the diagonal gets  (end-start)*lambda  added (als.cu:546-558, 653-656).  nvcc
+ * contracts that multiply-add into one FFMA (default -fmad=true); pinned by the golden
+ * vectors: with a separate multiply and add the diagonals are 1 ulp off the reference.
  * Output layout: full symmetric f x f, row-major (als.h:501-627).
  * ---------------------------------------------------------------------- */
 static void gram_row(const int* idx, int cnt, const float* factor, int f, float lambda, float* A) {
@@ -58,8 +59,8 @@ static void gram_row(const int* idx, int cnt, const float* factor, int f, float 
     }
     for (int i = 0; i < f; ++i)
         for (int j = 0; j < i; ++j) A[(size_t)i * f + j] = A[(size_t)j * f + i];
-    const float reg = (float)cnt * lambda; /* als.cu:546 */
-    for (int d = 0; d < f; ++d) A[(size_t)d * f + d] += reg;
+    for (int d = 0; d < f; ++d)   /* als.cu:546, 655: fused multiply-add */
+        A[(size_t)d * f + d] = fmaf((float)cnt, lambda, A[(size_t)d * f + d]);
 }
 
 /* b_u = sum_k val_k * theta[col_k]   (als.cu:750-757: cusparseScsrmm2 +

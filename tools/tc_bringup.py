@@ -1,0 +1,75 @@
+"""Bring-up diagnostics for the fused tcgen05 kernel (run on the GPU box).
+
+Materialises A through the fused kernel (cumf_gram, path=TC) on a few ragged rows and prints
+the error against the CPU oracle, for both orderings of the UMMA descriptor strides, then a
+single half-step (Gram + CG) against the SIMT path."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import cumf_als_b200 as c  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def csr(rng, lengths, n):
+    rowptr = np.zeros(len(lengths) + 1, np.int32)
+    rowptr[1:] = np.cumsum(lengths)
+    cols = np.concatenate([np.sort(rng.choice(n, size=k, replace=False)) for k in lengths] + [np.zeros(0, np.int64)])
+    return rowptr, cols.astype(np.int32), rng.integers(1, 6, cols.size).astype(np.float32)
+
+
+def main():
+    f, lam = 100, 0.05
+    rng = np.random.default_rng(1)
+    which = sys.argv[1] if len(sys.argv) > 1 else "gram"
+    lengths = [16, 1, 2, 15, 17, 31, 32, 33, 0, 100, 250, 1000, 3000]
+    n = 5000
+    rowptr, colidx, val = csr(rng, lengths, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    m = len(lengths)
+    ref = O.gram(rowptr, colidx, factor, f, lam)
+    rhs_ref = O.rhs(rowptr, colidx, val, factor, f)
+    if which == "gram":
+        tt = torch.full((m, f, f), float("nan"), device="cuda")
+        rhs = torch.full((m, f), float("nan"), device="cuda")
+        c.gram(0, m, tt, dev(rowptr), dev(colidx), lam, m, f, dev(factor), rhs=rhs, val=dev(val), path=c.PATH_TC)
+        torch.cuda.synchronize()
+        tt, rhs = tt.cpu().numpy(), rhs.cpu().numpy()
+        print("swap =", os.environ.get("CUMF_TC_SWAP_LBO_SBO", "0"))
+        for u in range(m):
+            scale = max(np.abs(ref[u]).max(), 1e-30)
+            err = np.abs(tt[u] - ref[u]).max() / scale
+            sym = np.abs(tt[u] - tt[u].T).max() / scale
+            print(f"  row {u:2d} len {lengths[u]:5d}: max rel err {err:.3e}  asym {sym:.2e}  "
+                  f"rhs exact {np.array_equal(rhs[u], rhs_ref[u])}  nan {np.isnan(tt[u]).any()}")
+        if np.nanmax(np.abs(tt - ref)) > 1e-2:
+            u = 9
+            print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", tt[u][0, :6])
+            print("  row 9 ref[1,:6]", ref[u][1, :6], "\n  row 9 got[1,:6]", tt[u][1, :6])
+    else:
+        # one half-step through plans: fused vs SIMT
+        x0 = (0.1 * rng.standard_normal((m, f))).astype(np.float32)
+        outs = {}
+        for name, path in (("simt", c.PATH_SIMT), ("tc", c.PATH_TC)):
+            plan = c.Plan(rowptr, 0, m, f, path)
+            x = dev(x0)
+            c.update_factor(plan, dev(colidx), dev(val), dev(factor), x, lam)
+            torch.cuda.synchronize()
+            outs[name] = x.cpu().numpy()
+            print(name, "launches", plan.last_launches)
+        for u in range(m):
+            a, b = outs["tc"][u].astype(np.float64), outs["simt"][u].astype(np.float64)
+            print(f"  row {u:2d} len {lengths[u]:5d}: rel diff {np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30):.3e}")
+
+
+if __name__ == "__main__":
+    main()
