@@ -16,8 +16,8 @@
 //   lo' = fp16( (v - hi) * 2048 )                      (scaled so it stays a normal fp16)
 // and  A = hi^T hi + (hi^T lo' + lo'^T hi) / 2048  is accumulated in fp32 in TMEM with three
 // kind::f16 MMAs per 16 gathered rows (the dropped lo^T lo term is < 2^-20 relative).  The
-// RHS  b = sum r_uj theta_j  is accumulated in exact fp32 FMAs in CSR order by the staging
-// warps (bit-identical to the SIMT path), and the CG is the fp32 register-resident solve of
+// RHS  b = sum r_uj theta_j  is accumulated with exact fp32 FMAs by the staging warps (two
+// interleaved partial sums per feature), and the CG is the fp32 register-resident solve of
 // cg.cu with identical semantics (cg.cu:47-230).
 //
 // CTA = 16 warps, persistent, one per SM, each owning a contiguous, cost-balanced range of
@@ -30,11 +30,13 @@
 //   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=224 and N=112,
 //                 K=16, smem descriptors (K-major, no swizzle); tcgen05.commit frees
 //                 operand stages / publishes accumulators; owns the TMEM allocation
-//   warps 4-7     staging: fp32 tile -> (hi | lo') fp16 K-major core-matrix layout,
-//                 fence.proxy.async, RHS accumulation
-//   warps 8-11 /  two epilogue+solver warpgroups (one per TMEM accumulator buffer):
-//   warps 12-15   tcgen05.ld of row i of A into registers, + lambda*n_u, 6-step CG with
-//                 named-barrier reductions, x written back; chunks of split rows store
+//   warps 4-11    staging: fp32 tile -> (hi | lo') fp16 K-major core-matrix layout (each half
+//                 of the warps converts 8 of the 16 gathered rows), fence.proxy.async, RHS
+//                 accumulation
+//   warps 12-15   epilogue + solver warpgroup: tcgen05.ld of row i of A into registers (the two
+//                 TMEM accumulators are drained every <= 64 k-steps and summed in fp32, which
+//                 bounds the tensor core's truncating accumulation chain), + lambda*n_u, 6-step
+//                 CG with named-barrier reductions, x written back; chunks of split rows store
 //                 their partial [A|b] instead (reduced + solved by the unfused kernels).
 #include "common.cuh"
 
@@ -60,11 +62,14 @@ constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 7680
 constexpr int IDX_RING = 2048;            // prefetched colidx / val window (ratings)
 constexpr int IDX_BATCH = 256;            // ratings per cp.async group
 constexpr int IDX_GROUPS = 4;             // groups kept in flight
-constexpr int CHUNK_RING = 128;
 constexpr int NUM_THREADS = 512;
 constexpr int PROD_WARPS = 3;             // producer warps (warp ids 0..2)
 constexpr int MMA_WARP = 3;
-constexpr int PROD_BAR = 3;               // named barrier id of the producer warps (1, 2: solver warpgroups)
+constexpr int PROD_BAR = 3;               // named barrier id of the producer warps (1: solver warpgroup)
+constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
+constexpr int STAGE_WARPS = 8;
+constexpr int FIRST_EPI_WARP = 12;        // warps 12..15: epilogue + solver
+constexpr int SUB_STEPS = 64;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;             // column stride between the two accumulators
 constexpr int N1 = 2 * FP;                // 224: [hi | lo'] as B operand
@@ -73,7 +78,8 @@ constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
 constexpr double kCgError = 1e-4;         // cg.cu:31
 
-constexpr uint32_t FLAG_FIRST = 1u, FLAG_LAST = 2u;
+// stage flags: chunk = one row (or one piece of a split row); sub = one TMEM accumulation tile
+constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST = 4u, FLAG_SUB_LAST = 8u;
 
 struct StageMeta {   // written by the producer (f32 ring) / staging warps (operand ring)
     uint32_t ring_off;   // offset of the stage's first rating in the idx/val rings
@@ -87,13 +93,11 @@ struct __align__(128) Smem {
     unsigned char op_stage[S2][OP_STAGE_BYTES];     // 30720
     int idx_ring[IDX_RING];
     float val_ring[IDX_RING];
-    Chunk chunk_ring[CHUNK_RING];
     StageMeta meta_f32[S1];
     StageMeta meta_op[S2];
-    Chunk acc_chunk[2];
-    float bsm[2][FP];
-    float sp[2][128];            // CG direction vector per solver warpgroup
-    float red[2][3][4];          // cross-warp partial sums
+    float bsm[2][2][FP];         // [buffer][k-half][feature] partial RHS
+    float sp[128];               // CG direction vector
+    float red[3][4];             // cross-warp partial sums
     unsigned long long full_f32[S1], empty_f32[S1], full_op[S2], empty_op[S2];
     unsigned long long acc_full[2], acc_empty[2], b_full[2], b_empty[2];
     uint32_t tmem_base;
@@ -195,7 +199,7 @@ struct Ring {   // stage index + phase bit of an mbarrier ring
     __device__ void next() { if (++s == n) { s = 0; ph ^= 1u; } }
 };
 
-// ---- solver warpgroup: fp32 CG with A row i in registers (cg.cu:36-231) ---------------------
+// ---- solver warpgroup helpers ---------------------------------------------------------------
 __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, int lane, int bar_id) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -223,11 +227,11 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], 4); }
-        for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], 4); mbar_init(&sm.empty_op[s], 1); }
+        for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], STAGE_WARPS); }
+        for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], STAGE_WARPS); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm.acc_full[b], 1); mbar_init(&sm.acc_empty[b], 4);
-            mbar_init(&sm.b_full[b], 4);   mbar_init(&sm.b_empty[b], 4);
+            mbar_init(&sm.acc_full[b], 1);          mbar_init(&sm.acc_empty[b], 4);
+            mbar_init(&sm.b_full[b], STAGE_WARPS);  mbar_init(&sm.b_empty[b], 4);
         }
         fence_mbar_init();
     }
@@ -246,7 +250,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             int fetched = pos0;       // next rating to prefetch
             int ready = pos0;         // ratings [pos0, ready) are in the rings
             int groups_in_flight = 0;
-            // every producer warp replays the same bookkeeping; only warp 0 moves the data
+            // every producer warp replays the same bookkeeping; only warp 0 moves the index data
             auto prefetch = [&]() {
                 if (warp == 0) {
 #pragma unroll
@@ -270,19 +274,17 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             for (int cb = c_begin; cb < c_end; cb += 32) {
                 const Chunk my_ck = next_ck;
                 if (cb + 32 + lane < c_end) next_ck = chunks[cb + 32 + lane];     // register prefetch of the next 32
-                if (warp == 0 && cb + lane < c_end) sm.chunk_ring[(cb - c_begin + lane) & (CHUNK_RING - 1)] = my_ck;
-                __syncwarp();
                 const int nb = min(32, c_end - cb);
                 for (int ci = 0; ci < nb; ++ci) {
                     const int cend = __shfl_sync(0xffffffffu, my_ck.end, ci);
-                    const uint32_t slot = (uint32_t)((cb - c_begin + ci) & (CHUNK_RING - 1));
-                    bool first = true;
+                    const uint32_t slot = (uint32_t)(cb - c_begin + ci);
+                    bool chunk_first = true;
+                    int sub_steps = 0;       // k-steps accumulated into the current TMEM tile
                     do {   // at least one (possibly empty) stage per chunk
                         const int cnt = min(KT, cend - pos);
                         // make sure the indices of this stage have landed in the ring
                         while (pos + cnt > ready) {
-                            // oldest group complete <=> at most (groups_in_flight-1) pending
-                            if (warp == 0) {
+                            if (warp == 0) {   // oldest group complete <=> at most (groups_in_flight-1) pending
                                 if (groups_in_flight >= 4) cp_async_wait<3>();
                                 else if (groups_in_flight == 3) cp_async_wait<2>();
                                 else if (groups_in_flight == 2) cp_async_wait<1>();
@@ -294,10 +296,13 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                             if (fetched < pos_end) prefetch();
                         }
                         mbar_wait(&sm.empty_f32[st.s], st.ph ^ 1u);
-                        const bool last = (pos + cnt >= cend);
+                        const bool chunk_last = (pos + cnt >= cend);
+                        const bool sub_first = (sub_steps == 0);
+                        const bool sub_last = chunk_last || (sub_steps + 1 == SUB_STEPS);
                         if (warp == 0 && lane == 0) {
                             sm.meta_f32[st.s] = StageMeta{(uint32_t)((pos - pos0) & (IDX_RING - 1)), (uint32_t)cnt, slot,
-                                                          (first ? FLAG_FIRST : 0u) | (last ? FLAG_LAST : 0u)};
+                                                          (chunk_first ? FLAG_CHUNK_FIRST : 0u) | (chunk_last ? FLAG_CHUNK_LAST : 0u) |
+                                                          (sub_first ? FLAG_SUB_FIRST : 0u) | (sub_last ? FLAG_SUB_LAST : 0u)};
                             // the single pending arrival keeps the phase open until this executes, so
                             // complete_tx from the other warps' rows may land before or after it
                             mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)cnt * ROW_BYTES);
@@ -309,142 +314,170 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                                         &sm.full_f32[st.s]);
                         }
                         pos += cnt;
-                        first = false;
+                        chunk_first = false;
+                        sub_steps = sub_last ? 0 : sub_steps + 1;
                         st.next();
                     } while (pos < cend);
                 }
             }
-            cp_async_wait<0>();
+            if (warp == 0) cp_async_wait<0>();
         } else if (warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
             if (lane == 0) {
                 constexpr uint32_t idesc1 = make_idesc(128, N1);
                 constexpr uint32_t idesc2 = make_idesc(128, N2);
                 Ring op(S2);
-                int q = 0;
-                while (q < n_chunks) {
+                int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
+                int done = 0;           // chunks finished
+                while (done < n_chunks) {
                     mbar_wait(&sm.full_op[op.s], op.ph);
                     const uint32_t flags = sm.meta_op[op.s].flags;
                     const int buf = q & 1;
-                    if (flags & FLAG_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                    if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t base = smem_u32(&sm.op_stage[op.s][0]);
-                    const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                   // rows 0.. : hi (| lo')
-                    const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);       // rows 112.. : lo'
+                    const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                  // rows 0.. : hi (| lo')
+                    const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);      // rows 112.. : lo'
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
                     // cols [0,112): hi^T hi ; cols [112,224): hi^T lo'
-                    umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_FIRST) ? 0u : 1u);
+                    umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
                     // cols [112,224) += lo'^T hi
                     umma_f16(d_tmem + FP, d_lo, d_hi, idesc2, 1u);
                     umma_commit(&sm.empty_op[op.s]);          // operand stage reusable once both MMAs retire
-                    if (flags & FLAG_LAST) { umma_commit(&sm.acc_full[buf]); ++q; }
+                    if (flags & FLAG_SUB_LAST) { umma_commit(&sm.acc_full[buf]); ++q; }
+                    if (flags & FLAG_CHUNK_LAST) ++done;
                     op.next();
                 }
             }
             __syncwarp();
-        } else if (warp < 8) {
+        } else if (warp < FIRST_EPI_WARP) {
             // ================================ staging warps =====================================
-            const int t = tid - 128;                  // feature handled by this thread
+            // 8 warps: half h of them converts gathered rows [8h, 8h+8) of every stage, thread t one feature
+            const int sw = warp - FIRST_STAGE_WARP;
+            const int h = sw >> 2;
+            const int t = (sw & 3) * 32 + lane;        // feature handled by this thread
             const bool active = t < F;
-            const int wl = lane;
             Ring st(S1), op(S2);
-            int q = 0;
+            int done = 0;
             float bacc = 0.f;
             const int g = t >> 3, r8 = t & 7;
-            while (q < n_chunks) {
+            while (done < n_chunks) {
                 mbar_wait(&sm.full_f32[st.s], st.ph);
                 const StageMeta meta = sm.meta_f32[st.s];
                 mbar_wait(&sm.empty_op[op.s], op.ph ^ 1u);
-                if (meta.flags & FLAG_FIRST) bacc = 0.f;
+                if (meta.flags & FLAG_CHUNK_FIRST) bacc = 0.f;
                 if (active) {
-                    const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t;
-                    uint32_t hi2[8], lo2[8];
+                    const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t + h * 8 * F;
+                    const uint32_t k0 = (uint32_t)(h * 8);
+                    float v[8], r[8];
 #pragma unroll
-                    for (int k = 0; k < KT; k += 2) {
-                        float v0 = 0.f, v1 = 0.f, r0 = 0.f, r1 = 0.f;
-                        if ((uint32_t)k < meta.cnt) { v0 = src[k * F]; r0 = sm.val_ring[(meta.ring_off + k) & (IDX_RING - 1)]; }
-                        if ((uint32_t)(k + 1) < meta.cnt) { v1 = src[(k + 1) * F]; r1 = sm.val_ring[(meta.ring_off + k + 1) & (IDX_RING - 1)]; }
-                        bacc = fmaf(r0, v0, bacc);          // b_u += r_uj * theta_j[t], CSR order (als.cu:750)
-                        bacc = fmaf(r1, v1, bacc);
-                        const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);
-                        const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+                    for (int k = 0; k < 8; ++k) {
+                        const bool ok = (k0 + k) < meta.cnt;
+                        v[k] = ok ? src[k * F] : 0.f;
+                        r[k] = ok ? sm.val_ring[(meta.ring_off + k0 + k) & (IDX_RING - 1)] : 0.f;
+                    }
+                    uint32_t hi2[4], lo2[4];
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2) {
+                        bacc = fmaf(r[k], v[k], bacc);          // b_u += r_uj * theta_j[t] (als.cu:750)
+                        bacc = fmaf(r[k + 1], v[k + 1], bacc);
+                        const float h0 = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
+                        const float h1 = __uint_as_float(__float_as_uint(v[k + 1]) & 0xFFFFE000u);
                         const __half2 hh = __floats2half2_rn(h0, h1);                       // exact
-                        const __half2 ll = __floats2half2_rn((v0 - h0) * kLoScale, (v1 - h1) * kLoScale);
+                        const __half2 ll = __floats2half2_rn((v[k] - h0) * kLoScale, (v[k + 1] - h1) * kLoScale);
                         hi2[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
                         lo2[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    unsigned char* ob = &sm.op_stage[op.s][0];
-                    uint4* hi_dst = reinterpret_cast<uint4*>(ob + g * OP_GROUP_BYTES + r8 * 16);
-                    uint4* lo_dst = reinterpret_cast<uint4*>(ob + (FP / 8 + g) * OP_GROUP_BYTES + r8 * 16);
-                    hi_dst[0] = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);                       // k 0..7
-                    hi_dst[OP_KCORE_BYTES / 16] = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);     // k 8..15
-                    lo_dst[0] = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-                    lo_dst[OP_KCORE_BYTES / 16] = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+                    unsigned char* ob = &sm.op_stage[op.s][0] + h * OP_KCORE_BYTES + r8 * 16;
+                    *reinterpret_cast<uint4*>(ob + g * OP_GROUP_BYTES) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+                    *reinterpret_cast<uint4*>(ob + (FP / 8 + g) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
                 }
-                if (t == 0) sm.meta_op[op.s] = meta;
+                if (sw == 0 && lane == 0) sm.meta_op[op.s] = meta;
                 fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
-                if (wl == 0) {
+                if (lane == 0) {
                     mbar_arrive(&sm.full_op[op.s]);
                     mbar_arrive(&sm.empty_f32[st.s]);
                 }
-                if (meta.flags & FLAG_LAST) {
-                    const int buf = q & 1;
-                    mbar_wait(&sm.b_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
-                    if (active) sm.bsm[buf][t] = bacc;
-                    if (t == 0) sm.acc_chunk[buf] = sm.chunk_ring[meta.chunk_slot];
+                if (meta.flags & FLAG_CHUNK_LAST) {
+                    const int buf = done & 1;
+                    mbar_wait(&sm.b_empty[buf], (((uint32_t)done >> 1) & 1u) ^ 1u);
+                    if (active) sm.bsm[buf][h][t] = bacc;
                     __syncwarp();
-                    if (wl == 0) mbar_arrive(&sm.b_full[buf]);
-                    ++q;
+                    if (lane == 0) mbar_arrive(&sm.b_full[buf]);
+                    ++done;
                 }
                 st.next();
                 op.next();
             }
         } else {
-            // ========================= epilogue + solver warpgroups =============================
-            const int wg = (warp - 8) >> 2;               // 0: warps 8-11, 1: warps 12-15
+            // ========================= epilogue + solver warpgroup ==============================
             const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
-            const int wiw = quad;                         // warp index inside the warpgroup
             const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
             const bool active = i < F;
-            const int bar_id = 1 + wg;
-            float* sp = sm.sp[wg];
-            for (int q = wg; q < n_chunks; q += 2) {
-                const int buf = wg;
-                const uint32_t ph = ((uint32_t)q >> 1) & 1u;
-                mbar_wait(&sm.acc_full[buf], ph);
-                mbar_wait(&sm.b_full[buf], ph);
-                tc_fence_after();
-                const Chunk ck = sm.acc_chunk[buf];
-                const float bi = active ? sm.bsm[buf][i] : 0.f;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-                // row i of hi^T hi straight into the registers that will hold A, then fold in the
-                // cross terms 16 columns at a time (keeps the live temporaries at 16)
-                uint32_t au[F];
-#pragma unroll
-                for (int c = 0; c < 96; c += 16) tmem_ld16(taddr + c, reinterpret_cast<uint32_t(&)[16]>(au[c]));
-                tmem_ld4(taddr + 96, reinterpret_cast<uint32_t(&)[4]>(au[96]));
-                tmem_ld_wait();
+            constexpr int bar_id = 1;
+            float* sp = sm.sp;
+            // the order of tiles is dictated by the chunk list: walk it the same way the producers do
+            int q = 0;
+            Chunk ck_next = chunks[c_begin];
+            for (int c = c_begin; c < c_end; ++c) {
+                const Chunk ck = ck_next;
+                if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
+                const int steps = max(1, (ck.end - ck.begin + KT - 1) / KT);
+                const int tiles = (steps + SUB_STEPS - 1) / SUB_STEPS;
                 float a[F];
+                for (int tile = 0; tile < tiles; ++tile, ++q) {
+                    const int buf = q & 1;
+                    mbar_wait(&sm.acc_full[buf], ((uint32_t)q >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
+                    // this tile = hi^T hi + (hi^T lo' + lo'^T hi)/2048 over <= SUB_STEPS k-steps; tiles of one
+                    // chunk are summed here in fp32 (round-to-nearest), which bounds the length of the
+                    // tensor core's own (truncating) accumulation chain
+                    if (tile == 0) {
 #pragma unroll
-                for (int c = 0; c < 96; c += 16) {
-                    uint32_t s[16];
-                    tmem_ld16(taddr + FP + c, s);
-                    tmem_ld_wait();
+                        for (int cc = 0; cc < 96; cc += 16) {
+                            uint32_t p[16], s[16];
+                            tmem_ld16(taddr + cc, p);
+                            tmem_ld16(taddr + FP + cc, s);
+                            tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) a[c + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(au[c + j]));
+                            for (int j = 0; j < 16; ++j) a[cc + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+                        }
+                        uint32_t p[4], s[4];
+                        tmem_ld4(taddr + 96, p);
+                        tmem_ld4(taddr + FP + 96, s);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) a[96 + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+                    } else {
+#pragma unroll
+                        for (int cc = 0; cc < 96; cc += 16) {
+                            uint32_t p[16], s[16];
+                            tmem_ld16(taddr + cc, p);
+                            tmem_ld16(taddr + FP + cc, s);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) a[cc + j] += fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+                        }
+                        uint32_t p[4], s[4];
+                        tmem_ld4(taddr + 96, p);
+                        tmem_ld4(taddr + FP + 96, s);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) a[96 + j] += fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);       // accumulator drained
                 }
-                {
-                    uint32_t s[4];
-                    tmem_ld4(taddr + FP + 96, s);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) a[96 + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(au[96 + j]));
-                }
-                // accumulator and b buffer are drained: hand them back
-                tc_fence_before();
+                // the chunk's RHS from the staging warps (two half-sums per feature)
+                const int cidx = c - c_begin;
+                const int bb = cidx & 1;
+                mbar_wait(&sm.b_full[bb], ((uint32_t)cidx >> 1) & 1u);
+                const float bi = active ? sm.bsm[bb][0][i] + sm.bsm[bb][1][i] : 0.f;
                 __syncwarp();
-                if (lane == 0) { mbar_arrive(&sm.acc_empty[buf]); mbar_arrive(&sm.b_empty[buf]); }
+                if (lane == 0) mbar_arrive(&sm.b_empty[bb]);
 
                 if (ck.slot >= 0) {
                     // chunk of a row split across CTAs: store the partial [A | b]; reduced and solved later
@@ -456,7 +489,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     }
                     continue;
                 }
-                // weighted-lambda regularisation on the diagonal (als.cu:546): (end-start)*lambda
+                // weighted-lambda regularisation on the diagonal (als.cu:546): (end-start)*lambda, one FFMA
                 const float nu = (float)(ck.end - ck.begin);
 #pragma unroll
                 for (int j = 0; j < F; ++j) if (j == i) a[j] = fmaf(nu, lambda, a[j]);
@@ -464,15 +497,15 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 // ---- CG (cg.cu:47-230), A row i in registers, p broadcast from shared memory ----
                 float* xrow = out + (size_t)ck.row * F;
                 float xi = active ? xrow[i] : 0.f;
-                auto spmv = [&]() -> float {
-                    float y = 0.f;
+                auto spmv = [&]() -> float {   // four independent FMA chains (ILP), summed pairwise
+                    float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
                     for (int j = 0; j < F; j += 4) {
                         const float4 pv = *reinterpret_cast<const float4*>(sp + j);
-                        y = fmaf(a[j], pv.x, y); y = fmaf(a[j + 1], pv.y, y);
-                        y = fmaf(a[j + 2], pv.z, y); y = fmaf(a[j + 3], pv.w, y);
+                        y0 = fmaf(a[j], pv.x, y0); y1 = fmaf(a[j + 1], pv.y, y1);
+                        y2 = fmaf(a[j + 2], pv.z, y2); y3 = fmaf(a[j + 3], pv.w, y3);
                     }
-                    return y;
+                    return (y0 + y1) + (y2 + y3);
                 };
                 const float own = active ? 1.f : 0.f;
                 named_bar_sync(bar_id, 128);                       // previous row's readers of sp are done
@@ -480,17 +513,17 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 named_bar_sync(bar_id, 128);
                 float r = active ? bi - spmv() : 0.f;              // r = b - A x
                 float p = r;
-                float rsold = wg_sum(own * r * r, sm.red[wg][0], wiw, lane, bar_id);
+                float rsold = wg_sum(own * r * r, sm.red[0], quad, lane, bar_id);
                 for (int it = 0; (float)it < cg_iter; ++it) {
                     named_bar_sync(bar_id, 128);
                     if (active) sp[i] = p;
                     named_bar_sync(bar_id, 128);
                     const float ap = active ? spmv() : 0.f;
-                    const float pap = wg_sum(own * p * ap, sm.red[wg][1], wiw, lane, bar_id);
+                    const float pap = wg_sum(own * p * ap, sm.red[1], quad, lane, bar_id);
                     const float alpha = rsold / pap;               // cg.cu:128 (no guard)
                     xi = fmaf(alpha, p, xi);
                     r = fmaf(-alpha, ap, r);
-                    const float rsnew = wg_sum(own * r * r, sm.red[wg][2], wiw, lane, bar_id);
+                    const float rsnew = wg_sum(own * r * r, sm.red[2], quad, lane, bar_id);
                     if ((double)rsnew < kCgError) break;           // cg.cu:195
                     const float beta = rsnew / rsold;
                     rsold = rsnew;

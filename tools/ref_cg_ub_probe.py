@@ -57,5 +57,30 @@ def main():
               f"systems off by >1e-4: {(e > 1e-4).sum()} / {e.size}")
 
 
+def doals_repeat():
+    """Is the reference's own doALS (CG, f=100) reproducible run to run?  Its block sums add the
+    four warp partials with shared-memory atomicAdd in arrival order (device_utilities.h:36-48)."""
+    from cumf_als_b200.data import Ratings
+    sys.path.insert(0, str(ROOT / "tests" / "golden"))
+    from make_golden import CaptureStdout
+    g = dict(np.load(ROOT / "tests" / "golden" / "doals_f100.npz"))
+    m, n, f, lam, iters = int(g["m"]), int(g["n"]), int(g["f"]), float(g["lam"]), int(g["iters"])
+    r = Ratings(m=m, n=n, **{k: g[k] for k in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices",
+                                                "csc_data", "coo_row", "test_row", "test_col", "test_val")})
+    outs = []
+    for rep in range(4):
+        th, X = g["theta0"].copy(), np.zeros((m, f), np.float32)
+        with CaptureStdout():
+            fin = O.ref_do_als(r, th, X, f, lam, iters, 1, 1, "cg")
+        outs.append((fin, th, X))
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+    print("reference doALS (cg, f=100) repeated on identical inputs:")
+    for k in range(1, 4):
+        print(f"  run {k} vs run 0: final rmse {outs[k][0]:.7f} vs {outs[0][0]:.7f}; rel X {rel(outs[k][2], outs[0][2]):.2e} "
+              f"theta {rel(outs[k][1], outs[0][1]):.2e}")
+    print(f"  run 0 vs committed golden: rel X {rel(outs[0][2], g['x_cg']):.2e} theta {rel(outs[0][1], g['theta_cg']):.2e}")
+
+
 if __name__ == "__main__":
     main()
+    doals_repeat()

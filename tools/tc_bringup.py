@@ -50,7 +50,7 @@ def main():
             err = np.abs(tt[u] - ref[u]).max() / scale
             sym = np.abs(tt[u] - tt[u].T).max() / scale
             print(f"  row {u:2d} len {lengths[u]:5d}: max rel err {err:.3e}  asym {sym:.2e}  "
-                  f"rhs exact {np.array_equal(rhs[u], rhs_ref[u])}  nan {np.isnan(tt[u]).any()}")
+                  f"rhs err {np.abs(rhs[u] - rhs_ref[u]).max() / max(np.abs(rhs_ref[u]).max(), 1e-30):.1e}  nan {np.isnan(tt[u]).any()}")
         if np.nanmax(np.abs(tt - ref)) > 1e-2:
             u = 9
             print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", tt[u][0, :6])
