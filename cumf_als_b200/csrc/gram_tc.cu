@@ -20,7 +20,7 @@
 // interleaved partial sums per feature), and the CG is the fp32 register-resident solve of
 // cg.cu with identical semantics (cg.cu:47-230).
 //
-// CTA = 16 warps, persistent, one per SM, each owning a contiguous, cost-balanced range of
+// CTA = 20 warps (5 warpgroups with setmaxnreg budgets 56/72/72/152/152), persistent, one per SM, each owning a contiguous, cost-balanced range of
 // row chunks (so its ratings are one contiguous stream):
 //   warps 0-2     producers: warp 0 keeps a cp.async-prefetched window of colidx/val in
 //                 smem rings; all three issue one cp.async.bulk (TMA, SASS UBLKCP) per
@@ -33,7 +33,7 @@
 //   warps 4-11    staging: fp32 tile -> (hi | lo') fp16 K-major core-matrix layout (each half
 //                 of the warps converts 8 of the 16 gathered rows), fence.proxy.async, RHS
 //                 accumulation
-//   warps 12-15   epilogue + solver warpgroup: tcgen05.ld of row i of A into registers (the two
+//   warps 12-19   two epilogue + solver warpgroups (alternate chunks): tcgen05.ld of row i of A into registers (the two
 //                 TMEM accumulators are drained every <= 64 k-steps and summed in fp32, which
 //                 bounds the tensor core's truncating accumulation chain), + lambda*n_u, 6-step
 //                 CG with named-barrier reductions, x written back; chunks of split rows store
@@ -62,13 +62,14 @@ constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 7680
 constexpr int IDX_RING = 2048;            // prefetched colidx / val window (ratings)
 constexpr int IDX_BATCH = 256;            // ratings per cp.async group
 constexpr int IDX_GROUPS = 4;             // groups kept in flight
-constexpr int NUM_THREADS = 512;
+constexpr int NUM_THREADS = 640;          // 5 warpgroups: producers+MMA, 2 x staging, 2 x epilogue/solver
 constexpr int PROD_WARPS = 3;             // producer warps (warp ids 0..2)
 constexpr int MMA_WARP = 3;
 constexpr int PROD_BAR = 3;               // named barrier id of the producer warps (1: solver warpgroup)
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
 constexpr int STAGE_WARPS = 8;
-constexpr int FIRST_EPI_WARP = 12;        // warps 12..15: epilogue + solver
+constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
+constexpr int REGS_PROD = 56, REGS_STAGE = 72, REGS_EPI = 152;   // setmaxnreg budgets per warpgroup
 constexpr int SUB_STEPS = 64;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;             // column stride between the two accumulators
@@ -81,23 +82,23 @@ constexpr double kCgError = 1e-4;         // cg.cu:31
 // stage flags: chunk = one row (or one piece of a split row); sub = one TMEM accumulation tile
 constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST = 4u, FLAG_SUB_LAST = 8u;
 
-struct StageMeta {   // written by the producer (f32 ring) / staging warps (operand ring)
-    uint32_t ring_off;   // offset of the stage's first rating in the idx/val rings
+struct __align__(16) StageMeta {   // written by producer warp 0 for every fp32 stage
+    float vals[KT];      // the stage's ratings r_uj (zero beyond cnt)
     uint32_t cnt;        // valid gathered rows (0..16)
-    uint32_t chunk_slot; // index into chunk_ring
     uint32_t flags;
+    uint32_t pad[2];
 };
 
-struct __align__(128) Smem {
+struct __align__(128) Smem {   // dynamic shared memory, used in place
     unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 51200
     unsigned char op_stage[S2][OP_STAGE_BYTES];     // 30720
     int idx_ring[IDX_RING];
     float val_ring[IDX_RING];
     StageMeta meta_f32[S1];
-    StageMeta meta_op[S2];
+    uint32_t meta_op[S2];        // stage flags forwarded to the MMA warp
     float bsm[2][2][FP];         // [buffer][k-half][feature] partial RHS
-    float sp[128];               // CG direction vector
-    float red[3][4];             // cross-warp partial sums
+    float sp[2][128];            // CG direction vector per solver warpgroup
+    float red[2][3][4];          // cross-warp partial sums
     unsigned long long full_f32[S1], empty_f32[S1], full_op[S2], empty_op[S2];
     unsigned long long acc_full[2], acc_empty[2], b_full[2], b_empty[2];
     uint32_t tmem_base;
@@ -208,13 +209,44 @@ __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, in
     return (red4[0] + red4[1]) + (red4[2] + red4[3]);
 }
 
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// drain one TMEM accumulator tile (row i) into / onto the register copy of A
+template <bool kFirst>
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F]) {
+#pragma unroll
+    for (int cc = 0; cc < 96; cc += 16) {
+        uint32_t p[16], s[16];
+        tmem_ld16(taddr + cc, p);
+        tmem_ld16(taddr + FP + cc, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float v = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+            a[cc + j] = kFirst ? v : a[cc + j] + v;
+        }
+    }
+    uint32_t p[4], s[4];
+    tmem_ld4(taddr + 96, p);
+    tmem_ld4(taddr + FP + 96, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float v = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+        a[96 + j] = kFirst ? v : a[96 + j] + v;
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
                       const float* __restrict__ factor, float* __restrict__ out, float lambda, float cg_iter,
                       float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl) {
-    extern __shared__ unsigned char smem_raw[];
-    Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
+    // compiler keeps the shared address space and emits LDS/STS)
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -222,6 +254,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     const int n_chunks = c_end - c_begin;
 
     // ---- one-time setup --------------------------------------------------------------------
+    if ((smem_u32(smem_raw) & 127u) != 0u) __trap();     // TMA rows / UMMA descriptors need 16 B, be generous
     {   // zero the operand ring: padded feature rows and don't-care rows stay zero for ever
         uint4* p = reinterpret_cast<uint4*>(&sm.op_stage[0][0]);
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
@@ -242,8 +275,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    if (n_chunks > 0) {
-        if (warp < PROD_WARPS) {
+    // register budget per warpgroup (sum = 128 * (56 + 72 + 72 + 152 + 152) = 64512 <= 65536)
+    if (warp < 4) {
+        reg_dec<REGS_PROD>();
+        if (n_chunks > 0 && warp < PROD_WARPS) {
             // ================================ producers =========================================
             const int pos0 = chunks[c_begin].begin;
             const int pos_end = chunks[c_end - 1].end;
@@ -277,7 +312,6 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const int nb = min(32, c_end - cb);
                 for (int ci = 0; ci < nb; ++ci) {
                     const int cend = __shfl_sync(0xffffffffu, my_ck.end, ci);
-                    const uint32_t slot = (uint32_t)(cb - c_begin + ci);
                     bool chunk_first = true;
                     int sub_steps = 0;       // k-steps accumulated into the current TMEM tile
                     do {   // at least one (possibly empty) stage per chunk
@@ -299,13 +333,19 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                         const bool chunk_last = (pos + cnt >= cend);
                         const bool sub_first = (sub_steps == 0);
                         const bool sub_last = chunk_last || (sub_steps + 1 == SUB_STEPS);
-                        if (warp == 0 && lane == 0) {
-                            sm.meta_f32[st.s] = StageMeta{(uint32_t)((pos - pos0) & (IDX_RING - 1)), (uint32_t)cnt, slot,
-                                                          (chunk_first ? FLAG_CHUNK_FIRST : 0u) | (chunk_last ? FLAG_CHUNK_LAST : 0u) |
-                                                          (sub_first ? FLAG_SUB_FIRST : 0u) | (sub_last ? FLAG_SUB_LAST : 0u)};
+                        if (warp == 0) {
+                            // the stage's ratings, 16-byte aligned for the staging warps (zero beyond cnt)
+                            if (lane < KT)
+                                sm.meta_f32[st.s].vals[lane] = (lane < cnt) ? sm.val_ring[(pos - pos0 + lane) & (IDX_RING - 1)] : 0.f;
+                            if (lane == 0) {
+                                sm.meta_f32[st.s].cnt = (uint32_t)cnt;
+                                sm.meta_f32[st.s].flags = (chunk_first ? FLAG_CHUNK_FIRST : 0u) | (chunk_last ? FLAG_CHUNK_LAST : 0u) |
+                                                          (sub_first ? FLAG_SUB_FIRST : 0u) | (sub_last ? FLAG_SUB_LAST : 0u);
+                            }
+                            __syncwarp();
                             // the single pending arrival keeps the phase open until this executes, so
                             // complete_tx from the other warps' rows may land before or after it
-                            mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)cnt * ROW_BYTES);
+                            if (lane == 0) mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)cnt * ROW_BYTES);
                         }
                         const int row_in_stage = warp + PROD_WARPS * lane;     // rows interleaved over the producer warps
                         if (row_in_stage < cnt) {
@@ -321,7 +361,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 }
             }
             if (warp == 0) cp_async_wait<0>();
-        } else if (warp == MMA_WARP) {
+        } else if (n_chunks > 0 && warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
             if (lane == 0) {
                 constexpr uint32_t idesc1 = make_idesc(128, N1);
@@ -331,7 +371,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 int done = 0;           // chunks finished
                 while (done < n_chunks) {
                     mbar_wait(&sm.full_op[op.s], op.ph);
-                    const uint32_t flags = sm.meta_op[op.s].flags;
+                    const uint32_t flags = sm.meta_op[op.s];
                     const int buf = q & 1;
                     if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
                     tc_fence_after();
@@ -350,7 +390,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 }
             }
             __syncwarp();
-        } else if (warp < FIRST_EPI_WARP) {
+        }
+    } else if (warp < FIRST_EPI_WARP) {
+        reg_dec<REGS_STAGE>();
+        if (n_chunks > 0) {
             // ================================ staging warps =====================================
             // 8 warps: half h of them converts gathered rows [8h, 8h+8) of every stage, thread t one feature
             const int sw = warp - FIRST_STAGE_WARP;
@@ -363,18 +406,22 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             const int g = t >> 3, r8 = t & 7;
             while (done < n_chunks) {
                 mbar_wait(&sm.full_f32[st.s], st.ph);
-                const StageMeta meta = sm.meta_f32[st.s];
+                const uint32_t flags = sm.meta_f32[st.s].flags;
+                const uint32_t cnt = sm.meta_f32[st.s].cnt;
                 mbar_wait(&sm.empty_op[op.s], op.ph ^ 1u);
-                if (meta.flags & FLAG_CHUNK_FIRST) bacc = 0.f;
+                if (flags & FLAG_CHUNK_FIRST) bacc = 0.f;
                 if (active) {
                     const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t + h * 8 * F;
-                    const uint32_t k0 = (uint32_t)(h * 8);
-                    float v[8], r[8];
+                    const float4 r0 = *reinterpret_cast<const float4*>(&sm.meta_f32[st.s].vals[h * 8]);
+                    const float4 r1 = *reinterpret_cast<const float4*>(&sm.meta_f32[st.s].vals[h * 8 + 4]);
+                    const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    float v[8];
+                    if (cnt == KT) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const bool ok = (k0 + k) < meta.cnt;
-                        v[k] = ok ? src[k * F] : 0.f;
-                        r[k] = ok ? sm.val_ring[(meta.ring_off + k0 + k) & (IDX_RING - 1)] : 0.f;
+                        for (int k = 0; k < 8; ++k) v[k] = src[k * F];
+                    } else {            // ragged last stage of a chunk: rows beyond cnt were not written by the TMA
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = ((uint32_t)(h * 8 + k) < cnt) ? src[k * F] : 0.f;
                     }
                     uint32_t hi2[4], lo2[4];
 #pragma unroll
@@ -392,14 +439,14 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     *reinterpret_cast<uint4*>(ob + g * OP_GROUP_BYTES) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
                     *reinterpret_cast<uint4*>(ob + (FP / 8 + g) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
                 }
-                if (sw == 0 && lane == 0) sm.meta_op[op.s] = meta;
+                if (sw == 0 && lane == 0) sm.meta_op[op.s] = flags;
                 fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&sm.full_op[op.s]);
                     mbar_arrive(&sm.empty_f32[st.s]);
                 }
-                if (meta.flags & FLAG_CHUNK_LAST) {
+                if (flags & FLAG_CHUNK_LAST) {
                     const int buf = done & 1;
                     mbar_wait(&sm.b_empty[buf], (((uint32_t)done >> 1) & 1u) ^ 1u);
                     if (active) sm.bsm[buf][h][t] = bacc;
@@ -410,14 +457,18 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 st.next();
                 op.next();
             }
-        } else {
-            // ========================= epilogue + solver warpgroup ==============================
+        }
+    } else {
+        reg_inc<REGS_EPI>();
+        if (n_chunks > 0) {
+            // ========================= epilogue + solver warpgroups =============================
+            const int wg = (warp - FIRST_EPI_WARP) >> 2;  // this warpgroup takes chunks with (index & 1) == wg
             const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
             const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
             const bool active = i < F;
-            constexpr int bar_id = 1;
-            float* sp = sm.sp;
-            // the order of tiles is dictated by the chunk list: walk it the same way the producers do
+            const int bar_id = 1 + wg;
+            float* sp = sm.sp[wg];
+            // tiles appear in chunk-list order: both warpgroups walk the list, each drains only its chunks
             int q = 0;
             Chunk ck_next = chunks[c_begin];
             for (int c = c_begin; c < c_end; ++c) {
@@ -425,59 +476,28 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
                 const int steps = max(1, (ck.end - ck.begin + KT - 1) / KT);
                 const int tiles = (steps + SUB_STEPS - 1) / SUB_STEPS;
+                const int cidx = c - c_begin;
+                if ((cidx & 1) != wg) { q += tiles; continue; }
                 float a[F];
                 for (int tile = 0; tile < tiles; ++tile, ++q) {
                     const int buf = q & 1;
                     mbar_wait(&sm.acc_full[buf], ((uint32_t)q >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-                    // this tile = hi^T hi + (hi^T lo' + lo'^T hi)/2048 over <= SUB_STEPS k-steps; tiles of one
-                    // chunk are summed here in fp32 (round-to-nearest), which bounds the length of the
-                    // tensor core's own (truncating) accumulation chain
-                    if (tile == 0) {
-#pragma unroll
-                        for (int cc = 0; cc < 96; cc += 16) {
-                            uint32_t p[16], s[16];
-                            tmem_ld16(taddr + cc, p);
-                            tmem_ld16(taddr + FP + cc, s);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) a[cc + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
-                        }
-                        uint32_t p[4], s[4];
-                        tmem_ld4(taddr + 96, p);
-                        tmem_ld4(taddr + FP + 96, s);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) a[96 + j] = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
-                    } else {
-#pragma unroll
-                        for (int cc = 0; cc < 96; cc += 16) {
-                            uint32_t p[16], s[16];
-                            tmem_ld16(taddr + cc, p);
-                            tmem_ld16(taddr + FP + cc, s);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) a[cc + j] += fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
-                        }
-                        uint32_t p[4], s[4];
-                        tmem_ld4(taddr + 96, p);
-                        tmem_ld4(taddr + FP + 96, s);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) a[96 + j] += fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
-                    }
+                    // tile = hi^T hi + (hi^T lo' + lo'^T hi)/2048 over <= SUB_STEPS k-steps; the tiles of one chunk
+                    // are summed here in fp32 (round-to-nearest), which bounds the length of the tensor core's
+                    // own (truncating) accumulation chain
+                    if (tile == 0) drain_tile<true>(taddr, a);
+                    else drain_tile<false>(taddr, a);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);       // accumulator drained
                 }
-                // the chunk's RHS from the staging warps (two half-sums per feature)
-                const int cidx = c - c_begin;
-                const int bb = cidx & 1;
-                mbar_wait(&sm.b_full[bb], ((uint32_t)cidx >> 1) & 1u);
-                const float bi = active ? sm.bsm[bb][0][i] + sm.bsm[bb][1][i] : 0.f;
+                // the chunk's RHS from the staging warps (two half-sums per feature); buffer index == wg
+                mbar_wait(&sm.b_full[wg], ((uint32_t)cidx >> 1) & 1u);
+                const float bi = active ? sm.bsm[wg][0][i] + sm.bsm[wg][1][i] : 0.f;
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.b_empty[bb]);
+                if (lane == 0) mbar_arrive(&sm.b_empty[wg]);
 
                 if (ck.slot >= 0) {
                     // chunk of a row split across CTAs: store the partial [A | b]; reduced and solved later
@@ -513,17 +533,17 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 named_bar_sync(bar_id, 128);
                 float r = active ? bi - spmv() : 0.f;              // r = b - A x
                 float p = r;
-                float rsold = wg_sum(own * r * r, sm.red[0], quad, lane, bar_id);
+                float rsold = wg_sum(own * r * r, sm.red[wg][0], quad, lane, bar_id);
                 for (int it = 0; (float)it < cg_iter; ++it) {
                     named_bar_sync(bar_id, 128);
                     if (active) sp[i] = p;
                     named_bar_sync(bar_id, 128);
                     const float ap = active ? spmv() : 0.f;
-                    const float pap = wg_sum(own * p * ap, sm.red[1], quad, lane, bar_id);
+                    const float pap = wg_sum(own * p * ap, sm.red[wg][1], quad, lane, bar_id);
                     const float alpha = rsold / pap;               // cg.cu:128 (no guard)
                     xi = fmaf(alpha, p, xi);
                     r = fmaf(-alpha, ap, r);
-                    const float rsnew = wg_sum(own * r * r, sm.red[2], quad, lane, bar_id);
+                    const float rsnew = wg_sum(own * r * r, sm.red[wg][2], quad, lane, bar_id);
                     if ((double)rsnew < kCgError) break;           // cg.cu:195
                     const float beta = rsnew / rsold;
                     rsold = rsnew;
@@ -614,7 +634,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         return CUMF_EINVAL;
     }
     if (nchunks == 0) return CUMF_OK;
-    const size_t smem = sizeof(Smem) + 128;
+    const size_t smem = sizeof(Smem);
     static bool attr_set = false;
     if (!attr_set) {
         CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
