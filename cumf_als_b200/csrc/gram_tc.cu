@@ -20,7 +20,7 @@
 // interleaved partial sums per feature), and the CG is the fp32 register-resident solve of
 // cg.cu with identical semantics (cg.cu:47-230).
 //
-// CTA = 20 warps (5 warpgroups with setmaxnreg budgets 56/72/72/152/152), persistent, one per SM, each owning a contiguous, cost-balanced range of
+// CTA = 20 warps (5 warpgroups with setmaxnreg budgets 48/64/64/152/152), persistent, one per SM, each owning a contiguous, cost-balanced range of
 // row chunks (so its ratings are one contiguous stream):
 //   warps 0-2     producers: warp 0 keeps a cp.async-prefetched window of colidx/val in
 //                 smem rings; all three issue one cp.async.bulk (TMA, SASS UBLKCP) per
@@ -69,7 +69,10 @@ constexpr int PROD_BAR = 3;               // named barrier id of the producer wa
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
 constexpr int STAGE_WARPS = 8;
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
-constexpr int REGS_PROD = 56, REGS_STAGE = 72, REGS_EPI = 152;   // setmaxnreg budgets per warpgroup
+// setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
+// 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
+constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
+static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
 constexpr int SUB_STEPS = 64;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;             // column stride between the two accumulators
@@ -275,7 +278,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    // register budget per warpgroup (sum = 128 * (56 + 72 + 72 + 152 + 152) = 64512 <= 65536)
+    // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough)
     if (warp < 4) {
         reg_dec<REGS_PROD>();
         if (n_chunks > 0 && warp < PROD_WARPS) {
