@@ -103,7 +103,10 @@ struct __align__(128) Smem {   // dynamic shared memory, used in place
     float sp[2][128];            // CG direction vector per solver warpgroup
     float red[2][3][4];          // cross-warp partial sums
     unsigned long long full_f32[S1], empty_f32[S1], full_op[S2], empty_op[S2];
-    unsigned long long acc_full[2], acc_empty[2], b_full[2], b_empty[2];
+    // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
+    // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
+    // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
+    unsigned long long acc_full[2][2], acc_empty[2], b_full[2], b_empty[2];
     uint32_t tmem_base;
 };
 
@@ -266,7 +269,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], STAGE_WARPS); }
         for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], STAGE_WARPS); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm.acc_full[b], 1);          mbar_init(&sm.acc_empty[b], 4);
+            mbar_init(&sm.acc_full[0][b], 1); mbar_init(&sm.acc_full[1][b], 1); mbar_init(&sm.acc_empty[b], 4);
             mbar_init(&sm.b_full[b], STAGE_WARPS);  mbar_init(&sm.b_empty[b], 4);
         }
         fence_mbar_init();
@@ -387,7 +390,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     // cols [112,224) += lo'^T hi
                     umma_f16(d_tmem + FP, d_lo, d_hi, idesc2, 1u);
                     umma_commit(&sm.empty_op[op.s]);          // operand stage reusable once both MMAs retire
-                    if (flags & FLAG_SUB_LAST) { umma_commit(&sm.acc_full[buf]); ++q; }
+                    if (flags & FLAG_SUB_LAST) { umma_commit(&sm.acc_full[done & 1][buf]); ++q; }   // chunk `done` belongs to warpgroup done&1
                     if (flags & FLAG_CHUNK_LAST) ++done;
                     op.next();
                 }
@@ -473,6 +476,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             float* sp = sm.sp[wg];
             // tiles appear in chunk-list order: both warpgroups walk the list, each drains only its chunks
             int q = 0;
+            uint32_t seen0 = 0, seen1 = 0;                // tiles this warpgroup has taken from TMEM buffer 0 / 1
             Chunk ck_next = chunks[c_begin];
             for (int c = c_begin; c < c_end; ++c) {
                 const Chunk ck = ck_next;
@@ -484,7 +488,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 float a[F];
                 for (int tile = 0; tile < tiles; ++tile, ++q) {
                     const int buf = q & 1;
-                    mbar_wait(&sm.acc_full[buf], ((uint32_t)q >> 1) & 1u);
+                    if (buf == 0) { mbar_wait(&sm.acc_full[wg][0], seen0 & 1u); ++seen0; }
+                    else          { mbar_wait(&sm.acc_full[wg][1], seen1 & 1u); ++seen1; }
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
                     // tile = hi^T hi + (hi^T lo' + lo'^T hi)/2048 over <= SUB_STEPS k-steps; the tiles of one chunk

@@ -55,6 +55,26 @@ def main():
             u = 9
             print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", tt[u][0, :6])
             print("  row 9 ref[1,:6]", ref[u][1, :6], "\n  row 9 got[1,:6]", tt[u][1, :6])
+    elif which == "stress":
+        # many chunks per CTA (CUMF_TC_CTAS small), multi-tile rows, split rows: fused vs SIMT
+        rng = np.random.default_rng(7)
+        lens = [int(x) for x in rng.integers(1, 2600, 400)] + [0, 1, 9000, 20000]
+        rowptr, colidx, val = csr(rng, lens, 24000)
+        factor = (0.3 * rng.standard_normal((24000, f))).astype(np.float32)
+        x0 = (0.1 * rng.standard_normal((len(lens), f))).astype(np.float32)
+        outs = {}
+        for name, path in (("simt", c.PATH_SIMT), ("tc", c.PATH_TC)):
+            plan = c.Plan(rowptr, 0, len(lens), f, path)
+            x = dev(x0)
+            for _ in range(2):
+                c.update_factor(plan, dev(colidx), dev(val), dev(factor), x, lam)
+            torch.cuda.synchronize()
+            outs[name] = x.cpu().numpy()
+        a, b = outs["tc"].astype(np.float64), outs["simt"].astype(np.float64)
+        ok = np.isfinite(b).all(axis=1)
+        rows = np.linalg.norm(a[ok] - b[ok], axis=1) / np.maximum(np.linalg.norm(b[ok], axis=1), 1e-30)
+        print(f"stress CTAS={os.environ.get('CUMF_TC_CTAS')}: {len(lens)} rows, median row rel diff {np.median(rows):.2e}, max {rows.max():.2e}")
+        assert rows.max() < 1e-3, "fused and SIMT half-steps disagree"
     else:
         # one half-step through plans: fused vs SIMT
         x0 = (0.1 * rng.standard_normal((m, f))).astype(np.float32)
