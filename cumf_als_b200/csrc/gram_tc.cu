@@ -40,6 +40,7 @@
 //                 their partial [A|b] instead (reduced + solved by the unfused kernels).
 #include "common.cuh"
 
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -54,7 +55,10 @@ constexpr int KT = 16;                    // gathered rows per MMA k-step (fp16 
 constexpr int S1 = 8;                     // fp32 staging ring depth (8 x 6.4 KB in flight per SM)
 constexpr int S2 = 4;                     // fp16 operand ring depth
 constexpr int ROW_BYTES = F * 4;          // one factor row
-constexpr int STAGE_F32_BYTES = KT * ROW_BYTES;
+constexpr int GROUP_ROWS = 4;              // rows fetched by one TMA tile::gather4 instruction
+constexpr int GROUP_BYTES = 1664;         // 4 x 400 B padded to a multiple of 128 B (TMA destination alignment)
+constexpr int GROUP_FLOATS = GROUP_BYTES / 4;
+constexpr int STAGE_F32_BYTES = (KT / GROUP_ROWS) * GROUP_BYTES;   // 6656
 constexpr int OP_ROWS = 2 * FP + 16;      // hi rows [0,112), lo' rows [112,224), 16 don't-care rows
 constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B): SBO
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
@@ -73,7 +77,10 @@ constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue +
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
 constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
 static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
-constexpr int SUB_STEPS = 64;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
+constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained:
+                                          // the tensor core truncates when it accumulates (measured ~6e-8
+                                          // relative bias per k-step), so chains are kept short and the
+                                          // tiles are summed with round-to-nearest in registers
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COLS = 256;             // column stride between the two accumulators
 constexpr int N1 = 2 * FP;                // 224: [hi | lo'] as B operand
@@ -133,10 +140,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
-__device__ __forceinline__ void tma_row_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes,
+// TMA tile::gather4: four rows (row coordinates r0..r3, column coordinate 0) of the 2-D tensor described
+// by `tmap` (box {F, 1}) land back to back at smem_dst; complete_tx(4 * ROW_BYTES) on `bar`.
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* tmap, int r0, int r1, int r2, int r3,
                                             unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -247,7 +258,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F]) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
-                      const float* __restrict__ factor, float* __restrict__ out, float lambda, float cg_iter,
+                      const __grid_constant__ CUtensorMap factor_map, float* __restrict__ out, float lambda, float cg_iter,
                       float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl) {
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
@@ -350,14 +361,22 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                             }
                             __syncwarp();
                             // the single pending arrival keeps the phase open until this executes, so
-                            // complete_tx from the other warps' rows may land before or after it
-                            if (lane == 0) mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)cnt * ROW_BYTES);
-                        }
-                        const int row_in_stage = warp + PROD_WARPS * lane;     // rows interleaved over the producer warps
-                        if (row_in_stage < cnt) {
-                            const int col = sm.idx_ring[(pos - pos0 + row_in_stage) & (IDX_RING - 1)];
-                            tma_row_g2s(&sm.f32_stage[st.s][row_in_stage * ROW_BYTES], factor + (size_t)col * F, ROW_BYTES,
-                                        &sm.full_f32[st.s]);
+                            // complete_tx from the other warps' groups may land before or after it
+                            if (lane == 0)
+                                mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)((cnt + GROUP_ROWS - 1) / GROUP_ROWS) * GROUP_ROWS * ROW_BYTES);
+                        } else {
+                            // warps 1 and 2 issue the gathers: lane l of warp w fetches rows [4g, 4g+4), g = 2(w-1)+l.
+                            // Rows past cnt are fetched from row 0 and ignored by the staging warps.
+                            const int g4 = 2 * (warp - 1) + lane;
+                            if (lane < 2 && g4 * GROUP_ROWS < cnt) {
+                                const int base = pos - pos0 + g4 * GROUP_ROWS;
+                                int rr[GROUP_ROWS];
+#pragma unroll
+                                for (int j = 0; j < GROUP_ROWS; ++j)
+                                    rr[j] = (g4 * GROUP_ROWS + j < cnt) ? sm.idx_ring[(base + j) & (IDX_RING - 1)] : 0;
+                                tma_gather4(&sm.f32_stage[st.s][g4 * GROUP_BYTES], &factor_map, rr[0], rr[1], rr[2], rr[3],
+                                            &sm.full_f32[st.s]);
+                            }
                         }
                         pos += cnt;
                         chunk_first = false;
@@ -417,17 +436,18 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 mbar_wait(&sm.empty_op[op.s], op.ph ^ 1u);
                 if (flags & FLAG_CHUNK_FIRST) bacc = 0.f;
                 if (active) {
-                    const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t + h * 8 * F;
+                    // rows 8h..8h+7 of the stage = gather groups 2h and 2h+1 (4 rows of F floats each, padded)
+                    const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t + h * 2 * GROUP_FLOATS;
                     const float4 r0 = *reinterpret_cast<const float4*>(&sm.meta_f32[st.s].vals[h * 8]);
                     const float4 r1 = *reinterpret_cast<const float4*>(&sm.meta_f32[st.s].vals[h * 8 + 4]);
                     const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                     float v[8];
                     if (cnt == KT) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = src[k * F];
+                        for (int k = 0; k < 8; ++k) v[k] = src[(k >> 2) * GROUP_FLOATS + (k & 3) * F];
                     } else {            // ragged last stage of a chunk: rows beyond cnt were not written by the TMA
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = ((uint32_t)(h * 8 + k) < cnt) ? src[k * F] : 0.f;
+                        for (int k = 0; k < 8; ++k) v[k] = ((uint32_t)(h * 8 + k) < cnt) ? src[(k >> 2) * GROUP_FLOATS + (k & 3) * F] : 0.f;
                     }
                     uint32_t hi2[4], lo2[4];
 #pragma unroll
@@ -578,7 +598,40 @@ struct TcWork {
     DevBuf cta_ptr;
     int grid = 0;
     int nchunks = 0;
+    CUtensorMap factor_map;             // 2-D view [rows][F] fp32 of the opposing factor, box {F, 1}
+    const float* mapped_factor = nullptr;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            set_last_error("cuTensorMapEncodeTiled is not available from this driver");
+            return CUMF_ECUDA;
+        }
+        encode = (EncodeFn)fn;
+    }
+    // The row count only bounds the coordinates the hardware accepts; the gathered indices are CSR column ids
+    // of rows that exist, so a generous bound is safe.
+    const cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)1 << 31};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ROW_BYTES};
+    const cuuint32_t box[2] = {(cuuint32_t)F, 1u};      // tile::gather4 fetches four such boxes (tools/gather4_probe.cu)
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d_factor), gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)rc));
+        return CUMF_ECUDA;
+    }
+    return CUMF_OK;
+}
 
 bool tc_path_supports(int f) {
     const char* off = getenv("CUMF_DISABLE_TC");
@@ -648,9 +701,14 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
+    if (w->mapped_factor != d_factor) {
+        CUMF_REQUIRE((reinterpret_cast<uintptr_t>(d_factor) & 15u) == 0, "the factor matrix must be 16-byte aligned for TMA");
+        CUMF_TRY(encode_factor_map(&w->factor_map, d_factor));
+        w->mapped_factor = d_factor;
+    }
     const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
     const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
-    als_fused_f100_kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), d_colidx, d_val, d_factor,
+    als_fused_f100_kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), d_colidx, d_val, w->factor_map,
                                                             d_out, lambda, cg_iter, d_scratchA, d_scratchB, desc_tmpl);
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;
