@@ -1,6 +1,6 @@
 // gram_tc.cu -- the fused B200 half-step kernel:
-//   TMA row gather -> split-fp16 operand staging -> tcgen05.mma (accumulators in TMEM)
-//   -> epilogue straight into an in-register conjugate-gradient solve.
+//   TMA tile::gather4 row gather -> split-fp16 operand staging -> tcgen05.mma (accumulators in
+//   TMEM) -> epilogue straight into an in-register conjugate-gradient solve.
 // A_u is never written to HBM; per rating the kernel moves one f-wide fp32 factor row,
 // one int32 column index and one fp32 value (B_gram_fused).
 //
@@ -14,30 +14,29 @@
 // input mode, so every gathered fp32 value v is split as  v = hi + lo,
 //   hi = v with the low 13 mantissa bits cleared (exactly representable in fp16),
 //   lo' = fp16( (v - hi) * 2048 )                      (scaled so it stays a normal fp16)
-// and  A = hi^T hi + (hi^T lo' + lo'^T hi) / 2048  is accumulated in fp32 in TMEM with three
-// kind::f16 MMAs per 16 gathered rows (the dropped lo^T lo term is < 2^-20 relative).  The
-// RHS  b = sum r_uj theta_j  is accumulated with exact fp32 FMAs by the staging warps (two
-// interleaved partial sums per feature), and the CG is the fp32 register-resident solve of
-// cg.cu with identical semantics (cg.cu:47-230).
+// and  A = hi^T hi + (hi^T lo' + lo'^T hi) / 2048  is accumulated in fp32 in TMEM with
+// kind::f16 MMAs (the dropped lo^T lo term is < 2^-20 relative).  The ratings get the same
+// split and ride along as two extra operand rows, so  b = sum r_uj theta_j  comes out of the
+// same MMAs.  The tensor core truncates when it accumulates (measured ~6e-8 relative bias per
+// k-step): accumulation chains are cut every 16 k-steps and the tiles summed with
+// round-to-nearest in registers.  The CG is the fp32 register-resident solve of cg.cu with
+// identical semantics (cg.cu:47-230).
 //
-// CTA = 20 warps (5 warpgroups with setmaxnreg budgets 48/64/64/152/152), persistent, one per SM, each owning a contiguous, cost-balanced range of
-// row chunks (so its ratings are one contiguous stream):
-//   warps 0-2     producers: warp 0 keeps a cp.async-prefetched window of colidx/val in
-//                 smem rings; all three issue one cp.async.bulk (TMA, SASS UBLKCP) per
-//                 gathered 400-byte factor row into an 8-stage fp32 ring (rows of a stage
-//                 interleaved over the warps: UBLKCP takes uniform-register operands, so a
-//                 warp issues its rows one at a time), completion on mbarriers (expect_tx)
-//   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=224 and N=112,
-//                 K=16, smem descriptors (K-major, no swizzle); tcgen05.commit frees
-//                 operand stages / publishes accumulators; owns the TMEM allocation
-//   warps 4-11    staging: fp32 tile -> (hi | lo') fp16 K-major core-matrix layout (each half
-//                 of the warps converts 8 of the 16 gathered rows), fence.proxy.async, RHS
-//                 accumulation
-//   warps 12-19   two epilogue + solver warpgroups (alternate chunks): tcgen05.ld of row i of A into registers (the two
-//                 TMEM accumulators are drained every <= 64 k-steps and summed in fp32, which
-//                 bounds the tensor core's truncating accumulation chain), + lambda*n_u, 6-step
-//                 CG with named-barrier reductions, x written back; chunks of split rows store
-//                 their partial [A|b] instead (reduced + solved by the unfused kernels).
+// CTA = 20 warps (5 warpgroups, setmaxnreg budgets 48/64/64/152/152), persistent, one per SM, each
+// owning a contiguous, cost-balanced range of row chunks (so its ratings are one stream):
+//   warp 0        planner: keeps a cp.async-prefetched window of colidx/val in smem rings,
+//                 publishes per-stage metadata and the stage's ratings, arms the stage mbarrier
+//   warps 1-2     gather: one TMA tile::gather4 (SASS UTMALDG.2D.GATHER4) per 4 gathered factor
+//                 rows into an 8-stage fp32 ring, complete_tx on the stage mbarrier
+//   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=240 / 112 / 16, K=16,
+//                 smem descriptors (K-major, no swizzle); tcgen05.commit frees operand stages /
+//                 publishes accumulator tiles; owns the TMEM allocation
+//   warps 4-11    staging, one warp per stage (8 stages in flight): fp32 rows -> (hi | lo' | r)
+//                 fp16 K-major core-matrix layout, fence.proxy.async
+//   warps 12-19   two epilogue + solver warpgroups (alternate chunks): tcgen05.ld of row i of
+//                 [A | b] into registers, + lambda*n_u, 6-step CG with named-barrier reductions,
+//                 x written back; chunks of split rows store their partial [A|b] instead
+//                 (reduced + solved by the unfused kernels).
 #include "common.cuh"
 
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -52,47 +51,53 @@ namespace {
 constexpr int F = 100;                    // rank handled by this kernel
 constexpr int FP = 112;                   // rank padded to a multiple of 16 (UMMA N granularity at M=128)
 constexpr int KT = 16;                    // gathered rows per MMA k-step (fp16 UMMA K)
-constexpr int S1 = 8;                     // fp32 staging ring depth (8 x 6.4 KB in flight per SM)
-constexpr int S2 = 4;                     // fp16 operand ring depth
+constexpr int S1 = 8;                     // fp32 staging ring depth == number of staging warps
+constexpr int S2 = 8;                     // fp16 operand ring depth: one slot per staging warp (a parity wait
+                                          // needs a waiter that observes every phase of its barrier)
 constexpr int ROW_BYTES = F * 4;          // one factor row
-constexpr int GROUP_ROWS = 4;              // rows fetched by one TMA tile::gather4 instruction
+constexpr int GROUP_ROWS = 4;             // rows fetched by one TMA tile::gather4 instruction
 constexpr int GROUP_BYTES = 1664;         // 4 x 400 B padded to a multiple of 128 B (TMA destination alignment)
 constexpr int GROUP_FLOATS = GROUP_BYTES / 4;
 constexpr int STAGE_F32_BYTES = (KT / GROUP_ROWS) * GROUP_BYTES;   // 6656
-constexpr int OP_ROWS = 2 * FP + 16;      // hi rows [0,112), lo' rows [112,224), 16 don't-care rows
+// operand stage: rows [0,112) hi, [112,224) lo', 224 r_hi, 225 r_lo', [226,240) zero
+constexpr int OP_ROWS = 2 * FP + 16;
+constexpr int R_ROW = 2 * FP;             // 224
 constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B): SBO
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
 constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 7680
 constexpr int IDX_RING = 2048;            // prefetched colidx / val window (ratings)
 constexpr int IDX_BATCH = 256;            // ratings per cp.async group
 constexpr int IDX_GROUPS = 4;             // groups kept in flight
-constexpr int NUM_THREADS = 640;          // 5 warpgroups: producers+MMA, 2 x staging, 2 x epilogue/solver
-constexpr int PROD_WARPS = 3;             // producer warps (warp ids 0..2)
+constexpr int NUM_THREADS = 640;          // 5 warpgroups: planner+gather+MMA, 2 x staging, 2 x epilogue/solver
+constexpr int PROD_WARPS = 3;             // planner + 2 gather warps (warp ids 0..2)
 constexpr int MMA_WARP = 3;
-constexpr int PROD_BAR = 3;               // named barrier id of the producer warps (1: solver warpgroup)
+constexpr int PROD_BAR = 3;               // named barrier id of warps 0..2 (1, 2: solver warpgroups)
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
 constexpr int STAGE_WARPS = 8;
+static_assert(STAGE_WARPS == S1 && STAGE_WARPS == S2, "one staging warp per fp32 ring slot and per operand ring slot");
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
 // setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
 constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
 static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
-constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained:
-                                          // the tensor core truncates when it accumulates (measured ~6e-8
-                                          // relative bias per k-step), so chains are kept short and the
-                                          // tiles are summed with round-to-nearest in registers
+constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COLS = 256;             // column stride between the two accumulators
-constexpr int N1 = 2 * FP;                // 224: [hi | lo'] as B operand
-constexpr int N2 = FP;                    // 112: hi as B operand (lo' as A)
+constexpr int ACC_COLS = 256;             // columns per accumulator tile: [0,112) P, [112,224) S, 224.. b_hi, 240.. b_lo
+constexpr int N1 = OP_ROWS;               // 240: [hi | lo' | r] as B operand, A = hi
+constexpr int N2 = FP;                    // 112: hi as B operand, A = lo'
+constexpr int N3 = 16;                    // r rows as B operand, A = lo'
+constexpr int BCOL_HI = R_ROW;            // TMEM column of  hi^T r_hi  (next column: hi^T r_lo')
+constexpr int BCOL_LO = 240;              // TMEM column of  lo'^T r_hi
 constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
-constexpr double kCgError = 1e-4;         // cg.cu:31
+// cg.cu:31,195: `rsnew < 1e-4` compares in double.  For a float rsnew that is exactly
+// rsnew < nextafterf(1e-4f, +inf): the double 1e-4 lies strictly between two adjacent floats.
+constexpr float kCgErrorF = 1.00000005e-4f;
 
 // stage flags: chunk = one row (or one piece of a split row); sub = one TMEM accumulation tile
 constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST = 4u, FLAG_SUB_LAST = 8u;
 
-struct __align__(16) StageMeta {   // written by producer warp 0 for every fp32 stage
+struct __align__(16) StageMeta {   // written by the planner for every fp32 stage
     float vals[KT];      // the stage's ratings r_uj (zero beyond cnt)
     uint32_t cnt;        // valid gathered rows (0..16)
     uint32_t flags;
@@ -100,21 +105,21 @@ struct __align__(16) StageMeta {   // written by producer warp 0 for every fp32 
 };
 
 struct __align__(128) Smem {   // dynamic shared memory, used in place
-    unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 51200
+    unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 53248
     unsigned char op_stage[S2][OP_STAGE_BYTES];     // 30720
     int idx_ring[IDX_RING];
     float val_ring[IDX_RING];
     StageMeta meta_f32[S1];
     uint32_t meta_op[S2];        // stage flags forwarded to the MMA warp
-    float bsm[2][2][FP];         // [buffer][k-half][feature] partial RHS
-    float sp[2][128];            // CG direction vector per solver warpgroup
+    float sp[2][2][128];         // CG direction vector per solver warpgroup, double buffered
     float red[2][3][4];          // cross-warp partial sums
     unsigned long long full_f32[S1], empty_f32[S1], full_op[S2], empty_op[S2];
     // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
     // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
     // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
-    unsigned long long acc_full[2][2], acc_empty[2], b_full[2], b_empty[2];
+    unsigned long long acc_full[2][2], acc_empty[2];
     uint32_t tmem_base;
+    int total_stages;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -229,9 +234,9 @@ __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, in
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// drain one TMEM accumulator tile (row i) into / onto the register copy of A
+// drain one TMEM accumulator tile (row i of [P | S | b]) into / onto the register copy of [A | b]
 template <bool kFirst>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F]) {
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float& b) {
 #pragma unroll
     for (int cc = 0; cc < 96; cc += 16) {
         uint32_t p[16], s[16];
@@ -244,16 +249,22 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F]) {
             a[cc + j] = kFirst ? v : a[cc + j] + v;
         }
     }
-    uint32_t p[4], s[4];
+    uint32_t p[4], s[4], bh[4], bl[4];
     tmem_ld4(taddr + 96, p);
     tmem_ld4(taddr + FP + 96, s);
+    tmem_ld4(taddr + BCOL_HI, bh);      // hi^T r_hi, hi^T r_lo'
+    tmem_ld4(taddr + BCOL_LO, bl);      // lo'^T r_hi
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const float v = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
         a[96 + j] = kFirst ? v : a[96 + j] + v;
     }
+    const float tb = fmaf(__uint_as_float(bh[1]) + __uint_as_float(bl[0]), kLoInv, __uint_as_float(bh[0]));
+    b = kFirst ? tb : b + tb;
 }
+
+__device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + KT - 1) / KT); }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
@@ -271,19 +282,25 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     const int n_chunks = c_end - c_begin;
 
     // ---- one-time setup --------------------------------------------------------------------
-    if ((smem_u32(smem_raw) & 127u) != 0u) __trap();     // TMA rows / UMMA descriptors need 16 B, be generous
-    {   // zero the operand ring: padded feature rows and don't-care rows stay zero for ever
+    if ((smem_u32(smem_raw) & 127u) != 0u) __trap();     // TMA destinations need 128 B, UMMA descriptors 16 B
+    {   // zero the operand ring: padded feature rows and the spare rows stay zero for ever
         uint4* p = reinterpret_cast<uint4*>(&sm.op_stage[0][0]);
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], STAGE_WARPS); }
-        for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], STAGE_WARPS); mbar_init(&sm.empty_op[s], 1); }
+        for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], 1); }
+        for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sm.acc_full[0][b], 1); mbar_init(&sm.acc_full[1][b], 1); mbar_init(&sm.acc_empty[b], 4);
-            mbar_init(&sm.b_full[b], STAGE_WARPS);  mbar_init(&sm.b_empty[b], 4);
         }
+        sm.total_stages = 0;
         fence_mbar_init();
+    }
+    __syncthreads();
+    {   // number of k-steps (= stages) this CTA will run: every role needs it to know when to stop
+        int local = 0;
+        for (int c = c_begin + tid; c < c_end; c += NUM_THREADS) local += chunk_steps(chunks[c]);
+        if (local) atomicAdd(&sm.total_stages, local);
     }
     if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, TMEM_COLS);
     fence_proxy_async();      // the zero fill above must be visible to the tensor-core (async) proxy
@@ -291,18 +308,19 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+    const int total_stages = sm.total_stages;
 
     // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough)
     if (warp < 4) {
         reg_dec<REGS_PROD>();
         if (n_chunks > 0 && warp < PROD_WARPS) {
-            // ================================ producers =========================================
+            // ========================= planner (warp 0) + gather warps (1, 2) ====================
             const int pos0 = chunks[c_begin].begin;
             const int pos_end = chunks[c_end - 1].end;
             int fetched = pos0;       // next rating to prefetch
             int ready = pos0;         // ratings [pos0, ready) are in the rings
             int groups_in_flight = 0;
-            // every producer warp replays the same bookkeeping; only warp 0 moves the index data
+            // the three warps replay the same bookkeeping; only warp 0 moves the index data
             auto prefetch = [&]() {
                 if (warp == 0) {
 #pragma unroll
@@ -342,7 +360,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                                 else cp_async_wait<0>();
                             }
                             --groups_in_flight;
-                            named_bar_sync(PROD_BAR, PROD_WARPS * 32);      // ring contents visible to all producers
+                            named_bar_sync(PROD_BAR, PROD_WARPS * 32);      // ring contents visible to all three warps
                             ready += IDX_BATCH;
                             if (fetched < pos_end) prefetch();
                         }
@@ -351,7 +369,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                         const bool sub_first = (sub_steps == 0);
                         const bool sub_last = chunk_last || (sub_steps + 1 == SUB_STEPS);
                         if (warp == 0) {
-                            // the stage's ratings, 16-byte aligned for the staging warps (zero beyond cnt)
+                            // the stage's ratings, 16-byte aligned for the staging warp (zero beyond cnt)
                             if (lane < KT)
                                 sm.meta_f32[st.s].vals[lane] = (lane < cnt) ? sm.val_ring[(pos - pos0 + lane) & (IDX_RING - 1)] : 0.f;
                             if (lane == 0) {
@@ -361,12 +379,12 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                             }
                             __syncwarp();
                             // the single pending arrival keeps the phase open until this executes, so
-                            // complete_tx from the other warps' groups may land before or after it
+                            // complete_tx from the gather warps may land before or after it
                             if (lane == 0)
                                 mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)((cnt + GROUP_ROWS - 1) / GROUP_ROWS) * GROUP_ROWS * ROW_BYTES);
                         } else {
-                            // warps 1 and 2 issue the gathers: lane l of warp w fetches rows [4g, 4g+4), g = 2(w-1)+l.
-                            // Rows past cnt are fetched from row 0 and ignored by the staging warps.
+                            // lane l of gather warp w fetches rows [4g, 4g+4) of the stage, g = 2(w-1)+l.
+                            // Rows past cnt are fetched from row 0 and ignored by the staging warp.
                             const int g4 = 2 * (warp - 1) + lane;
                             if (lane < 2 && g4 * GROUP_ROWS < cnt) {
                                 const int base = pos - pos0 + g4 * GROUP_ROWS;
@@ -391,27 +409,30 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             if (lane == 0) {
                 constexpr uint32_t idesc1 = make_idesc(128, N1);
                 constexpr uint32_t idesc2 = make_idesc(128, N2);
-                Ring op(S2);
+                constexpr uint32_t idesc3 = make_idesc(128, N3);
                 int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
                 int done = 0;           // chunks finished
-                while (done < n_chunks) {
-                    mbar_wait(&sm.full_op[op.s], op.ph);
-                    const uint32_t flags = sm.meta_op[op.s];
+                for (int n = 0; n < total_stages; ++n) {
+                    const int slot = n & (S2 - 1);
+                    mbar_wait(&sm.full_op[slot], ((uint32_t)n / S2) & 1u);
+                    const uint32_t flags = sm.meta_op[slot];
                     const int buf = q & 1;
                     if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(&sm.op_stage[op.s][0]);
-                    const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                  // rows 0.. : hi (| lo')
+                    const uint32_t base = smem_u32(&sm.op_stage[slot][0]);
+                    const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                  // rows 0..   : hi | lo' | r
                     const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);      // rows 112.. : lo'
+                    const uint64_t d_r = make_smem_desc(base + (R_ROW / 8) * OP_GROUP_BYTES, desc_tmpl);    // rows 224.. : r_hi, r_lo'
                     const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
-                    // cols [0,112): hi^T hi ; cols [112,224): hi^T lo'
+                    // cols [0,112): hi^T hi ; [112,224): hi^T lo' ; 224: hi^T r_hi ; 225: hi^T r_lo'
                     umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
                     // cols [112,224) += lo'^T hi
                     umma_f16(d_tmem + FP, d_lo, d_hi, idesc2, 1u);
-                    umma_commit(&sm.empty_op[op.s]);          // operand stage reusable once both MMAs retire
+                    // cols [240,256): lo'^T r_hi (only column 240 is used)
+                    umma_f16(d_tmem + BCOL_LO, d_lo, d_r, idesc3, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
+                    umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
                     if (flags & FLAG_SUB_LAST) { umma_commit(&sm.acc_full[done & 1][buf]); ++q; }   // chunk `done` belongs to warpgroup done&1
                     if (flags & FLAG_CHUNK_LAST) ++done;
-                    op.next();
                 }
             }
             __syncwarp();
@@ -419,69 +440,72 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     } else if (warp < FIRST_EPI_WARP) {
         reg_dec<REGS_STAGE>();
         if (n_chunks > 0) {
-            // ================================ staging warps =====================================
-            // 8 warps: half h of them converts gathered rows [8h, 8h+8) of every stage, thread t one feature
-            const int sw = warp - FIRST_STAGE_WARP;
-            const int h = sw >> 2;
-            const int t = (sw & 3) * 32 + lane;        // feature handled by this thread
-            const bool active = t < F;
-            Ring st(S1), op(S2);
-            int done = 0;
-            float bacc = 0.f;
-            const int g = t >> 3, r8 = t & 7;
-            while (done < n_chunks) {
-                mbar_wait(&sm.full_f32[st.s], st.ph);
-                const uint32_t flags = sm.meta_f32[st.s].flags;
-                const uint32_t cnt = sm.meta_f32[st.s].cnt;
-                mbar_wait(&sm.empty_op[op.s], op.ph ^ 1u);
-                if (flags & FLAG_CHUNK_FIRST) bacc = 0.f;
-                if (active) {
-                    // rows 8h..8h+7 of the stage = gather groups 2h and 2h+1 (4 rows of F floats each, padded)
-                    const float* src = reinterpret_cast<const float*>(&sm.f32_stage[st.s][0]) + t + h * 2 * GROUP_FLOATS;
-                    const float4 r0 = *reinterpret_cast<const float4*>(&sm.meta_f32[st.s].vals[h * 8]);
-                    const float4 r1 = *reinterpret_cast<const float4*>(&sm.meta_f32[st.s].vals[h * 8 + 4]);
-                    const float r[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                    float v[8];
-                    if (cnt == KT) {
+            // ======================= staging: one warp per stage, 8 stages in flight ===============
+            const int sw = warp - FIRST_STAGE_WARP;      // stage n is handled by warp n % 8 in ring slot n % 8
+            const unsigned char* fbase = &sm.f32_stage[sw][0];
+            unsigned char* obase = &sm.op_stage[sw][0];
+            for (int n = sw; n < total_stages; n += STAGE_WARPS) {
+                const uint32_t ph = ((uint32_t)n / STAGE_WARPS) & 1u;
+                mbar_wait(&sm.full_f32[sw], ph);
+                const uint32_t flags = sm.meta_f32[sw].flags;
+                const uint32_t cnt = sm.meta_f32[sw].cnt;
+                mbar_wait(&sm.empty_op[sw], ph ^ 1u);
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    const int c = lane + 32 * j;         // feature handled in this pass
+                    if (c < F) {
+                        const float* src = reinterpret_cast<const float*>(fbase) + c;
+                        float v[KT];
+                        if (cnt == KT) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = src[(k >> 2) * GROUP_FLOATS + (k & 3) * F];
-                    } else {            // ragged last stage of a chunk: rows beyond cnt were not written by the TMA
+                            for (int k = 0; k < KT; ++k) v[k] = src[(k >> 2) * GROUP_FLOATS + (k & 3) * F];
+                        } else {            // ragged last stage of a chunk: rows beyond cnt hold stale data
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = ((uint32_t)(h * 8 + k) < cnt) ? src[(k >> 2) * GROUP_FLOATS + (k & 3) * F] : 0.f;
+                            for (int k = 0; k < KT; ++k) v[k] = ((uint32_t)k < cnt) ? src[(k >> 2) * GROUP_FLOATS + (k & 3) * F] : 0.f;
+                        }
+                        uint32_t hi2[8], lo2[8];
+#pragma unroll
+                        for (int k = 0; k < KT; k += 2) {
+                            const float h0 = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
+                            const float h1 = __uint_as_float(__float_as_uint(v[k + 1]) & 0xFFFFE000u);
+                            const __half2 hh = __floats2half2_rn(h0, h1);                       // exact
+                            const __half2 ll = __floats2half2_rn((v[k] - h0) * kLoScale, (v[k + 1] - h1) * kLoScale);
+                            hi2[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+                            lo2[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+                        }
+                        unsigned char* ob = obase + (c >> 3) * OP_GROUP_BYTES + (c & 7) * 16;
+                        *reinterpret_cast<uint4*>(ob) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);                                   // k 0..7
+                        *reinterpret_cast<uint4*>(ob + OP_KCORE_BYTES) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);                  // k 8..15
+                        *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+                        *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
                     }
-                    uint32_t hi2[4], lo2[4];
+                }
+                if (lane == 31) {
+                    // the ratings ride along as operand rows 224 (r_hi) and 225 (r_lo'): b = sum r theta from the same MMAs
+                    uint32_t hi2[8], lo2[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k += 2) {
-                        bacc = fmaf(r[k], v[k], bacc);          // b_u += r_uj * theta_j[t] (als.cu:750)
-                        bacc = fmaf(r[k + 1], v[k + 1], bacc);
-                        const float h0 = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
-                        const float h1 = __uint_as_float(__float_as_uint(v[k + 1]) & 0xFFFFE000u);
-                        const __half2 hh = __floats2half2_rn(h0, h1);                       // exact
-                        const __half2 ll = __floats2half2_rn((v[k] - h0) * kLoScale, (v[k + 1] - h1) * kLoScale);
+                    for (int k = 0; k < KT; k += 2) {
+                        const float r0 = sm.meta_f32[sw].vals[k], r1 = sm.meta_f32[sw].vals[k + 1];
+                        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
+                        const float h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
+                        const __half2 hh = __floats2half2_rn(h0, h1);
+                        const __half2 ll = __floats2half2_rn((r0 - h0) * kLoScale, (r1 - h1) * kLoScale);
                         hi2[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
                         lo2[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    unsigned char* ob = &sm.op_stage[op.s][0] + h * OP_KCORE_BYTES + r8 * 16;
-                    *reinterpret_cast<uint4*>(ob + g * OP_GROUP_BYTES) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
-                    *reinterpret_cast<uint4*>(ob + (FP / 8 + g) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+                    unsigned char* ob = obase + (R_ROW / 8) * OP_GROUP_BYTES;
+                    *reinterpret_cast<uint4*>(ob) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
+                    *reinterpret_cast<uint4*>(ob + OP_KCORE_BYTES) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);
+                    *reinterpret_cast<uint4*>(ob + 16) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+                    *reinterpret_cast<uint4*>(ob + 16 + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
                 }
-                if (sw == 0 && lane == 0) sm.meta_op[op.s] = flags;
+                if (lane == 0) sm.meta_op[sw] = flags;
                 fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05.mma
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&sm.full_op[op.s]);
-                    mbar_arrive(&sm.empty_f32[st.s]);
+                    mbar_arrive(&sm.full_op[sw]);
+                    mbar_arrive(&sm.empty_f32[sw]);
                 }
-                if (flags & FLAG_CHUNK_LAST) {
-                    const int buf = done & 1;
-                    mbar_wait(&sm.b_empty[buf], (((uint32_t)done >> 1) & 1u) ^ 1u);
-                    if (active) sm.bsm[buf][h][t] = bacc;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.b_full[buf]);
-                    ++done;
-                }
-                st.next();
-                op.next();
             }
         }
     } else {
@@ -493,19 +517,18 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
             const bool active = i < F;
             const int bar_id = 1 + wg;
-            float* sp = sm.sp[wg];
             // tiles appear in chunk-list order: both warpgroups walk the list, each drains only its chunks
             int q = 0;
             uint32_t seen0 = 0, seen1 = 0;                // tiles this warpgroup has taken from TMEM buffer 0 / 1
+            uint32_t spb = 0;                             // which copy of sp the next broadcast uses
             Chunk ck_next = chunks[c_begin];
             for (int c = c_begin; c < c_end; ++c) {
                 const Chunk ck = ck_next;
                 if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
-                const int steps = max(1, (ck.end - ck.begin + KT - 1) / KT);
-                const int tiles = (steps + SUB_STEPS - 1) / SUB_STEPS;
-                const int cidx = c - c_begin;
-                if ((cidx & 1) != wg) { q += tiles; continue; }
+                const int tiles = (chunk_steps(ck) + SUB_STEPS - 1) / SUB_STEPS;
+                if (((c - c_begin) & 1) != wg) { q += tiles; continue; }
                 float a[F];
+                float bi = 0.f;
                 for (int tile = 0; tile < tiles; ++tile, ++q) {
                     const int buf = q & 1;
                     if (buf == 0) { mbar_wait(&sm.acc_full[wg][0], seen0 & 1u); ++seen0; }
@@ -515,17 +538,12 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     // tile = hi^T hi + (hi^T lo' + lo'^T hi)/2048 over <= SUB_STEPS k-steps; the tiles of one chunk
                     // are summed here in fp32 (round-to-nearest), which bounds the length of the tensor core's
                     // own (truncating) accumulation chain
-                    if (tile == 0) drain_tile<true>(taddr, a);
-                    else drain_tile<false>(taddr, a);
+                    if (tile == 0) drain_tile<true>(taddr, a, bi);
+                    else drain_tile<false>(taddr, a, bi);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);       // accumulator drained
                 }
-                // the chunk's RHS from the staging warps (two half-sums per feature); buffer index == wg
-                mbar_wait(&sm.b_full[wg], ((uint32_t)cidx >> 1) & 1u);
-                const float bi = active ? sm.bsm[wg][0][i] + sm.bsm[wg][1][i] : 0.f;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.b_empty[wg]);
 
                 if (ck.slot >= 0) {
                     // chunk of a row split across CTAs: store the partial [A | b]; reduced and solved later
@@ -537,15 +555,14 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     }
                     continue;
                 }
-                // weighted-lambda regularisation on the diagonal (als.cu:546): (end-start)*lambda, one FFMA
-                const float nu = (float)(ck.end - ck.begin);
-#pragma unroll
-                for (int j = 0; j < F; ++j) if (j == i) a[j] = fmaf(nu, lambda, a[j]);
+                // weighted-lambda regularisation (als.cu:546): A + (end-start)*lambda*I, applied inside the
+                // mat-vec as  (A p)_i + reg * p_i  (same real-number result, no 100-way register select)
+                const float reg = (float)(ck.end - ck.begin) * lambda;
 
                 // ---- CG (cg.cu:47-230), A row i in registers, p broadcast from shared memory ----
                 float* xrow = out + (size_t)ck.row * F;
                 float xi = active ? xrow[i] : 0.f;
-                auto spmv = [&]() -> float {   // four independent FMA chains (ILP), summed pairwise
+                auto spmv = [&](const float* sp, float self) -> float {   // four independent FMA chains, summed pairwise
                     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
                     for (int j = 0; j < F; j += 4) {
@@ -553,26 +570,28 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                         y0 = fmaf(a[j], pv.x, y0); y1 = fmaf(a[j + 1], pv.y, y1);
                         y2 = fmaf(a[j + 2], pv.z, y2); y3 = fmaf(a[j + 3], pv.w, y3);
                     }
-                    return (y0 + y1) + (y2 + y3);
+                    return fmaf(reg, self, (y0 + y1) + (y2 + y3));
                 };
                 const float own = active ? 1.f : 0.f;
-                named_bar_sync(bar_id, 128);                       // previous row's readers of sp are done
+                // sp is double buffered: a copy is rewritten only two broadcasts later, i.e. after at least one
+                // warpgroup barrier that every reader of the old contents has passed
+                float* sp = sm.sp[wg][spb]; spb ^= 1u;
                 if (active) sp[i] = xi;
                 named_bar_sync(bar_id, 128);
-                float r = active ? bi - spmv() : 0.f;              // r = b - A x
+                float r = active ? bi - spmv(sp, xi) : 0.f;        // r = b - A x
                 float p = r;
                 float rsold = wg_sum(own * r * r, sm.red[wg][0], quad, lane, bar_id);
                 for (int it = 0; (float)it < cg_iter; ++it) {
-                    named_bar_sync(bar_id, 128);
+                    sp = sm.sp[wg][spb]; spb ^= 1u;
                     if (active) sp[i] = p;
                     named_bar_sync(bar_id, 128);
-                    const float ap = active ? spmv() : 0.f;
+                    const float ap = active ? spmv(sp, p) : 0.f;
                     const float pap = wg_sum(own * p * ap, sm.red[wg][1], quad, lane, bar_id);
                     const float alpha = rsold / pap;               // cg.cu:128 (no guard)
                     xi = fmaf(alpha, p, xi);
                     r = fmaf(-alpha, ap, r);
                     const float rsnew = wg_sum(own * r * r, sm.red[wg][2], quad, lane, bar_id);
-                    if ((double)rsnew < kCgError) break;           // cg.cu:195
+                    if (rsnew < kCgErrorF) break;                  // cg.cu:195
                     const float beta = rsnew / rsold;
                     rsold = rsnew;
                     p = fmaf(beta, p, r);
