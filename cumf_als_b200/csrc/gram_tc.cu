@@ -51,7 +51,7 @@ namespace {
 constexpr int F = 100;                    // rank handled by this kernel
 constexpr int FP = 112;                   // rank padded to a multiple of 16 (UMMA N granularity at M=128)
 constexpr int KT = 16;                    // gathered rows per MMA k-step (fp16 UMMA K)
-constexpr int S1 = 8;                     // fp32 staging ring depth == number of staging warps
+constexpr int S1 = 16;                    // fp32 staging ring depth: 16 x 6.5 KB of gathered rows in flight per SM
 constexpr int S2 = 8;                     // fp16 operand ring depth: one slot per staging warp (a parity wait
                                           // needs a waiter that observes every phase of its barrier)
 constexpr int ROW_BYTES = F * 4;          // one factor row
@@ -74,7 +74,7 @@ constexpr int MMA_WARP = 3;
 constexpr int PROD_BAR = 3;               // named barrier id of warps 0..2 (1, 2: solver warpgroups)
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
 constexpr int STAGE_WARPS = 8;
-static_assert(STAGE_WARPS == S1 && STAGE_WARPS == S2, "one staging warp per fp32 ring slot and per operand ring slot");
+static_assert(S1 % STAGE_WARPS == 0 && STAGE_WARPS == S2, "every ring slot has exactly one staging warp as its consumer / producer");
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
 // setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
@@ -105,8 +105,8 @@ struct __align__(16) StageMeta {   // written by the planner for every fp32 stag
 };
 
 struct __align__(128) Smem {   // dynamic shared memory, used in place
-    unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 53248
-    unsigned char op_stage[S2][OP_STAGE_BYTES];     // 30720
+    unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 106496
+    unsigned char op_stage[S2][OP_STAGE_BYTES];     // 61440
     int idx_ring[IDX_RING];
     float val_ring[IDX_RING];
     StageMeta meta_f32[S1];
@@ -441,15 +441,16 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         reg_dec<REGS_STAGE>();
         if (n_chunks > 0) {
             // ======================= staging: one warp per stage, 8 stages in flight ===============
-            const int sw = warp - FIRST_STAGE_WARP;      // stage n is handled by warp n % 8 in ring slot n % 8
-            const unsigned char* fbase = &sm.f32_stage[sw][0];
+            // stage n is handled by warp n % 8: fp32 ring slot n % S1, operand ring slot n % 8 (its own)
+            const int sw = warp - FIRST_STAGE_WARP;
             unsigned char* obase = &sm.op_stage[sw][0];
             for (int n = sw; n < total_stages; n += STAGE_WARPS) {
-                const uint32_t ph = ((uint32_t)n / STAGE_WARPS) & 1u;
-                mbar_wait(&sm.full_f32[sw], ph);
-                const uint32_t flags = sm.meta_f32[sw].flags;
-                const uint32_t cnt = sm.meta_f32[sw].cnt;
-                mbar_wait(&sm.empty_op[sw], ph ^ 1u);
+                const int fs = n & (S1 - 1);
+                const unsigned char* fbase = &sm.f32_stage[fs][0];
+                mbar_wait(&sm.full_f32[fs], ((uint32_t)n / S1) & 1u);
+                const uint32_t flags = sm.meta_f32[fs].flags;
+                const uint32_t cnt = sm.meta_f32[fs].cnt;
+                mbar_wait(&sm.empty_op[sw], (((uint32_t)n / STAGE_WARPS) & 1u) ^ 1u);
 #pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
                     const int c = lane + 32 * j;         // feature handled in this pass
@@ -485,7 +486,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     uint32_t hi2[8], lo2[8];
 #pragma unroll
                     for (int k = 0; k < KT; k += 2) {
-                        const float r0 = sm.meta_f32[sw].vals[k], r1 = sm.meta_f32[sw].vals[k + 1];
+                        const float r0 = sm.meta_f32[fs].vals[k], r1 = sm.meta_f32[fs].vals[k + 1];
                         const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
                         const float h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
                         const __half2 hh = __floats2half2_rn(h0, h1);
@@ -504,7 +505,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(&sm.full_op[sw]);
-                    mbar_arrive(&sm.empty_f32[sw]);
+                    mbar_arrive(&sm.empty_f32[fs]);
                 }
             }
         }
