@@ -180,8 +180,10 @@ def run_ours(args, w):
     solver.set_factors(theta0, X0)
 
     if world > 1:
-        from cumf_als_b200.dist import ShardedAls
-        sharded = ShardedAls(solver, r, world, rank)
+        from cumf_als_b200.dist import GpuEngine, ShardedAls
+        x_ranges = nnz_balanced_ranges(r.csr_indptr, world)
+        t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
+        sharded = ShardedAls(GpuEngine(solver, local_rank), x_ranges, t_ranges, r.nnz, r.nnz_test)
         step = sharded.iterate
     else:
         step = lambda k: solver.iterate(k)

@@ -232,7 +232,7 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
         if (rc == CUMF_OK) rc = p->rhs.alloc(sizeof(float) * (size_t)f * p->batch_rows);
     }
     if (rc == CUMF_OK && path == CUMF_PATH_TC) {
-        rc = tc_plan_create(&p->tc, p->chunks, p->splits, owned, f);
+        rc = tc_plan_create(&p->tc, p->chunks, p->d_chunks.as<Chunk>(), p->splits, owned, f);
         // rows split across CTAs are reduced and solved through the materialised path
         if (rc == CUMF_OK && !p->splits.empty() && alloc_workspace) {
             p->batch_rows = (int)p->splits.size();

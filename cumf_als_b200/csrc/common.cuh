@@ -99,7 +99,7 @@ int sse_partial_capacity();
 // Fused tcgen05 path (gram_tc.cu).  Returns CUMF_EUNSUPPORTED when f is not handled.
 bool tc_path_supports(int f);
 struct TcWork;  // opaque per-plan state of the fused kernel
-int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const std::vector<SplitRow>& splits,
+int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* d_chunks, const std::vector<SplitRow>& splits,
                    int rows_total, int f);
 void tc_plan_destroy(TcWork* w);
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,

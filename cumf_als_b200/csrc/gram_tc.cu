@@ -24,15 +24,16 @@
 //
 // CTA = 20 warps (5 warpgroups, setmaxnreg budgets 48/64/64/152/152), persistent, one per SM, each
 // owning a contiguous, cost-balanced range of row chunks (so its ratings are one stream):
-//   warp 0        planner: keeps a cp.async-prefetched window of colidx/val in smem rings,
-//                 publishes per-stage metadata and the stage's ratings, arms the stage mbarrier
-//   warps 1-2     gather: one TMA tile::gather4 (SASS UTMALDG.2D.GATHER4) per 4 gathered factor
-//                 rows into an 8-stage fp32 ring, complete_tx on the stage mbarrier
+//   warps 0-2     idle (they only return their registers to the pool)
 //   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=240 / 112 / 16, K=16,
 //                 smem descriptors (K-major, no swizzle); tcgen05.commit frees operand stages /
 //                 publishes accumulator tiles; owns the TMEM allocation
-//   warps 4-11    staging, one warp per stage (8 stages in flight): fp32 rows -> (hi | lo' | r)
-//                 fp16 K-major core-matrix layout, fence.proxy.async
+//   warps 4-11    autonomous stage workers, one warp per stage, 16 stages of gathered rows in flight:
+//                 each warp reads its stages' descriptors from a precomputed stage table, prefetches
+//                 the 16 column indices / ratings, arms the stage mbarrier and issues four TMA
+//                 tile::gather4 (SASS UTMALDG.2D.GATHER4, 4 factor rows each) into its own ring slot,
+//                 later converts the landed fp32 rows -> (hi | lo' | r) fp16 in the UMMA K-major
+//                 core-matrix layout (fence.proxy.async) and re-arms the slot two stages ahead
 //   warps 12-19   two epilogue + solver warpgroups (alternate chunks): tcgen05.ld of row i of
 //                 [A | b] into registers, + lambda*n_u, 6-step CG with named-barrier reductions,
 //                 x written back; chunks of split rows store their partial [A|b] instead
@@ -65,20 +66,15 @@ constexpr int R_ROW = 2 * FP;             // 224
 constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B): SBO
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
 constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 7680
-constexpr int IDX_RING = 2048;            // prefetched colidx / val window (ratings)
-constexpr int IDX_BATCH = 256;            // ratings per cp.async group
-constexpr int IDX_GROUPS = 4;             // groups kept in flight
-constexpr int NUM_THREADS = 640;          // 5 warpgroups: planner+gather+MMA, 2 x staging, 2 x epilogue/solver
-constexpr int PROD_WARPS = 3;             // planner + 2 gather warps (warp ids 0..2)
+constexpr int NUM_THREADS = 640;          // 5 warpgroups: (idle x3 + MMA), 2 x stage workers, 2 x epilogue/solver
 constexpr int MMA_WARP = 3;
-constexpr int PROD_BAR = 3;               // named barrier id of warps 0..2 (1, 2: solver warpgroups)
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
 constexpr int STAGE_WARPS = 8;
 static_assert(S1 % STAGE_WARPS == 0 && STAGE_WARPS == S2, "every ring slot has exactly one staging warp as its consumer / producer");
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
 // setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
-constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
+constexpr int REGS_LAUNCH = 96, REGS_PROD = 24, REGS_STAGE = 72, REGS_EPI = 152;
 static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
@@ -97,29 +93,27 @@ constexpr float kCgErrorF = 1.00000005e-4f;
 // stage flags: chunk = one row (or one piece of a split row); sub = one TMEM accumulation tile
 constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST = 4u, FLAG_SUB_LAST = 8u;
 
-struct __align__(16) StageMeta {   // written by the planner for every fp32 stage
-    float vals[KT];      // the stage's ratings r_uj (zero beyond cnt)
-    uint32_t cnt;        // valid gathered rows (0..16)
-    uint32_t flags;
-    uint32_t pad[2];
+// One k-step of work: 16 (or fewer) consecutive ratings of one chunk.  Precomputed per plan
+// (stage table), so every stage worker warp is autonomous.
+struct StageDesc {
+    int pos;             // offset of the stage's first rating (relative to the plan's first rating)
+    uint32_t info;       // cnt (bits 0..7) | flags << 8
 };
+static_assert(sizeof(StageDesc) == 8, "StageDesc is loaded as one 8-byte word");
 
 struct __align__(128) Smem {   // dynamic shared memory, used in place
     unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 106496
     unsigned char op_stage[S2][OP_STAGE_BYTES];     // 61440
-    int idx_ring[IDX_RING];
-    float val_ring[IDX_RING];
-    StageMeta meta_f32[S1];
+    float stage_vals[S1][KT];    // the ratings of the stage in flight in each fp32 slot (zero beyond cnt)
     uint32_t meta_op[S2];        // stage flags forwarded to the MMA warp
     float sp[2][2][128];         // CG direction vector per solver warpgroup, double buffered
     float red[2][3][4];          // cross-warp partial sums
-    unsigned long long full_f32[S1], empty_f32[S1], full_op[S2], empty_op[S2];
+    unsigned long long full_f32[S1], full_op[S2], empty_op[S2];
     // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
     // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
     // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
     unsigned long long acc_full[2][2], acc_empty[2];
     uint32_t tmem_base;
-    int total_stages;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -154,11 +148,6 @@ __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* t
         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -214,14 +203,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct Ring {   // stage index + phase bit of an mbarrier ring
-    int s = 0;
-    uint32_t ph = 0;
-    int n;
-    __device__ explicit Ring(int n_) : n(n_) {}
-    __device__ void next() { if (++s == n) { s = 0; ph ^= 1u; } }
-};
-
 // ---- solver warpgroup helpers ---------------------------------------------------------------
 __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, int lane, int bar_id) {
 #pragma unroll
@@ -266,8 +247,28 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
 
 __device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + KT - 1) / KT); }
 
+// stage table of a plan: one StageDesc per k-step, in chunk order (built once per plan)
+__global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ chunk_stage_base,
+                                        int nchunks, StageDesc* __restrict__ table) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const Chunk ck = chunks[c];
+    const int steps = chunk_steps(ck);
+    StageDesc* out = table + chunk_stage_base[c];
+    for (int s = 0; s < steps; ++s) {
+        const int pos = ck.begin + s * KT;
+        const int cnt = max(0, min(KT, ck.end - pos));
+        const bool last = (s == steps - 1);
+        const uint32_t flags = (s == 0 ? FLAG_CHUNK_FIRST : 0u) | (last ? FLAG_CHUNK_LAST : 0u) |
+                               ((s % SUB_STEPS) == 0 ? FLAG_SUB_FIRST : 0u) |
+                               ((last || (s % SUB_STEPS) == SUB_STEPS - 1) ? FLAG_SUB_LAST : 0u);
+        out[s] = StageDesc{pos, (uint32_t)cnt | (flags << 8)};
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
+                      const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
                       const __grid_constant__ CUtensorMap factor_map, float* __restrict__ out, float lambda, float cg_iter,
                       float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl) {
@@ -280,6 +281,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     const int warp = tid >> 5, lane = tid & 31;
     const int c_begin = cta_chunk_ptr[blockIdx.x], c_end = cta_chunk_ptr[blockIdx.x + 1];
     const int n_chunks = c_end - c_begin;
+    const int s_begin = cta_stage_ptr[blockIdx.x];
+    const int total_stages = cta_stage_ptr[blockIdx.x + 1] - s_begin;
 
     // ---- one-time setup --------------------------------------------------------------------
     if ((smem_u32(smem_raw) & 127u) != 0u) __trap();     // TMA destinations need 128 B, UMMA descriptors 16 B
@@ -288,19 +291,12 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int s = 0; s < S1; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.empty_f32[s], 1); }
+        for (int s = 0; s < S1; ++s) mbar_init(&sm.full_f32[s], 1);
         for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&sm.acc_full[0][b], 1); mbar_init(&sm.acc_full[1][b], 1); mbar_init(&sm.acc_empty[b], 4);
         }
-        sm.total_stages = 0;
         fence_mbar_init();
-    }
-    __syncthreads();
-    {   // number of k-steps (= stages) this CTA will run: every role needs it to know when to stop
-        int local = 0;
-        for (int c = c_begin + tid; c < c_end; c += NUM_THREADS) local += chunk_steps(chunks[c]);
-        if (local) atomicAdd(&sm.total_stages, local);
     }
     if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, TMEM_COLS);
     fence_proxy_async();      // the zero fill above must be visible to the tensor-core (async) proxy
@@ -308,103 +304,11 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
-    const int total_stages = sm.total_stages;
 
     // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough)
     if (warp < 4) {
         reg_dec<REGS_PROD>();
-        if (n_chunks > 0 && warp < PROD_WARPS) {
-            // ========================= planner (warp 0) + gather warps (1, 2) ====================
-            const int pos0 = chunks[c_begin].begin;
-            const int pos_end = chunks[c_end - 1].end;
-            int fetched = pos0;       // next rating to prefetch
-            int ready = pos0;         // ratings [pos0, ready) are in the rings
-            int groups_in_flight = 0;
-            // the three warps replay the same bookkeeping; only warp 0 moves the index data
-            auto prefetch = [&]() {
-                if (warp == 0) {
-#pragma unroll
-                    for (int j = 0; j < IDX_BATCH / 32; ++j) {
-                        const int p = fetched + j * 32 + lane;
-                        if (p < pos_end) {
-                            cp_async_4(&sm.idx_ring[(p - pos0) & (IDX_RING - 1)], colidx + p);
-                            cp_async_4(&sm.val_ring[(p - pos0) & (IDX_RING - 1)], val + p);
-                        }
-                    }
-                    cp_async_commit();
-                }
-                fetched += IDX_BATCH;
-                ++groups_in_flight;
-            };
-            for (int g = 0; g < IDX_GROUPS; ++g) prefetch();
-
-            Ring st(S1);
-            Chunk next_ck = (c_begin + lane < c_end) ? chunks[c_begin + lane] : Chunk{0, 0, 0, -1};
-            int pos = pos0;
-            for (int cb = c_begin; cb < c_end; cb += 32) {
-                const Chunk my_ck = next_ck;
-                if (cb + 32 + lane < c_end) next_ck = chunks[cb + 32 + lane];     // register prefetch of the next 32
-                const int nb = min(32, c_end - cb);
-                for (int ci = 0; ci < nb; ++ci) {
-                    const int cend = __shfl_sync(0xffffffffu, my_ck.end, ci);
-                    bool chunk_first = true;
-                    int sub_steps = 0;       // k-steps accumulated into the current TMEM tile
-                    do {   // at least one (possibly empty) stage per chunk
-                        const int cnt = min(KT, cend - pos);
-                        // make sure the indices of this stage have landed in the ring
-                        while (pos + cnt > ready) {
-                            if (warp == 0) {   // oldest group complete <=> at most (groups_in_flight-1) pending
-                                if (groups_in_flight >= 4) cp_async_wait<3>();
-                                else if (groups_in_flight == 3) cp_async_wait<2>();
-                                else if (groups_in_flight == 2) cp_async_wait<1>();
-                                else cp_async_wait<0>();
-                            }
-                            --groups_in_flight;
-                            named_bar_sync(PROD_BAR, PROD_WARPS * 32);      // ring contents visible to all three warps
-                            ready += IDX_BATCH;
-                            if (fetched < pos_end) prefetch();
-                        }
-                        mbar_wait(&sm.empty_f32[st.s], st.ph ^ 1u);
-                        const bool chunk_last = (pos + cnt >= cend);
-                        const bool sub_first = (sub_steps == 0);
-                        const bool sub_last = chunk_last || (sub_steps + 1 == SUB_STEPS);
-                        if (warp == 0) {
-                            // the stage's ratings, 16-byte aligned for the staging warp (zero beyond cnt)
-                            if (lane < KT)
-                                sm.meta_f32[st.s].vals[lane] = (lane < cnt) ? sm.val_ring[(pos - pos0 + lane) & (IDX_RING - 1)] : 0.f;
-                            if (lane == 0) {
-                                sm.meta_f32[st.s].cnt = (uint32_t)cnt;
-                                sm.meta_f32[st.s].flags = (chunk_first ? FLAG_CHUNK_FIRST : 0u) | (chunk_last ? FLAG_CHUNK_LAST : 0u) |
-                                                          (sub_first ? FLAG_SUB_FIRST : 0u) | (sub_last ? FLAG_SUB_LAST : 0u);
-                            }
-                            __syncwarp();
-                            // the single pending arrival keeps the phase open until this executes, so
-                            // complete_tx from the gather warps may land before or after it
-                            if (lane == 0)
-                                mbar_arrive_expect_tx(&sm.full_f32[st.s], (uint32_t)((cnt + GROUP_ROWS - 1) / GROUP_ROWS) * GROUP_ROWS * ROW_BYTES);
-                        } else {
-                            // lane l of gather warp w fetches rows [4g, 4g+4) of the stage, g = 2(w-1)+l.
-                            // Rows past cnt are fetched from row 0 and ignored by the staging warp.
-                            const int g4 = 2 * (warp - 1) + lane;
-                            if (lane < 2 && g4 * GROUP_ROWS < cnt) {
-                                const int base = pos - pos0 + g4 * GROUP_ROWS;
-                                int rr[GROUP_ROWS];
-#pragma unroll
-                                for (int j = 0; j < GROUP_ROWS; ++j)
-                                    rr[j] = (g4 * GROUP_ROWS + j < cnt) ? sm.idx_ring[(base + j) & (IDX_RING - 1)] : 0;
-                                tma_gather4(&sm.f32_stage[st.s][g4 * GROUP_BYTES], &factor_map, rr[0], rr[1], rr[2], rr[3],
-                                            &sm.full_f32[st.s]);
-                            }
-                        }
-                        pos += cnt;
-                        chunk_first = false;
-                        sub_steps = sub_last ? 0 : sub_steps + 1;
-                        st.next();
-                    } while (pos < cend);
-                }
-            }
-            if (warp == 0) cp_async_wait<0>();
-        } else if (n_chunks > 0 && warp == MMA_WARP) {
+        if (n_chunks > 0 && warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
             if (lane == 0) {
                 constexpr uint32_t idesc1 = make_idesc(128, N1);
@@ -440,17 +344,61 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     } else if (warp < FIRST_EPI_WARP) {
         reg_dec<REGS_STAGE>();
         if (n_chunks > 0) {
-            // ======================= staging: one warp per stage, 8 stages in flight ===============
-            // stage n is handled by warp n % 8: fp32 ring slot n % S1, operand ring slot n % 8 (its own)
+            // ============ autonomous stage workers: warp w owns stages w, w+8, w+16, ... ===========
+            // own-stage t (global stage n = w + 8t) lives in fp32 slot w + 8(t&1) and operand slot w.
             const int sw = warp - FIRST_STAGE_WARP;
             unsigned char* obase = &sm.op_stage[sw][0];
-            for (int n = sw; n < total_stages; n += STAGE_WARPS) {
-                const int fs = n & (S1 - 1);
+            const int own = (total_stages > sw) ? (total_stages - sw + STAGE_WARPS - 1) / STAGE_WARPS : 0;
+            auto load_desc = [&](int t) -> StageDesc {
+                return (t < own) ? stage_tab[s_begin + sw + STAGE_WARPS * t] : StageDesc{0, 0u};
+            };
+            // lane k < 16 fetches column index and rating k of a stage (coalesced 64-byte reads)
+            auto load_idx = [&](const StageDesc& d) -> int {
+                return (lane < (int)(d.info & 0xffu)) ? __ldg(colidx + d.pos + lane) : 0;
+            };
+            auto load_val = [&](const StageDesc& d) -> float {
+                return (lane < (int)(d.info & 0xffu)) ? __ldg(val + d.pos + lane) : 0.f;
+            };
+            // arm the slot's mbarrier and launch the gathers of one stage (warp-collective)
+            auto issue = [&](int fs, const StageDesc& d, int my_idx, float my_val) {
+                const int cnt = (int)(d.info & 0xffu);
+                if (lane < KT) sm.stage_vals[fs][lane] = my_val;
+                const int src = (lane & 3) * GROUP_ROWS;
+                const int i0 = __shfl_sync(0xffffffffu, my_idx, src + 0);
+                const int i1 = __shfl_sync(0xffffffffu, my_idx, src + 1);
+                const int i2 = __shfl_sync(0xffffffffu, my_idx, src + 2);
+                const int i3 = __shfl_sync(0xffffffffu, my_idx, src + 3);
+                // rows past cnt carry index 0 (load_idx): fetched from row 0 and ignored by the conversion
+                if (lane == 0)
+                    mbar_arrive_expect_tx(&sm.full_f32[fs], (uint32_t)((cnt + GROUP_ROWS - 1) / GROUP_ROWS) * GROUP_ROWS * ROW_BYTES);
+                __syncwarp();
+                if (lane < KT / GROUP_ROWS && lane * GROUP_ROWS < cnt)
+                    tma_gather4(&sm.f32_stage[fs][lane * GROUP_BYTES], &factor_map, i0, i1, i2, i3, &sm.full_f32[fs]);
+            };
+
+            // prologue: descriptors of own-stages 0..3, gathers of 0 and 1 in flight, indices of 2 ready
+            StageDesc d0 = load_desc(0), d1 = load_desc(1), d2 = load_desc(2), d3 = load_desc(3);
+            {
+                const int ia = load_idx(d0); const float va = load_val(d0);
+                const int ib = load_idx(d1); const float vb = load_val(d1);
+                if (own > 0) issue(sw, d0, ia, va);
+                if (own > 1) issue(sw + STAGE_WARPS, d1, ib, vb);
+            }
+            int idx2 = load_idx(d2);
+            float val2 = load_val(d2);
+
+            for (int t = 0; t < own; ++t) {
+                // software prefetch: descriptor of t+4, indices/ratings of t+3 (consumed next iteration)
+                const StageDesc d4 = load_desc(t + 4);
+                const int idx3 = load_idx(d3);
+                const float val3 = load_val(d3);
+
+                const int fs = sw + STAGE_WARPS * (t & 1);
+                const uint32_t cnt = d0.info & 0xffu;
+                const uint32_t flags = d0.info >> 8;
                 const unsigned char* fbase = &sm.f32_stage[fs][0];
-                mbar_wait(&sm.full_f32[fs], ((uint32_t)n / S1) & 1u);
-                const uint32_t flags = sm.meta_f32[fs].flags;
-                const uint32_t cnt = sm.meta_f32[fs].cnt;
-                mbar_wait(&sm.empty_op[sw], (((uint32_t)n / STAGE_WARPS) & 1u) ^ 1u);
+                mbar_wait(&sm.full_f32[fs], ((uint32_t)t >> 1) & 1u);
+                mbar_wait(&sm.empty_op[sw], ((uint32_t)t & 1u) ^ 1u);
 #pragma unroll 1
                 for (int j = 0; j < 4; ++j) {
                     const int c = lane + 32 * j;         // feature handled in this pass
@@ -486,7 +434,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     uint32_t hi2[8], lo2[8];
 #pragma unroll
                     for (int k = 0; k < KT; k += 2) {
-                        const float r0 = sm.meta_f32[fs].vals[k], r1 = sm.meta_f32[fs].vals[k + 1];
+                        const float r0 = sm.stage_vals[fs][k], r1 = sm.stage_vals[fs][k + 1];
                         const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
                         const float h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
                         const __half2 hh = __floats2half2_rn(h0, h1);
@@ -501,12 +449,13 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     *reinterpret_cast<uint4*>(ob + 16 + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
                 }
                 if (lane == 0) sm.meta_op[sw] = flags;
-                fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05.mma
+                fence_proxy_async();                  // generic-proxy accesses of both rings ordered before async-proxy ones
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&sm.full_op[sw]);
-                    mbar_arrive(&sm.empty_f32[fs]);
-                }
+                if (lane == 0) mbar_arrive(&sm.full_op[sw]);
+                // this warp is the only user of fp32 slot fs: refill it with own-stage t+2 right away
+                if (t + 2 < own) issue(fs, d2, idx2, val2);
+                d0 = d1; d1 = d2; d2 = d3; d3 = d4;
+                idx2 = idx3; val2 = val3;
             }
         }
     } else {
@@ -615,7 +564,9 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
 
 // ---- host side -----------------------------------------------------------------------------
 struct TcWork {
-    DevBuf cta_ptr;
+    DevBuf cta_ptr;                     // first chunk of every CTA (+1)
+    DevBuf cta_stage_ptr;               // first stage (k-step) of every CTA (+1)
+    DevBuf stage_tab;                   // StageDesc per k-step, chunk order
     int grid = 0;
     int nchunks = 0;
     CUtensorMap factor_map;             // 2-D view [rows][F] fp32 of the opposing factor, box {F, 1}
@@ -653,13 +604,15 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
     return CUMF_OK;
 }
 
+void tc_plan_destroy(TcWork* w);
+
 bool tc_path_supports(int f) {
     const char* off = getenv("CUMF_DISABLE_TC");
     if (off && *off == '1') return false;
     return f == F;
 }
 
-int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const std::vector<SplitRow>&, int, int f) {
+int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* d_chunks, const std::vector<SplitRow>&, int, int f) {
     if (f != F) {
         set_last_error("fused tcgen05 kernel handles f = 100 only");
         return CUMF_EUNSUPPORTED;
@@ -688,15 +641,44 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const std::ve
         ptr[b] = c;
     }
     ptr[grid] = n;
+    // stage table: k-steps per chunk -> prefix -> one descriptor per k-step, filled on the device
+    std::vector<int> stage_base(n + 1, 0);
+    for (int c = 0; c < n; ++c) {
+        const long long nnz = chunks[c].end - chunks[c].begin;
+        const long long steps = std::max<long long>(1, (nnz + KT - 1) / KT);
+        if (stage_base[c] + steps > 0x7fffffffLL) {
+            set_last_error("tc_plan_create: too many k-steps for one shard");
+            return CUMF_EINVAL;
+        }
+        stage_base[c + 1] = stage_base[c] + (int)steps;
+    }
+    std::vector<int> sptr(grid + 1, 0);
+    for (int b = 0; b <= grid; ++b) sptr[b] = stage_base[ptr[b]];
+
     TcWork* w = new TcWork();
     w->grid = grid;
     w->nchunks = n;
+    DevBuf d_base;
     int rc = w->cta_ptr.alloc(sizeof(int) * (grid + 1));
-    if (rc == CUMF_OK && cudaMemcpy(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (rc == CUMF_OK) rc = w->cta_stage_ptr.alloc(sizeof(int) * (grid + 1));
+    if (rc == CUMF_OK) rc = w->stage_tab.alloc(sizeof(StageDesc) * (size_t)std::max(1, stage_base[n]));
+    if (rc == CUMF_OK) rc = d_base.alloc(sizeof(int) * (n + 1));
+    if (rc == CUMF_OK &&
+        (cudaMemcpy(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+         cudaMemcpy(w->cta_stage_ptr.p, sptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+         cudaMemcpy(d_base.p, stage_base.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice) != cudaSuccess)) {
         set_last_error("tc_plan_create: upload failed");
         rc = CUMF_ECUDA;
     }
-    if (rc != CUMF_OK) { w->cta_ptr.release(); delete w; return rc; }
+    if (rc == CUMF_OK && n > 0) {
+        fill_stage_table_kernel<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), n, w->stage_tab.as<StageDesc>());
+        if (cudaDeviceSynchronize() != cudaSuccess) {
+            set_last_error(std::string("tc_plan_create: stage table: ") + cudaGetErrorString(cudaGetLastError()));
+            rc = CUMF_ECUDA;
+        }
+    }
+    d_base.release();
+    if (rc != CUMF_OK) { tc_plan_destroy(w); return rc; }
     *out = w;
     return CUMF_OK;
 }
@@ -704,6 +686,8 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const std::ve
 void tc_plan_destroy(TcWork* w) {
     if (!w) return;
     w->cta_ptr.release();
+    w->cta_stage_ptr.release();
+    w->stage_tab.release();
     delete w;
 }
 
@@ -728,7 +712,8 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     }
     const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
     const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
-    als_fused_f100_kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), d_colidx, d_val, w->factor_map,
+    als_fused_f100_kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
+                                                            w->cta_stage_ptr.as<int>(), d_colidx, d_val, w->factor_map,
                                                             d_out, lambda, cg_iter, d_scratchA, d_scratchB, desc_tmpl);
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;
