@@ -697,12 +697,14 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
                path == CUMF_PATH_SIMT ? "simt" : (path == CUMF_PATH_TC ? "tcgen05" : "auto"));
     }
     cumf_als_solver* s = nullptr;
+    const double t_setup = wall_seconds();
     if (cumf_als_create(&s, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
                         cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
                         cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, 0, m, 0, n,
                         DEVICEID, solver, path) != CUMF_OK)
         die("cumf_als_create");
     if (cumf_als_set_factors(s, thetaTHost, XTHost) != CUMF_OK) die("cumf_als_set_factors");
+    if (debug) printf("\tsetup (upload + work plans) run %f seconds.\n", wall_seconds() - t_setup);
     if (!quiet) printf("*******start iterations...\n");
     float final_rmse = 0.f;
     for (int iter = 0; iter < ITERS; ++iter) {

@@ -399,54 +399,60 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const unsigned char* fbase = &sm.f32_stage[fs][0];
                 mbar_wait(&sm.full_f32[fs], ((uint32_t)t >> 1) & 1u);
                 mbar_wait(&sm.empty_op[sw], ((uint32_t)t & 1u) ^ 1u);
-#pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    const int c = lane + 32 * j;         // feature handled in this pass
-                    if (c < F) {
-                        const float* src = reinterpret_cast<const float*>(fbase) + c;
-                        float v[KT];
-                        if (cnt == KT) {
-#pragma unroll
-                            for (int k = 0; k < KT; ++k) v[k] = src[(k >> 2) * GROUP_FLOATS + (k & 3) * F];
-                        } else {            // ragged last stage of a chunk: rows beyond cnt hold stale data
-#pragma unroll
-                            for (int k = 0; k < KT; ++k) v[k] = ((uint32_t)k < cnt) ? src[(k >> 2) * GROUP_FLOATS + (k & 3) * F] : 0.f;
-                        }
-                        uint32_t hi2[8], lo2[8];
-#pragma unroll
-                        for (int k = 0; k < KT; k += 2) {
-                            const float h0 = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
-                            const float h1 = __uint_as_float(__float_as_uint(v[k + 1]) & 0xFFFFE000u);
-                            const __half2 hh = __floats2half2_rn(h0, h1);                       // exact
-                            const __half2 ll = __floats2half2_rn((v[k] - h0) * kLoScale, (v[k + 1] - h1) * kLoScale);
-                            hi2[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
-                            lo2[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
-                        }
-                        unsigned char* ob = obase + (c >> 3) * OP_GROUP_BYTES + (c & 7) * 16;
-                        *reinterpret_cast<uint4*>(ob) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);                                   // k 0..7
-                        *reinterpret_cast<uint4*>(ob + OP_KCORE_BYTES) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);                  // k 8..15
-                        *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-                        *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
-                    }
+                if (cnt < KT) {
+                    // ragged last stage of a chunk: rows beyond cnt were not fetched -> zero them once, so the
+                    // conversion below has a single unpredicated path
+                    float* base = reinterpret_cast<float*>(const_cast<unsigned char*>(fbase));
+                    for (int k = (int)cnt; k < KT; ++k)
+                        for (int c = lane; c < F; c += 32) base[(k >> 2) * GROUP_FLOATS + (k & 3) * F + c] = 0.f;
+                    __syncwarp();
                 }
-                if (lane == 31) {
-                    // the ratings ride along as operand rows 224 (r_hi) and 225 (r_lo'): b = sum r theta from the same MMAs
+                // features 0..95: three passes, lane = feature within the pass, all 16 gathered rows
+#pragma unroll 1
+                for (int j = 0; j < 3; ++j) {
+                    const int c = lane + 32 * j;
+                    const float* src = reinterpret_cast<const float*>(fbase) + c;
+                    float v[KT];
+#pragma unroll
+                    for (int k = 0; k < KT; ++k) v[k] = src[(k >> 2) * GROUP_FLOATS + (k & 3) * F];
                     uint32_t hi2[8], lo2[8];
 #pragma unroll
                     for (int k = 0; k < KT; k += 2) {
-                        const float r0 = sm.stage_vals[fs][k], r1 = sm.stage_vals[fs][k + 1];
-                        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
-                        const float h1 = __uint_as_float(__float_as_uint(r1) & 0xFFFFE000u);
-                        const __half2 hh = __floats2half2_rn(h0, h1);
-                        const __half2 ll = __floats2half2_rn((r0 - h0) * kLoScale, (r1 - h1) * kLoScale);
+                        const float h0 = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
+                        const float h1 = __uint_as_float(__float_as_uint(v[k + 1]) & 0xFFFFE000u);
+                        const __half2 hh = __floats2half2_rn(h0, h1);                       // exact
+                        const __half2 ll = __floats2half2_rn((v[k] - h0) * kLoScale, (v[k + 1] - h1) * kLoScale);
                         hi2[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
                         lo2[k >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    unsigned char* ob = obase + (R_ROW / 8) * OP_GROUP_BYTES;
-                    *reinterpret_cast<uint4*>(ob) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);
-                    *reinterpret_cast<uint4*>(ob + OP_KCORE_BYTES) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);
-                    *reinterpret_cast<uint4*>(ob + 16) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-                    *reinterpret_cast<uint4*>(ob + 16 + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+                    unsigned char* ob = obase + (c >> 3) * OP_GROUP_BYTES + (c & 7) * 16;
+                    *reinterpret_cast<uint4*>(ob) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);                                   // k 0..7
+                    *reinterpret_cast<uint4*>(ob + OP_KCORE_BYTES) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);                  // k 8..15
+                    *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+                    *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+                }
+                {
+                    // features 96..99: 4 x 16 elements spread over the 32 lanes (two consecutive rows each)
+                    const int c = 96 + (lane & 3), k = (lane >> 2) * 2;
+                    const float* src = reinterpret_cast<const float*>(fbase) + c;
+                    const float v0 = src[(k >> 2) * GROUP_FLOATS + (k & 3) * F];
+                    const float v1 = src[((k + 1) >> 2) * GROUP_FLOATS + ((k + 1) & 3) * F];
+                    const float h0 = __uint_as_float(__float_as_uint(v0) & 0xFFFFE000u);
+                    const float h1 = __uint_as_float(__float_as_uint(v1) & 0xFFFFE000u);
+                    const __half2 hh = __floats2half2_rn(h0, h1);
+                    const __half2 ll = __floats2half2_rn((v0 - h0) * kLoScale, (v1 - h1) * kLoScale);
+                    unsigned char* ob = obase + (c >> 3) * OP_GROUP_BYTES + (k >> 3) * OP_KCORE_BYTES + (c & 7) * 16 + (k & 7) * 2;
+                    *reinterpret_cast<uint32_t*>(ob) = *reinterpret_cast<const uint32_t*>(&hh);
+                    *reinterpret_cast<uint32_t*>(ob + (FP / 8) * OP_GROUP_BYTES) = *reinterpret_cast<const uint32_t*>(&ll);
+                }
+                if (lane < KT) {
+                    // the ratings ride along as operand rows 224 (r_hi) and 225 (r_lo'): b = sum r theta from the
+                    // same MMAs.  Lane k converts rating k and drops its two halves into place.
+                    const float r0 = sm.stage_vals[fs][lane];
+                    const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
+                    unsigned char* ob = obase + (R_ROW / 8) * OP_GROUP_BYTES + (lane >> 3) * OP_KCORE_BYTES + (lane & 7) * 2;
+                    *reinterpret_cast<__half*>(ob) = __float2half_rn(h0);
+                    *reinterpret_cast<__half*>(ob + 16) = __float2half_rn((r0 - h0) * kLoScale);
                 }
                 if (lane == 0) sm.meta_op[sw] = flags;
                 fence_proxy_async();                  // generic-proxy accesses of both rings ordered before async-proxy ones
