@@ -74,7 +74,7 @@ static_assert(S1 % STAGE_WARPS == 0 && STAGE_WARPS == S2, "every ring slot has e
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
 // setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
-constexpr int REGS_LAUNCH = 96, REGS_PROD = 24, REGS_STAGE = 72, REGS_EPI = 152;
+constexpr int REGS_LAUNCH = 96, REGS_PROD = 40, REGS_STAGE = 64, REGS_EPI = 152;
 static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
@@ -184,6 +184,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -310,36 +315,41 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         reg_dec<REGS_PROD>();
         if (n_chunks > 0 && warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
-            if (lane == 0) {
-                constexpr uint32_t idesc1 = make_idesc(128, N1);
-                constexpr uint32_t idesc2 = make_idesc(128, N2);
-                constexpr uint32_t idesc3 = make_idesc(128, N3);
-                int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
-                int done = 0;           // chunks finished
-                for (int n = 0; n < total_stages; ++n) {
-                    const int slot = n & (S2 - 1);
-                    mbar_wait(&sm.full_op[slot], ((uint32_t)n / S2) & 1u);
-                    const uint32_t flags = sm.meta_op[slot];
-                    const int buf = q & 1;
-                    if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
-                    const uint32_t base = smem_u32(&sm.op_stage[slot][0]);
-                    const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                  // rows 0..   : hi | lo' | r
-                    const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);      // rows 112.. : lo'
-                    const uint64_t d_r = make_smem_desc(base + (R_ROW / 8) * OP_GROUP_BYTES, desc_tmpl);    // rows 224.. : r_hi, r_lo'
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+            // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
+            // divergent path); one elected lane issues the tcgen05 instructions.
+            constexpr uint32_t idesc1 = make_idesc(128, N1);
+            constexpr uint32_t idesc2 = make_idesc(128, N2);
+            constexpr uint32_t idesc3 = make_idesc(128, N3);
+            const uint32_t op_base0 = smem_u32(&sm.op_stage[0][0]);
+            int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
+            int done = 0;           // chunks finished
+            for (int n = 0; n < total_stages; ++n) {
+                const int slot = n & (S2 - 1);
+                mbar_wait(&sm.full_op[slot], ((uint32_t)n / S2) & 1u);
+                const uint32_t flags = sm.meta_op[slot];
+                const int buf = q & 1;
+                if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t base = op_base0 + (uint32_t)slot * OP_STAGE_BYTES;
+                const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                  // rows 0..   : hi | lo' | r
+                const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);      // rows 112.. : lo'
+                const uint64_t d_r = make_smem_desc(base + (R_ROW / 8) * OP_GROUP_BYTES, desc_tmpl);    // rows 224.. : r_hi, r_lo'
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+                const uint32_t acc = (flags & FLAG_SUB_FIRST) ? 0u : 1u;
+                if (elect_one()) {
                     // cols [0,112): hi^T hi ; [112,224): hi^T lo' ; 224: hi^T r_hi ; 225: hi^T r_lo'
-                    umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
+                    umma_f16(d_tmem, d_hi, d_hi, idesc1, acc);
                     // cols [112,224) += lo'^T hi
                     umma_f16(d_tmem + FP, d_lo, d_hi, idesc2, 1u);
                     // cols [240,256): lo'^T r_hi (only column 240 is used)
-                    umma_f16(d_tmem + BCOL_LO, d_lo, d_r, idesc3, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
+                    umma_f16(d_tmem + BCOL_LO, d_lo, d_r, idesc3, acc);
                     umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
-                    if (flags & FLAG_SUB_LAST) { umma_commit(&sm.acc_full[done & 1][buf]); ++q; }   // chunk `done` belongs to warpgroup done&1
-                    if (flags & FLAG_CHUNK_LAST) ++done;
+                    if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[done & 1][buf]);   // chunk `done` belongs to warpgroup done&1
                 }
+                __syncwarp();
+                if (flags & FLAG_SUB_LAST) ++q;
+                if (flags & FLAG_CHUNK_LAST) ++done;
             }
-            __syncwarp();
         }
     } else if (warp < FIRST_EPI_WARP) {
         reg_dec<REGS_STAGE>();
