@@ -25,7 +25,7 @@
 // CTA = 20 warps (5 warpgroups, setmaxnreg budgets 48/64/64/152/152), persistent, one per SM, each
 // owning a contiguous, cost-balanced range of row chunks (so its ratings are one stream):
 //   warps 0-2     idle (they only return their registers to the pool)
-//   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=240 / 112 / 16, K=16,
+//   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=256 and N=128, K=16,
 //                 smem descriptors (K-major, no swizzle); tcgen05.commit frees operand stages /
 //                 publishes accumulator tiles; owns the TMEM allocation
 //   warps 4-11    autonomous stage workers, one warp per stage, 16 stages of gathered rows in flight:
@@ -60,12 +60,13 @@ constexpr int GROUP_ROWS = 4;             // rows fetched by one TMA tile::gathe
 constexpr int GROUP_BYTES = 1664;         // 4 x 400 B padded to a multiple of 128 B (TMA destination alignment)
 constexpr int GROUP_FLOATS = GROUP_BYTES / 4;
 constexpr int STAGE_F32_BYTES = (KT / GROUP_ROWS) * GROUP_BYTES;   // 6656
-// operand stage: rows [0,112) hi, [112,224) lo', 224 r_hi, 225 r_lo', [226,240) zero
-constexpr int OP_ROWS = 2 * FP + 16;
-constexpr int R_ROW = 2 * FP;             // 224
+// operand stage (256 rows x 16 k): [0,112) hi, 112 r_hi, 113 r_lo', [114,128) zero, [128,240) lo', [240,256) zero
+constexpr int OP_ROWS = 256;
+constexpr int R_ROW = FP;                 // 112: the two rating rows sit right behind hi
+constexpr int LO_ROW = FP + 16;           // 128: first lo' row
 constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B): SBO
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
-constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 7680
+constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 8192
 constexpr int NUM_THREADS = 640;          // 5 warpgroups: (idle x3 + MMA), 2 x stage workers, 2 x epilogue/solver
 constexpr int MMA_WARP = 3;
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
@@ -74,16 +75,19 @@ static_assert(S1 % STAGE_WARPS == 0 && STAGE_WARPS == S2, "every ring slot has e
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
 // setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
-constexpr int REGS_LAUNCH = 96, REGS_PROD = 40, REGS_STAGE = 64, REGS_EPI = 152;
+constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
 static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COLS = 256;             // columns per accumulator tile: [0,112) P, [112,224) S, 224.. b_hi, 240.. b_lo
-constexpr int N1 = OP_ROWS;               // 240: [hi | lo' | r] as B operand, A = hi
-constexpr int N2 = FP;                    // 112: hi as B operand, A = lo'
-constexpr int N3 = 16;                    // r rows as B operand, A = lo'
-constexpr int BCOL_HI = R_ROW;            // TMEM column of  hi^T r_hi  (next column: hi^T r_lo')
-constexpr int BCOL_LO = 240;              // TMEM column of  lo'^T r_hi
+// accumulator tile, 256 TMEM columns:  [0,112) P = hi^T hi | 112 hi^T r_hi | 113 hi^T r_lo' |
+//                                      [128,240) S = hi^T lo' + lo'^T hi | 240 lo'^T r_hi
+// from two MMAs per k-step:  D[:,0:256] (+)= hi^T [hi | r | lo' | 0]   and   D[:,128:256] += lo'^T [hi | r]
+constexpr int ACC_COLS = 256;
+constexpr int N1 = 256;                   // B = all 256 operand rows, A = hi
+constexpr int N2 = 128;                   // B = rows [0,128) (hi, r), A = lo', D columns [128,256)
+constexpr int SCOL = LO_ROW;              // 128: first TMEM column of S
+constexpr int BCOL_HI = R_ROW;            // 112: TMEM column of  hi^T r_hi  (next column: hi^T r_lo')
+constexpr int BCOL_LO = SCOL + R_ROW;     // 240: TMEM column of  lo'^T r_hi
 constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
 // cg.cu:31,195: `rsnew < 1e-4` compares in double.  For a float rsnew that is exactly
@@ -227,7 +231,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
     for (int cc = 0; cc < 96; cc += 16) {
         uint32_t p[16], s[16];
         tmem_ld16(taddr + cc, p);
-        tmem_ld16(taddr + FP + cc, s);
+        tmem_ld16(taddr + SCOL + cc, s);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -237,7 +241,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
     }
     uint32_t p[4], s[4], bh[4], bl[4];
     tmem_ld4(taddr + 96, p);
-    tmem_ld4(taddr + FP + 96, s);
+    tmem_ld4(taddr + SCOL + 96, s);
     tmem_ld4(taddr + BCOL_HI, bh);      // hi^T r_hi, hi^T r_lo'
     tmem_ld4(taddr + BCOL_LO, bl);      // lo'^T r_hi
     tmem_ld_wait();
@@ -316,39 +320,42 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         if (n_chunks > 0 && warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
             // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
-            // divergent path); one elected lane issues the tcgen05 instructions.
+            // divergent path); one elected lane issues the tcgen05 instructions.  The loop is unrolled over
+            // the 8 operand slots so every shared-memory descriptor is base + compile-time constant.
             constexpr uint32_t idesc1 = make_idesc(128, N1);
             constexpr uint32_t idesc2 = make_idesc(128, N2);
-            constexpr uint32_t idesc3 = make_idesc(128, N3);
             const uint32_t op_base0 = smem_u32(&sm.op_stage[0][0]);
+            const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
             int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
             int done = 0;           // chunks finished
-            for (int n = 0; n < total_stages; ++n) {
-                const int slot = n & (S2 - 1);
-                mbar_wait(&sm.full_op[slot], ((uint32_t)n / S2) & 1u);
-                const uint32_t flags = sm.meta_op[slot];
-                const int buf = q & 1;
-                if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t base = op_base0 + (uint32_t)slot * OP_STAGE_BYTES;
-                const uint64_t d_hi = make_smem_desc(base, desc_tmpl);                                  // rows 0..   : hi | lo' | r
-                const uint64_t d_lo = make_smem_desc(base + (FP / 8) * OP_GROUP_BYTES, desc_tmpl);      // rows 112.. : lo'
-                const uint64_t d_r = make_smem_desc(base + (R_ROW / 8) * OP_GROUP_BYTES, desc_tmpl);    // rows 224.. : r_hi, r_lo'
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
-                const uint32_t acc = (flags & FLAG_SUB_FIRST) ? 0u : 1u;
-                if (elect_one()) {
-                    // cols [0,112): hi^T hi ; [112,224): hi^T lo' ; 224: hi^T r_hi ; 225: hi^T r_lo'
-                    umma_f16(d_tmem, d_hi, d_hi, idesc1, acc);
-                    // cols [112,224) += lo'^T hi
-                    umma_f16(d_tmem + FP, d_lo, d_hi, idesc2, 1u);
-                    // cols [240,256): lo'^T r_hi (only column 240 is used)
-                    umma_f16(d_tmem + BCOL_LO, d_lo, d_r, idesc3, acc);
-                    umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
-                    if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[done & 1][buf]);   // chunk `done` belongs to warpgroup done&1
+            for (int n0 = 0; n0 < total_stages; n0 += S2) {
+                const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
+#pragma unroll
+                for (int slot = 0; slot < S2; ++slot) {
+                    if (n0 + slot < total_stages) {
+                        mbar_wait(&sm.full_op[slot], ph);
+                        const uint32_t flags = sm.meta_op[slot];
+                        const int buf = q & 1;
+                        if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                        tc_fence_after();
+                        // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and
+                        // the whole ring lies below the field's 256 KB wrap, so plain addition is exact
+                        const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);                                        // rows 0..   : hi | r | lo' | 0
+                        const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);        // rows 128.. : lo' | 0
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+                        if (elect_one()) {
+                            // D[:, 0:256] (+)= hi^T [hi | r | lo' | 0]
+                            umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
+                            // D[:, 128:256] += lo'^T [hi | r]
+                            umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
+                            umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
+                            if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[done & 1][buf]);   // chunk `done` belongs to warpgroup done&1
+                        }
+                        __syncwarp();
+                        if (flags & FLAG_SUB_LAST) ++q;
+                        if (flags & FLAG_CHUNK_LAST) ++done;
+                    }
                 }
-                __syncwarp();
-                if (flags & FLAG_SUB_LAST) ++q;
-                if (flags & FLAG_CHUNK_LAST) ++done;
             }
         }
     } else if (warp < FIRST_EPI_WARP) {
@@ -438,8 +445,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     unsigned char* ob = obase + (c >> 3) * OP_GROUP_BYTES + (c & 7) * 16;
                     *reinterpret_cast<uint4*>(ob) = make_uint4(hi2[0], hi2[1], hi2[2], hi2[3]);                                   // k 0..7
                     *reinterpret_cast<uint4*>(ob + OP_KCORE_BYTES) = make_uint4(hi2[4], hi2[5], hi2[6], hi2[7]);                  // k 8..15
-                    *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
-                    *reinterpret_cast<uint4*>(ob + (FP / 8) * OP_GROUP_BYTES + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
+                    *reinterpret_cast<uint4*>(ob + (LO_ROW / 8) * OP_GROUP_BYTES) = make_uint4(lo2[0], lo2[1], lo2[2], lo2[3]);
+                    *reinterpret_cast<uint4*>(ob + (LO_ROW / 8) * OP_GROUP_BYTES + OP_KCORE_BYTES) = make_uint4(lo2[4], lo2[5], lo2[6], lo2[7]);
                 }
                 {
                     // features 96..99: 4 x 16 elements spread over the 32 lanes (two consecutive rows each)
@@ -453,10 +460,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     const __half2 ll = __floats2half2_rn((v0 - h0) * kLoScale, (v1 - h1) * kLoScale);
                     unsigned char* ob = obase + (c >> 3) * OP_GROUP_BYTES + (k >> 3) * OP_KCORE_BYTES + (c & 7) * 16 + (k & 7) * 2;
                     *reinterpret_cast<uint32_t*>(ob) = *reinterpret_cast<const uint32_t*>(&hh);
-                    *reinterpret_cast<uint32_t*>(ob + (FP / 8) * OP_GROUP_BYTES) = *reinterpret_cast<const uint32_t*>(&ll);
+                    *reinterpret_cast<uint32_t*>(ob + (LO_ROW / 8) * OP_GROUP_BYTES) = *reinterpret_cast<const uint32_t*>(&ll);
                 }
                 if (lane < KT) {
-                    // the ratings ride along as operand rows 224 (r_hi) and 225 (r_lo'): b = sum r theta from the
+                    // the ratings ride along as operand rows 112 (r_hi) and 113 (r_lo'): b = sum r theta from the
                     // same MMAs.  Lane k converts rating k and drops its two halves into place.
                     const float r0 = sm.stage_vals[fs][lane];
                     const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
