@@ -35,6 +35,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+METRIC = "ALS iterations/sec ({workload}-shaped synthetic, f={f}, CG solver; BASELINE.json metric (i))"
+
 WORKLOADS = {
     # name: m, n, nnz, nnz_test, f, lambda, seed, reference (X_BATCH, THETA_BATCH) (test_als.sh:5-28)
     "netflix": dict(m=17770, n=480189, nnz=99072112, nnz_test=1408395, f=100, lam=0.048, seed=1002, ref_batches=(1, 3)),
@@ -70,7 +72,7 @@ class ClockSampler:
         try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
         return self
@@ -113,6 +115,15 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload: str, path: str):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None
+    return json.loads(p.read_text()).get(f"{workload}:{path}")
 
 
 def gram_bytes(rows, nnz, f, fused: bool):
@@ -218,7 +229,7 @@ def run_ours(args, w):
         gram_ms = (tm["gram_x_ms"] + tm["gram_theta_ms"]) / max(tm["iterations"], 1)
         achieved = gb / (gram_ms / 1e3) if gram_ms > 0 else None
         line = {
-            "metric": "ALS iterations/sec (Netflix-shaped f=100, CG solver)", "value": iters_per_s,
+            "metric": METRIC.format(workload=args.workload, f=f), "value": iters_per_s,
             "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -231,7 +242,8 @@ def run_ours(args, w):
             "gpu_launches": int(tm["launches"]),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": ncu_traffic(args.workload, "fused" if fused else "simt") if world == 1 and args.scale == 1.0 else None,
                          "kernel": "gram (+rhs" + (" + fused CG)" if fused else ")") + " X side + theta side",
                          "bytes_per_iteration_gb": gb, "kernel_ms_per_iteration": gram_ms,
                          "gram_x_ms": tm["gram_x_ms"] / max(tm["iterations"], 1),
@@ -245,7 +257,12 @@ def run_ours(args, w):
     if rank == 0 and world == 1 and not args.no_e2e:
         os.environ["CUMF_QUIET"] = "1"
         os.environ["CUMF_PATH"] = args.path
-        th, X = theta0.copy(), X0.copy()
+        # the reference's CLI keeps every input in pinned host memory (cudaMallocHost, main.cpp:50-69): same here
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+        for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row",
+                     "test_row", "test_col", "test_val"):
+            setattr(r, name, pin(getattr(r, name)))
+        th, X = pin(theta0), pin(X0)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         fin = c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz, r.nnz_test, lam,
@@ -317,7 +334,7 @@ def run_reference(args, w):
     gb = (gram_bytes(r.m, r.nnz, f, False) + gram_bytes(r.n, r.nnz, f, False)) / 1e9
     gram_s = (sum(kx) + sum(kt)) / iters if kx else None
     line = {
-        "impl": "reference", "metric": "ALS iterations/sec (Netflix-shaped f=100, CG solver)", "value": value,
+        "impl": "reference", "metric": METRIC.format(workload=args.workload, f=f), "value": value,
         "unit": "iterations/s", "n_gpus": 1, "steps": iters, "warmup": 0, "ms_per_step": 1e3 * als_s / iters,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
