@@ -313,10 +313,17 @@ def run_reference(args, w):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_als_%s.so not built" % variant}))
         return
     from make_golden import CaptureStdout
+    # pinned host inputs, like the reference's own CLI (cudaMallocHost, main.cpp:50-69): its per-iteration
+    # CSR re-upload (als.cu:734-739) then runs at full PCIe speed
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row",
+                 "test_row", "test_col", "test_val"):
+        setattr(r, name, pin(getattr(r, name)))
+    theta0, X0 = pin(theta0), pin(X0)
     if args.warmup > 0:   # context / cuBLAS / cuSPARSE initialisation outside the timed call
         with CaptureStdout():
             O.ref_do_als(r, theta0.copy(), X0.copy(), f, lam, 1, xb, tb, variant, local_rank)
-    th, X = theta0.copy(), X0.copy()
+    th, X = pin(theta0), pin(X0)
     iters = args.steps
     with ClockSampler(local_rank) as clocks:
         t0 = time.perf_counter()
