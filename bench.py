@@ -226,7 +226,11 @@ def run_ours(args, w):
         nnz_x = int(r.csr_indptr[xr[1]] - r.csr_indptr[xr[0]])
         nnz_t = int(r.csc_indptr[tr_[1]] - r.csc_indptr[tr_[0]])
         gb = (gram_bytes(xs, nnz_x, f, fused) + gram_bytes(ts, nnz_t, f, fused)) / 1e9   # per iteration, this rank
-        gram_ms = (tm["gram_x_ms"] + tm["gram_theta_ms"]) / max(tm["iterations"], 1)
+        iters_done = tm["iterations"] if tm["iterations"] > 0 else args.steps      # sharded runs drive the half-steps directly
+        tm["iterations"] = iters_done
+        if world > 1:
+            tm["x_ms"], tm["theta_ms"] = tm["gram_x_ms"], tm["gram_theta_ms"]     # per-rank kernel time (rank 0)
+        gram_ms = (tm["gram_x_ms"] + tm["gram_theta_ms"]) / max(iters_done, 1)
         achieved = gb / (gram_ms / 1e3) if gram_ms > 0 else None
         line = {
             "metric": METRIC.format(workload=args.workload, f=f), "value": iters_per_s,
