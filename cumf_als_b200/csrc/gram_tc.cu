@@ -328,32 +328,41 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
             int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
             int done = 0;           // chunks finished
+            // one k-step: D[:, 0:256] (+)= hi^T [hi | r | lo' | 0] ;  D[:, 128:256] += lo'^T [hi | r]
+            auto issue_step = [&](int slot, uint32_t flags, int buf, int chunk_parity) {
+                // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and the
+                // whole ring lies below the field's 256 KB wrap, so plain addition is exact
+                const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);                                    // rows 0..   : hi | r | lo' | 0
+                const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);    // rows 128.. : lo' | 0
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+                umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
+                umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
+                umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
+                if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[chunk_parity][buf]);   // chunk c belongs to solver warpgroup c & 1
+            };
             for (int n0 = 0; n0 < total_stages; n0 += S2) {
                 const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
+                // two k-steps per pass: their barrier waits and flag reads overlap, one elected region issues both
 #pragma unroll
-                for (int slot = 0; slot < S2; ++slot) {
+                for (int slot = 0; slot < S2; slot += 2) {
                     if (n0 + slot < total_stages) {
+                        const bool two = (n0 + slot + 1 < total_stages);
                         mbar_wait(&sm.full_op[slot], ph);
-                        const uint32_t flags = sm.meta_op[slot];
-                        const int buf = q & 1;
-                        if (flags & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[buf], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                        if (two) mbar_wait(&sm.full_op[slot + 1], ph);
+                        const uint32_t f0 = sm.meta_op[slot];
+                        const uint32_t f1 = two ? sm.meta_op[slot + 1] : 0u;
+                        const int q1 = q + ((f0 & FLAG_SUB_LAST) ? 1 : 0);
+                        const int done1 = done + ((f0 & FLAG_CHUNK_LAST) ? 1 : 0);
+                        if (f0 & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[q & 1], (((uint32_t)q >> 1) & 1u) ^ 1u);
+                        if (f1 & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[q1 & 1], (((uint32_t)q1 >> 1) & 1u) ^ 1u);
                         tc_fence_after();
-                        // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and
-                        // the whole ring lies below the field's 256 KB wrap, so plain addition is exact
-                        const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);                                        // rows 0..   : hi | r | lo' | 0
-                        const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);        // rows 128.. : lo' | 0
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
                         if (elect_one()) {
-                            // D[:, 0:256] (+)= hi^T [hi | r | lo' | 0]
-                            umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
-                            // D[:, 128:256] += lo'^T [hi | r]
-                            umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
-                            umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
-                            if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[done & 1][buf]);   // chunk `done` belongs to warpgroup done&1
+                            issue_step(slot, f0, q & 1, done & 1);
+                            if (two) issue_step(slot + 1, f1, q1 & 1, done1 & 1);
                         }
                         __syncwarp();
-                        if (flags & FLAG_SUB_LAST) ++q;
-                        if (flags & FLAG_CHUNK_LAST) ++done;
+                        q = q1 + ((f1 & FLAG_SUB_LAST) ? 1 : 0);
+                        done = done1 + ((f1 & FLAG_CHUNK_LAST) ? 1 : 0);
                     }
                 }
             }
