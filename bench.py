@@ -287,6 +287,92 @@ def run_ours(args, w):
         dist.destroy_process_group()
 
 
+def run_ours_partial_gram(args, w):
+    """N ranks, theta sharded (E2): partial [A|b] of every X row per rank -> NCCL all-reduce -> replicated CG;
+    theta-step rank-local.  Same line format; phases timed with CUDA events on the launching stream."""
+    import torch
+    import torch.distributed as dist
+    import cumf_als_b200 as c
+    from cumf_als_b200.data import nnz_balanced_ranges
+    from cumf_als_b200.dist import GpuPartialGramEngine, PartialGramAls
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    r, theta0, X0 = make_inputs(w, args.scale, "cuda")
+    f, lam = w["f"], w["lam"]
+    path = {"auto": c.PATH_AUTO, "simt": c.PATH_SIMT, "tc": c.PATH_TC}[args.path]
+    t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
+    eng = GpuPartialGramEngine(r, f, lam, theta0, X0, t_ranges[rank], local_rank, path=path)
+    drv = PartialGramAls(eng, r.nnz, r.nnz_test)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    drv.iterate(args.warmup)
+    eng.launches = 0
+    drv.allreduce_bytes = 0
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ms = drv.iterate(args.steps)
+        barrier()
+    # one more, instrumented, iteration for the phase split (outside the timed region)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    ev[0].record()
+    parts = [eng.partial_gram(b) for b in range(len(eng.batches))] if len(eng.batches) == 1 else None
+    phases = None
+    if parts is not None:
+        tt, rhs = parts[0]
+        ev[1].record()
+        if world > 1:
+            dist.all_reduce(tt)
+            dist.all_reduce(rhs)
+        ev[2].record()
+        eng.solve_x(0, tt, rhs)
+        ev[3].record()
+        eng.update_theta()
+        ev[4].record()
+        torch.cuda.synchronize()
+        phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["partial_gram_ms", "allreduce_ms", "cg_x_ms", "theta_ms"])}
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    train_rmse, test_rmse = drv.rmse()
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        fused = args.path != "simt" and _tc_active(c, f)
+        t0, t1 = t_ranges[rank]
+        nnz_t = int(r.csc_indptr[t1] - r.csc_indptr[t0])
+        gb = (gram_bytes(r.m, eng.local_nnz, f, False) + gram_bytes(t1 - t0, nnz_t, f, fused)) / 1e9
+        kernel_ms = (phases["partial_gram_ms"] + phases["theta_ms"]) if phases else None
+        achieved = gb / (kernel_ms / 1e3) if kernel_ms else None
+        print(json.dumps({
+            "metric": METRIC.format(workload=args.workload, f=f), "value": args.steps / (ms / 1e3),
+            "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
+                       "lambda": lam, "solver": "cg6", "path": "tcgen05" if fused else "simt",
+                       "sharding": f"theta rows nnz-balanced over {world} ranks; X-step = partial [A|b] + NCCL all-reduce "
+                                   f"+ replicated CG; theta-step rank-local (no factor exchange)",
+                       "l2": "inputs exceed L2: no flush"},
+            "phases_ms": phases, "allreduce_bytes_per_iteration": drv.allreduce_bytes // max(args.steps, 1),
+            "train_rmse": train_rmse, "test_rmse": test_rmse, "gpu_launches": int(eng.launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "partial gram (materialised) X side + fused theta side, rank 0",
+                         "bytes_per_iteration_gb": gb, "kernel_ms_per_iteration": kernel_ms, "peak_source": peak_src},
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def _tc_active(c, f):
     try:
         import ctypes
@@ -376,12 +462,17 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink nnz (debug only; 1.0 = the BASELINE workload)")
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--ref-variant", default="cg", choices=["cg", "lu"])
+    ap.add_argument("--sharding", default="rows", choices=["rows", "partial-gram"],
+                    help="N>1: 'rows' = each rank updates its rows from full factors and broadcasts them (E1); "
+                         "'partial-gram' = theta sharded, partial [A|b] all-reduced (E2, hugewiki.cu:2629-2827)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
+    elif args.sharding == "partial-gram":
+        run_ours_partial_gram(args, w)
     else:
         run_ours(args, w)
 

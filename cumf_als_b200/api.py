@@ -54,6 +54,8 @@ SIGNATURES = {
     "cumf_lu": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "cumf_rmse": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_long, C.c_int, C.c_int, _f32p, _f64p, _vp]),
     "cumf_plan_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cumf_plan_create_ranges": (C.c_int, [C.POINTER(_vp), _vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "cumf_plan_gram": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     "cumf_plan_destroy": (C.c_int, [_vp]),
     "cumf_plan_last_launches": (C.c_int, [_vp]),
     "cumf_update_factor": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int, C.c_float, _vp]),
@@ -203,6 +205,25 @@ class Plan:
         self.base = int(rp[row_begin])
         _check(load_library().cumf_plan_create(C.byref(self._h), _hp(rp), rows, row_begin, self.row_end, f, path),
                "cumf_plan_create")
+
+    @classmethod
+    def from_ranges(cls, begin: np.ndarray, end: np.ndarray, f: int = 100, path: int = PATH_AUTO) -> "Plan":
+        """Partial-Gram plan (cumf_plan_create_ranges): row u covers ratings [begin[u], end[u])."""
+        b, e = _host(begin, np.int64), _host(end, np.int64)
+        if b.shape != e.shape or b.ndim != 1:
+            raise ValueError("begin/end must be 1-D arrays of the same length")
+        self = cls.__new__(cls)
+        self._h = _vp()
+        self.row_begin, self.row_end, self.f, self.base = 0, b.size, f, 0
+        _check(load_library().cumf_plan_create_ranges(C.byref(self._h), _hp(b), _hp(e), b.size, f, path),
+               "cumf_plan_create_ranges")
+        return self
+
+    def gram(self, colidx, val, factor, lam: float, tt, rhs, stream=None) -> None:
+        """Partial [A|b] of every row over the plan's ranges into tt [rows,f*f] / rhs [rows,f]
+        (cumf_plan_gram; asynchronous on the stream)."""
+        _check(load_library().cumf_plan_gram(self._h, _dptr(colidx), _dptr(val), _dptr(factor), lam, _dptr(tt),
+                                             _dptr(rhs), _stream_ptr(stream)), "cumf_plan_gram")
 
     @property
     def last_launches(self) -> int:

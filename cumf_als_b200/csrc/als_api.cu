@@ -165,9 +165,11 @@ static void plan_free(cumf_plan* p) {
 
 // force_slots: treat every row as "split" (each chunk stores its partial [A|b]); used by cumf_gram
 // to materialise A through the fused kernel.
-static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
-                            int path, bool alloc_workspace, bool force_slots = false) {
-    CUMF_REQUIRE(out && h_rowptr, "null pointer");
+// The rating range of row r is [h_begin[r], h_end[r]) (absolute positions in colidx/val).  With a CSR row
+// pointer that is (rowptr[r], rowptr[r+1]); the partial-Gram scheme passes narrower per-row ranges.
+static int plan_create_core(cumf_plan** out, const long long* h_begin, const long long* h_end, int rows, int row_begin,
+                            int row_end, int f, int path, bool alloc_workspace, bool force_slots) {
+    CUMF_REQUIRE(out && h_begin && h_end, "null pointer");
     CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
     CUMF_TRY(check_f(f));
     CUMF_TRY(check_device());
@@ -180,7 +182,12 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
         return CUMF_EUNSUPPORTED;
     }
     p->path = path;
-    p->base = h_rowptr[row_begin];
+    // chunk offsets are relative to the smallest position the plan touches
+    p->base = 0;
+    for (int r = row_begin; r < row_end; ++r)
+        if (h_end[r] > h_begin[r]) { p->base = h_begin[r]; break; }
+    for (int r = row_begin; r < row_end; ++r)
+        if (h_end[r] > h_begin[r]) p->base = std::min<long long>(p->base, h_begin[r]);
 
     const int max_chunk = (int)env_long("CUMF_SPLIT_NNZ", path == CUMF_PATH_TC ? 8192 : 4096);
     const int owned = row_end - row_begin;
@@ -188,8 +195,9 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
     int slot = 0;
     for (int r = row_begin; r < row_end; ++r) {
         p->row_chunk_ptr[r - row_begin] = (int)p->chunks.size();
-        const long long s = (long long)h_rowptr[r] - p->base, e = (long long)h_rowptr[r + 1] - p->base;
-        const long long n = e - s;
+        const long long n = h_end[r] - h_begin[r];
+        // an empty row keeps a (0,0) chunk so that it still gets its lambda*0 system / zero partial
+        const long long s = n > 0 ? h_begin[r] - p->base : 0, e = s + n;
         if (n < 0 || e > 0x7fffffffLL) {
             plan_free(p);
             set_last_error("row pointers must be non-decreasing and a shard must hold < 2^31 ratings");
@@ -249,10 +257,6 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
     return CUMF_OK;
 }
 
-extern "C" int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
-                                int path) {
-    return plan_create_impl(out, h_rowptr, rows, row_begin, row_end, f, path, true);
-}
 
 extern "C" int cumf_plan_destroy(cumf_plan* plan) {
     plan_free(plan);
@@ -272,6 +276,67 @@ static void plan_time_end(cumf_plan* p, cudaStream_t st, cudaEvent_t e0, cudaEve
     cudaEventRecord(e1, st);
     p->kernel_events.emplace_back(e0, e1);
 }
+static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
+                            int path, bool alloc_workspace, bool force_slots = false) {
+    CUMF_REQUIRE(out && h_rowptr, "null pointer");
+    CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
+    std::vector<long long> b(rows + 1), e(rows + 1);
+    for (int r = row_begin; r < row_end; ++r) { b[r] = h_rowptr[r]; e[r] = h_rowptr[r + 1]; }
+    return plan_create_core(out, b.data(), e.data(), rows, row_begin, row_end, f, path, alloc_workspace, force_slots);
+}
+
+extern "C" int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
+                                int path) {
+    return plan_create_impl(out, h_rowptr, rows, row_begin, row_end, f, path, true);
+}
+
+// Partial-Gram plan: all `rows` rows, row r restricted to ratings [h_begin[r], h_end[r]).  On the fused path
+// every chunk stores its partial [A|b] (nothing is solved in-kernel), so the plan carries one slot per chunk.
+extern "C" int cumf_plan_create_ranges(cumf_plan** out, const long long* h_begin, const long long* h_end, int rows,
+                                       int f, int path) {
+    CUMF_REQUIRE(path == CUMF_PATH_SIMT || path == CUMF_PATH_TC || path == CUMF_PATH_AUTO, "path");
+    if (path == CUMF_PATH_AUTO) path = tc_path_supports(f) ? CUMF_PATH_TC : CUMF_PATH_SIMT;
+    return plan_create_core(out, h_begin, h_end, rows, 0, rows, f, path, false, path == CUMF_PATH_TC);
+}
+
+// [A|b] of every row of the plan over the plan's rating ranges, lambda * (ratings in range) on the diagonal
+// (the per-GPU partial of hugewiki.cu:1675-1678 when the ranges are one GPU's share); tt is [rows][f*f],
+// rhs is [rows][f].  Asynchronous on `stream`.
+extern "C" int cumf_plan_gram(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
+                              float lambda, float* d_tt, float* d_rhs, void* stream) {
+    CUMF_REQUIRE(p && d_colidx && d_val && d_factor && d_tt && d_rhs, "null pointer");
+    CUMF_REQUIRE(p->row_begin == 0 && p->row_end == p->rows, "cumf_plan_gram needs a plan over all its rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int f = p->f;
+    const long long base = p->base;
+    p->last_launches = 0;
+    cudaEvent_t e0, e1;
+    plan_time_begin(p, st, &e0, &e1);
+    if (p->path == CUMF_PATH_TC) {
+        CUMF_REQUIRE(p->splits.size() == (size_t)p->rows, "plan was not created by cumf_plan_create_ranges");
+        int launches = 0;
+        CUMF_TRY(tc_update_factor(p->tc, p->d_chunks.as<Chunk>(), (int)p->chunks.size(), d_colidx + base, d_val + base,
+                                  d_factor, nullptr, f, lambda, 0.f, p->scratchA.as<float>(), p->scratchB.as<float>(),
+                                  st, &launches));
+        p->last_launches += launches;
+        CUMF_TRY(launch_split_reduce(p->d_splits.as<SplitRow>(), 0, (int)p->splits.size(), f, lambda, 0, 0, d_tt, d_rhs,
+                                     p->scratchA.as<float>(), p->scratchB.as<float>(), st));
+        p->last_launches += 1;
+    } else {
+        CUMF_TRY(launch_gram_simt(p->d_chunks.as<Chunk>(), 0, (int)p->chunks.size(), d_colidx + base, d_val + base,
+                                  d_factor, f, lambda, 0, d_tt, d_rhs, p->scratchA.as<float>(),
+                                  p->scratchB.as<float>(), st));
+        p->last_launches += 1;
+        if (!p->splits.empty()) {
+            CUMF_TRY(launch_split_reduce(p->d_splits.as<SplitRow>(), 0, (int)p->splits.size(), f, lambda, 0, 0, d_tt,
+                                         d_rhs, p->scratchA.as<float>(), p->scratchB.as<float>(), st));
+            p->last_launches += 1;
+        }
+    }
+    plan_time_end(p, st, e0, e1);
+    return CUMF_OK;
+}
+
 static double plan_collect_kernel_ms(cumf_plan* p) {
     for (auto& e : p->kernel_events) {
         float ms = 0.f;

@@ -135,6 +135,26 @@ int cumf_update_factor(cumf_plan* plan, const int* d_colidx, const float* d_val,
                        const float* d_factor, float* d_out, float lambda, int solver, float cgIter,
                        void* stream);
 
+/* ---- data-parallel partial Gram (the multi-GPU form of hugewiki.cu:2629-2696) ---
+ * When the OPPOSING factor is sharded by rows across GPUs, GPU g forms, for every
+ * row u of the side being updated, the partial system over the ratings whose
+ * column id falls in g's shard.  Column ids are sorted inside a CSR row, so that
+ * share is one contiguous range [h_begin[u], h_end[u]) of the row's ratings
+ * (absolute positions in colidx/val; h_begin[u] == h_end[u] for "none").
+ * cumf_plan_create_ranges builds the work decomposition for those ranges;
+ * cumf_plan_gram materialises
+ *   tt[u]  = sum_{j in range(u)} theta_j theta_j^T + lambda * |range(u)| * I
+ *   rhs[u] = sum_{j in range(u)} r_uj theta_j
+ * (lambda scaled by the LOCAL count, hugewiki.cu:1675-1678, so that the sum over
+ * GPUs carries lambda * n_u).  The caller all-reduces tt and rhs over the GPUs
+ * (hugewiki.cu:2769-2827 does it with peer copies + reduce kernels; here NCCL on
+ * the same device pointers) and solves with cumf_cg / cumf_lu.  d_colidx / d_val
+ * are the FULL arrays the positions index.  Asynchronous on `stream`.          */
+int cumf_plan_create_ranges(cumf_plan** out, const long long* h_begin, const long long* h_end,
+                            int rows, int f, int path);
+int cumf_plan_gram(cumf_plan* plan, const int* d_colidx, const float* d_val, const float* d_factor,
+                   float lambda, float* d_tt, float* d_rhs, void* stream);
+
 /* ---- resident solver handle (what cumf_doALS is built from) -------------------
  * Uploads CSR/CSC/COO once (the reference re-uploads CSR every iteration,
  * als.cu:734-739) and keeps the factors on the device.  Row ranges select the

@@ -380,3 +380,75 @@ def test_doals_fused_midsize_vs_simt(cuda):
     rows = np.linalg.norm(th_tc.astype(np.float64) - th_si, axis=1) / np.linalg.norm(th_si.astype(np.float64), axis=1)
     print("fused vs simt after 3 iterations: median row rel", np.median(rows), "fro", rel_fro(th_tc, th_si))
     assert np.median(rows) < 2e-3
+
+
+# ---- partial Gram over per-row rating ranges (multi-GPU form, hugewiki.cu:1675-1678, 2629-2696) -----------------
+@pytest.mark.parametrize("f,path", [(20, c.PATH_SIMT), (100, c.PATH_SIMT), (100, c.PATH_TC)])
+def test_plan_gram_ranges_vs_oracle(cuda, f, path):
+    """cumf_plan_create_ranges + cumf_plan_gram: [A|b] over a sub-range of every row, lambda * local count."""
+    rng = np.random.default_rng(11)
+    n, lam = 3000, 0.05
+    lengths = [0, 1, 16, 17, 40, 333, 5, 64, 1200, 2, 90, 31] * 14
+    rowptr, colidx, val = random_csr(rng, lengths, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    rows = len(lengths)
+    # columns [t0, t1): the share of one of three "GPUs"; some rows get nothing
+    from cumf_als_b200.dist import compact_share, local_share
+    t0, t1 = 1000, 2100
+    begin, end = local_share(rowptr, colidx, t0, t1)
+    assert (end - begin).min() == 0 and (end - begin).max() > 300
+    plan = c.Plan.from_ranges(begin, end, f, path)
+    tt = cuda.full((rows, f * f), float("nan"), dtype=cuda.float32, device="cuda")
+    rhs = cuda.full((rows, f), float("nan"), dtype=cuda.float32, device="cuda")
+    plan.gram(dev(cuda, colidx), dev(cuda, val), dev(cuda, factor), lam, tt, rhs)
+    cuda.cuda.synchronize()
+    tt, rhs = tt.cpu().numpy().reshape(rows, f, f), rhs.cpu().numpy()
+    ip, ccol, cval = compact_share(rowptr, colidx, val, t0, t1)
+    ref = O.gram(ip.astype(np.int32), ccol, factor, f, lam)
+    ref_b = O.rhs(ip.astype(np.int32), ccol, cval, factor, f)
+    if path == c.PATH_SIMT:
+        assert np.array_equal(tt, ref) and np.array_equal(rhs, ref_b)          # same FMA chain: bit-exact
+    else:
+        for u in range(rows):
+            scale = max(np.abs(ref[u]).max(), 1e-30)
+            assert np.abs(tt[u] - ref[u]).max() / scale < 3e-6, (u, lengths[u])
+        assert np.allclose(rhs, ref_b, rtol=1e-5, atol=1e-4)
+    empty = np.flatnonzero(end == begin)
+    assert not tt[empty].any() and not rhs[empty].any()                          # lambda * 0: an all-zero partial
+    plan.close()
+
+
+@pytest.mark.parametrize("f,path", [(20, c.PATH_SIMT), (100, c.PATH_TC)])
+def test_partial_gram_engines_two_shares_on_one_gpu(cuda, f, path):
+    """The E2 iteration with two theta shards living on one GPU (the all-reduce replaced by an explicit sum):
+    X replicated without exchange, theta rank-local, result == the unsharded oracle run to fp32 tolerance."""
+    from cumf_als_b200.data import nnz_balanced_ranges
+    from cumf_als_b200.dist import GpuPartialGramEngine
+    r = synth_ratings(700, 1500, 60000, 3000, seed=21)
+    lam, iters = 0.05, 2
+    theta0, x0 = init_factors(r.m, r.n, f, seed=6)
+    tr = nnz_balanced_ranges(r.csc_indptr, 2)
+    engs = [GpuPartialGramEngine(r, f, lam, theta0, x0, t, 0, path=path, cap_bytes=4 * f * (f + 1) * 300) for t in tr]
+    assert len(engs[0].batches) == 3 and engs[0].local_nnz + engs[1].local_nnz == r.nnz
+    for _ in range(iters):
+        for b in range(len(engs[0].batches)):
+            parts = [e.partial_gram(b) for e in engs]
+            tt, rhs = parts[0][0] + parts[1][0], parts[0][1] + parts[1][1]
+            for e in engs:
+                e.solve_x(b, tt.clone(), rhs.clone())
+        for e in engs:
+            e.update_theta()
+    cuda.cuda.synchronize()
+    assert cuda.equal(engs[0].x, engs[1].x)
+    theta = engs[0].theta.clone()
+    theta[tr[1][0]:tr[1][1]] = engs[1].theta[tr[1][0]:tr[1][1]]
+    sse = np.sum([e.sse() for e in engs], axis=0)
+    th_o, X_o = theta0.copy(), x0.copy()
+    fin_o, hist = O.do_als(r, th_o, X_o, f, lam, iters, 0)
+    eff = 256 * ((r.nnz_test - 1) // 256)
+    assert np.sqrt(sse[0] / r.nnz) == pytest.approx(float(hist[-1, 0]), rel=TOL)
+    # the oracle divides by nnz_test although it sums `eff` samples (als.cu:1006-1018)
+    assert np.sqrt(sse[1] / r.nnz_test) == pytest.approx(float(hist[-1, 1]), rel=TOL)
+    assert eff <= r.nnz_test
+    assert rel_fro(engs[0].x.cpu().numpy(), X_o) < 10 * TOL
+    assert rel_fro(theta.cpu().numpy(), th_o) < 10 * TOL
