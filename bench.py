@@ -321,11 +321,11 @@ def run_ours_partial_gram(args, w):
         barrier()
     # one more, instrumented, iteration for the phase split (outside the timed region)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    ev[0].record()
-    parts = [eng.partial_gram(b) for b in range(len(eng.batches))] if len(eng.batches) == 1 else None
     phases = None
-    if parts is not None:
-        tt, rhs = parts[0]
+    if len(eng.batches) == 1:
+        barrier()
+        ev[0].record()
+        tt, rhs = eng.partial_gram(0)
         ev[1].record()
         if world > 1:
             dist.all_reduce(tt)

@@ -79,15 +79,25 @@ constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
 static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
-// accumulator tile, 256 TMEM columns:  [0,112) P = hi^T hi | 112 hi^T r_hi | 113 hi^T r_lo' |
-//                                      [128,240) S = hi^T lo' + lo'^T hi | 240 lo'^T r_hi
-// from two MMAs per k-step:  D[:,0:256] (+)= hi^T [hi | r | lo' | 0]   and   D[:,128:256] += lo'^T [hi | r]
+// accumulator tile, one MMA per k-step:  D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']
+//   lanes 0..99 (features i):  [0,112) P[i][:] = hi_i . hi_j | 112 hi_i . r_hi | 113 hi_i . r_lo' | [128,240) S[i][:] = hi_i . lo'_j
+//   lane 112 (the r_hi row):   [0,112) r_hi . hi_j                                                | [128,240) r_hi . lo'_j
+// The symmetric half of the cross term (lo'^T hi = S^T) is not computed by the tensor core: the epilogue forms
+//   G = P/2 + S/2048  (row i per thread, lane 112 carries the rating row)   and   [A|b] = G + G^T
+// through a shared-memory transpose once per chunk.  That halves the MMA work of the cross terms and the
+// operand bytes the tensor core reads per k-step.
 constexpr int ACC_COLS = 256;
+constexpr int N1_SYM = 240;               // kSym: B = operand rows [0,240), A = rows [0,128)
+// !kSym (short rows, where the solver warpgroups are the bottleneck and the transpose would cost more than the
+// MMA it saves): the tensor core also forms lo'^T [hi | r] onto columns [128,256), so S = hi^T lo' + lo'^T hi,
+// column 240 = lo'^T r_hi, and row i of [A|b] = P + S/2048 needs no exchange between threads.
 constexpr int N1 = 256;                   // B = all 256 operand rows, A = hi
 constexpr int N2 = 128;                   // B = rows [0,128) (hi, r), A = lo', D columns [128,256)
+constexpr int BCOL_LO = LO_ROW + R_ROW;   // 240: TMEM column of  lo'^T r_hi  (!kSym)
 constexpr int SCOL = LO_ROW;              // 128: first TMEM column of S
 constexpr int BCOL_HI = R_ROW;            // 112: TMEM column of  hi^T r_hi  (next column: hi^T r_lo')
-constexpr int BCOL_LO = SCOL + R_ROW;     // 240: TMEM column of  lo'^T r_hi
+constexpr int TR_ROWS = 50;               // rows of G exchanged per transpose pass (2 passes cover f = 100)
+static_assert(2 * TR_ROWS == F, "two transpose passes");
 constexpr float kLoScale = 2048.0f;
 constexpr float kLoInv = 1.0f / 2048.0f;
 // cg.cu:31,195: `rsnew < 1e-4` compares in double.  For a float rsnew that is exactly
@@ -110,6 +120,7 @@ struct __align__(128) Smem {   // dynamic shared memory, used in place
     unsigned char op_stage[S2][OP_STAGE_BYTES];     // 61440
     float stage_vals[S1][KT];    // the ratings of the stage in flight in each fp32 slot (zero beyond cnt)
     uint32_t meta_op[S2];        // stage flags forwarded to the MMA warp
+    float tr[2][(TR_ROWS + 1) * F];   // per solver warpgroup: TR_ROWS rows of G (+ the rating row) for the transpose
     float sp[2][2][128];         // CG direction vector per solver warpgroup, double buffered
     float red[2][3][4];          // cross-warp partial sums
     unsigned long long full_f32[S1], full_op[S2], empty_op[S2];
@@ -119,6 +130,8 @@ struct __align__(128) Smem {   // dynamic shared memory, used in place
     unsigned long long acc_full[2][2], acc_empty[2];
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt into");
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -224,9 +237,11 @@ __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, in
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// drain one TMEM accumulator tile (row i of [P | S | b]) into / onto the register copy of [A | b]
-template <bool kFirst>
+// drain one TMEM accumulator tile into / onto the register copy of row i:
+//   kSym:  G = P/2 + S/2048 and its rating column (symmetrised later);   !kSym:  [A|b] = P + S/2048 directly
+template <bool kFirst, bool kSym>
 __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float& b) {
+    constexpr float kP = kSym ? 0.5f : 1.0f;
 #pragma unroll
     for (int cc = 0; cc < 96; cc += 16) {
         uint32_t p[16], s[16];
@@ -235,7 +250,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float v = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+            const float v = fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j]));
             a[cc + j] = kFirst ? v : a[cc + j] + v;
         }
     }
@@ -243,14 +258,15 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
     tmem_ld4(taddr + 96, p);
     tmem_ld4(taddr + SCOL + 96, s);
     tmem_ld4(taddr + BCOL_HI, bh);      // hi^T r_hi, hi^T r_lo'
-    tmem_ld4(taddr + BCOL_LO, bl);      // lo'^T r_hi
+    if (!kSym) tmem_ld4(taddr + BCOL_LO, bl);      // lo'^T r_hi
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float v = fmaf(__uint_as_float(s[j]), kLoInv, __uint_as_float(p[j]));
+        const float v = fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j]));
         a[96 + j] = kFirst ? v : a[96 + j] + v;
     }
-    const float tb = fmaf(__uint_as_float(bh[1]) + __uint_as_float(bl[0]), kLoInv, __uint_as_float(bh[0]));
+    const float tb = kSym ? fmaf(__uint_as_float(bh[1]), kLoInv, 0.5f * __uint_as_float(bh[0]))
+                          : fmaf(__uint_as_float(bh[1]) + __uint_as_float(bl[0]), kLoInv, __uint_as_float(bh[0]));
     b = kFirst ? tb : b + tb;
 }
 
@@ -275,6 +291,7 @@ __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const 
     }
 }
 
+template <bool kSym>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
@@ -322,21 +339,23 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
             // divergent path); one elected lane issues the tcgen05 instructions.  The loop is unrolled over
             // the 8 operand slots so every shared-memory descriptor is base + compile-time constant.
-            constexpr uint32_t idesc1 = make_idesc(128, N1);
+            constexpr uint32_t idesc1 = make_idesc(128, kSym ? N1_SYM : N1);
             constexpr uint32_t idesc2 = make_idesc(128, N2);
             const uint32_t op_base0 = smem_u32(&sm.op_stage[0][0]);
             const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
             int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
             int done = 0;           // chunks finished
-            // one k-step: D[:, 0:256] (+)= hi^T [hi | r | lo' | 0] ;  D[:, 128:256] += lo'^T [hi | r]
+            // one k-step: D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']   (+ D[:, 128:256] += lo'^T [hi | r] if !kSym)
             auto issue_step = [&](int slot, uint32_t flags, int buf, int chunk_parity) {
                 // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and the
                 // whole ring lies below the field's 256 KB wrap, so plain addition is exact
-                const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);                                    // rows 0..   : hi | r | lo' | 0
-                const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);    // rows 128.. : lo' | 0
+                const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
                 umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
-                umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
+                if (!kSym) {
+                    const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);    // rows 128.. : lo' | 0
+                    umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
+                }
                 umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
                 if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[chunk_parity][buf]);   // chunk c belongs to solver warpgroup c & 1
             };
@@ -511,20 +530,55 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 if (((c - c_begin) & 1) != wg) { q += tiles; continue; }
                 float a[F];
                 float bi = 0.f;
+                // warm start x_u (cg.cu:47): requested before the tile waits so its latency is hidden behind them
+                float* xrow = out + (size_t)ck.row * F;
+                float xi = (active && ck.slot < 0) ? xrow[i] : 0.f;
                 for (int tile = 0; tile < tiles; ++tile, ++q) {
                     const int buf = q & 1;
                     if (buf == 0) { mbar_wait(&sm.acc_full[wg][0], seen0 & 1u); ++seen0; }
                     else          { mbar_wait(&sm.acc_full[wg][1], seen1 & 1u); ++seen1; }
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * ACC_COLS);
-                    // tile = hi^T hi + (hi^T lo' + lo'^T hi)/2048 over <= SUB_STEPS k-steps; the tiles of one chunk
+                    // tile = (hi^T hi)/2 + (hi^T lo')/2048 over <= SUB_STEPS k-steps; the tiles of one chunk
                     // are summed here in fp32 (round-to-nearest), which bounds the length of the tensor core's
                     // own (truncating) accumulation chain
-                    if (tile == 0) drain_tile<true>(taddr, a, bi);
-                    else drain_tile<false>(taddr, a, bi);
+                    if (tile == 0) drain_tile<true, kSym>(taddr, a, bi);
+                    else drain_tile<false, kSym>(taddr, a, bi);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);       // accumulator drained
+                }
+
+                // ---- [A | b] = G + G^T: rows of G go through shared memory, TR_ROWS at a time.  Thread i adds
+                // G[j][i] to its G[i][j]; where row j was symmetrised in an earlier pass (i < base) the buffer
+                // already holds the finished A[j][i], which is taken as is (A is symmetric bit for bit).
+                if (kSym) {
+                    float* tb = sm.tr[wg];
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        constexpr int kRowFloat4 = F / 4;
+                        const int base = pass * TR_ROWS;
+                        if (i >= base && i < base + TR_ROWS) {
+                            float4* dst = reinterpret_cast<float4*>(tb + (i - base) * F);
+#pragma unroll
+                            for (int j = 0; j < kRowFloat4; ++j) dst[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                        }
+                        if (pass == 0 && i == R_ROW) {          // lane 112: r_hi . (hi_j/2 + lo'_j/2048)
+                            float4* dst = reinterpret_cast<float4*>(tb + TR_ROWS * F);
+#pragma unroll
+                            for (int j = 0; j < kRowFloat4; ++j) dst[j] = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                        }
+                        named_bar_sync(bar_id, 128);
+                        if (active) {
+                            if (pass == 0) bi += tb[TR_ROWS * F + i];
+#pragma unroll
+                            for (int jj = 0; jj < TR_ROWS; ++jj) {
+                                const float v = tb[jj * F + i];
+                                a[pass * TR_ROWS + jj] = (i < base) ? v : a[pass * TR_ROWS + jj] + v;
+                            }
+                        }
+                        named_bar_sync(bar_id, 128);             // all reads done before the buffer is rewritten
+                    }
                 }
 
                 if (ck.slot >= 0) {
@@ -542,8 +596,6 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const float reg = (float)(ck.end - ck.begin) * lambda;
 
                 // ---- CG (cg.cu:47-230), A row i in registers, p broadcast from shared memory ----
-                float* xrow = out + (size_t)ck.row * F;
-                float xi = active ? xrow[i] : 0.f;
                 auto spmv = [&](const float* sp, float self) -> float {   // four independent FMA chains, summed pairwise
                     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
@@ -601,6 +653,7 @@ struct TcWork {
     DevBuf stage_tab;                   // StageDesc per k-step, chunk order
     int grid = 0;
     int nchunks = 0;
+    bool sym = false;                   // long chunks: the tensor core forms half of the cross term, the epilogue transposes
     CUtensorMap factor_map;             // 2-D view [rows][F] fp32 of the opposing factor, box {F, 1}
     const float* mapped_factor = nullptr;
 };
@@ -690,6 +743,12 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     TcWork* w = new TcWork();
     w->grid = grid;
     w->nchunks = n;
+    {   // per-chunk epilogue cost (transpose) vs per-k-step MMA saving: the symmetric mode pays from ~32 k-steps per chunk;
+        // measured on Netflix: X side (348 k-steps/chunk) 9.6 -> 8.6 ms, theta side (13 k-steps/chunk) 14.8 -> 16.2 ms
+        const char* m = getenv("CUMF_TC_SYM");
+        const long long sym_min_steps = 64;
+        w->sym = (m && *m) ? (*m == '1') : (n > 0 && (long long)stage_base[n] >= sym_min_steps * n);
+    }
     DevBuf d_base;
     int rc = w->cta_ptr.alloc(sizeof(int) * (grid + 1));
     if (rc == CUMF_OK) rc = w->cta_stage_ptr.alloc(sizeof(int) * (grid + 1));
@@ -734,7 +793,8 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     const size_t smem = sizeof(Smem);
     static bool attr_set = false;
     if (!attr_set) {
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     if (w->mapped_factor != d_factor) {
@@ -744,9 +804,10 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     }
     const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
     const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
-    als_fused_f100_kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
-                                                            w->cta_stage_ptr.as<int>(), d_colidx, d_val, w->factor_map,
-                                                            d_out, lambda, cg_iter, d_scratchA, d_scratchB, desc_tmpl);
+    auto kernel = w->sym ? als_fused_f100_kernel<true> : als_fused_f100_kernel<false>;
+    kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
+                                             w->cta_stage_ptr.as<int>(), d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter,
+                                             d_scratchA, d_scratchB, desc_tmpl);
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;
     return CUMF_OK;
