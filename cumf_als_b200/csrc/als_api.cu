@@ -148,6 +148,12 @@ struct cumf_plan {
     int batch_rows = 0;
     int last_launches = 0;
     TcWork* tc = nullptr;
+    // Optional by-product of a fused CG half-step: per solver warpgroup (2 x CTAs) and per split row the sum of
+    // x^T b + x^T r + reg x^T x, from which the squared error of the rows' ratings follows (gram_tc.cu).  Enabled by
+    // the resident solver for the train RMSE; valid until the opposing factor changes.
+    bool collect_sse = false, sse_terms_valid = false;
+    DevBuf sse_terms;
+    int sse_terms_count = 0;
     // optional timing of the dominant (Gram) kernel
     bool time_kernel = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
@@ -157,7 +163,7 @@ struct cumf_plan {
 static void plan_free(cumf_plan* p) {
     if (!p) return;
     p->d_chunks.release(); p->d_splits.release();
-    p->scratchA.release(); p->scratchB.release(); p->tt.release(); p->rhs.release();
+    p->scratchA.release(); p->scratchB.release(); p->tt.release(); p->rhs.release(); p->sse_terms.release();
     if (p->tc) tc_plan_destroy(p->tc);
     for (auto& e : p->kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete p;
@@ -372,19 +378,33 @@ extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float
     const SplitRow* d_splits = p->d_splits.as<SplitRow>();
 
     if (p->path == CUMF_PATH_TC && solver == CUMF_SOLVER_CG) {
+        const int ns = (int)p->splits.size();
+        double* terms = nullptr;
+        p->sse_terms_valid = false;
+        if (p->collect_sse) {
+            const int want = 2 * tc_plan_grid(p->tc) + ns;
+            if (p->sse_terms_count != want) {
+                p->sse_terms.release();
+                CUMF_TRY(p->sse_terms.alloc(sizeof(double) * std::max(1, want)));
+                p->sse_terms_count = want;
+            }
+            terms = p->sse_terms.as<double>();
+            CUMF_CUDA_TRY(cudaMemsetAsync(terms, 0, sizeof(double) * std::max(1, want), st));
+        }
         cudaEvent_t e0, e1;
         plan_time_begin(p, st, &e0, &e1);
         CUMF_TRY(tc_update_factor(p->tc, d_chunks, (int)p->chunks.size(), d_colidx, d_val, d_factor, d_out,
-                                  f, lambda, cgIter, p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches));
+                                  f, lambda, cgIter, p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches, terms));
         plan_time_end(p, st, e0, e1);
         // rows that were split across CTAs: reduce their partials into a compact batch, solve it
-        const int ns = (int)p->splits.size();
         if (ns > 0) {
             CUMF_TRY(launch_split_reduce(d_splits, 0, ns, f, lambda, /*compact=*/1, 0, p->tt.as<float>(),
                                          p->rhs.as<float>(), p->scratchA.as<float>(), p->scratchB.as<float>(), st));
-            CUMF_TRY(launch_cg(p->tt.as<float>(), d_out, p->rhs.as<float>(), ns, f, cgIter, d_splits, st));
+            CUMF_TRY(launch_cg(p->tt.as<float>(), d_out, p->rhs.as<float>(), ns, f, cgIter, d_splits, st, lambda,
+                               terms ? terms + 2 * tc_plan_grid(p->tc) : nullptr));
             launches += 2;
         }
+        p->sse_terms_valid = (terms != nullptr);
         p->last_launches = launches;
         return CUMF_OK;
     }
@@ -543,6 +563,17 @@ struct cumf_als_solver {
     long train_cnt = 0, test_cnt = 0;
     DevBuf theta, x;                    // full replicas
     DevBuf sse, partials;
+    // uploads run on their own (non-blocking) stream; the first use of each group waits on its event, so the
+    // first X half-step overlaps the CSC upload and the first theta half-step the COO/test upload
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_csr = nullptr, ev_csc = nullptr, ev_rmse = nullptr;
+    // train RMSE walk: -1 undecided, 0 literal (cooRow[i], csrCol[i], csrVal[i]) pairs, 1 by CSC columns (theta row
+    // in registers, X gathered), 2 by CSR rows (X row in registers, theta gathered); 1/2 need cooRow == CSR rows
+    int train_mode = -1;
+    // train RMSE from the theta half-step's by-product (plan.sse_terms): needs the whole matrix on this GPU, the fused
+    // CG path, cooRow == CSR rows, and X untouched since that half-step
+    bool theta_fresh = false;
+    double sum_r2 = -1.0;               // sum of squared train ratings (computed on first use)
     cumf_plan* px = nullptr;
     cumf_plan* pt = nullptr;
     // timers
@@ -558,24 +589,33 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     s->theta.release(); s->x.release(); s->sse.release(); s->partials.release();
     plan_free(s->px);
     plan_free(s->pt);
+    if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
+    if (s->ev_csr) cudaEventDestroy(s->ev_csr);
+    if (s->ev_csc) cudaEventDestroy(s->ev_csc);
+    if (s->ev_rmse) cudaEventDestroy(s->ev_rmse);
     delete s;
     return CUMF_OK;
 }
 
+// Asynchronous when `host` is pinned (the reference CLI's buffers are, main.cpp:50-69); from pageable memory the
+// runtime stages the copy and the call returns when the source has been read -- same result either way.
 template <typename T>
-static int upload(DevBuf& buf, const T* host, size_t count) {
+static int upload(DevBuf& buf, const T* host, size_t count, cudaStream_t st) {
     CUMF_TRY(buf.alloc(sizeof(T) * count));
-    if (count) CUMF_CUDA_TRY(cudaMemcpy(buf.p, host, sizeof(T) * count, cudaMemcpyHostToDevice));
+    if (count) CUMF_CUDA_TRY(cudaMemcpyAsync(buf.p, host, sizeof(T) * count, cudaMemcpyHostToDevice, st));
     return CUMF_OK;
 }
 
-extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
-                               const float* csrValHostPtr, const int* cscRowIndexHostPtr,
-                               const int* cscColIndexHostPtr, const float* cscValHostPtr,
-                               const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
-                               const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
-                               long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
-                               int device, int solver, int path) {
+// wait_uploads = false leaves the rating uploads in flight when it returns (the half-steps and the RMSE wait on
+// their events): only for callers that keep the host arrays alive until the first RMSE, i.e. cumf_doALS.
+static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                           const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                           const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                           const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                           const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                           long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                           int device, int solver, int path, bool wait_uploads,
+                           const float* thetaTHost = nullptr, const float* XTHost = nullptr) {
     CUMF_REQUIRE(out && csrRowIndexHostPtr && csrColIndexHostPtr && csrValHostPtr && cscRowIndexHostPtr &&
                      cscColIndexHostPtr && cscValHostPtr, "null pointer");
     CUMF_REQUIRE(m > 0 && n > 0 && nnz >= 0 && nnz_test >= 0, "bad sizes");
@@ -596,12 +636,40 @@ extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHost
     // cscColIndex is the pointer array (n+1), cscRowIndex the row ids (nnz).
     const long long xo = csrRowIndexHostPtr[x_begin], xn = (long long)csrRowIndexHostPtr[x_end] - xo;
     const long long to = cscColIndexHostPtr[t_begin], tn = (long long)cscColIndexHostPtr[t_end] - to;
-    if ((rc = upload(s->csr_col, csrColIndexHostPtr + xo, (size_t)xn)) != CUMF_OK) return fail(rc);
-    if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn)) != CUMF_OK) return fail(rc);
-    if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn)) != CUMF_OK) return fail(rc);
-    if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn)) != CUMF_OK) return fail(rc);
+    // Work plans first: their small synchronous copies would otherwise queue behind the rating uploads on the
+    // copy engine.  Factors and scratch next, then the ratings in the order the iteration needs them.
+    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
+    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
+    s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
+    // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
+    s->pt->collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
+                          solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr && env_long("CUMF_SSE_DIRECT", 0) == 0);
+    if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
+    if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
+    if (cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_csr, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_csc, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_rmse, cudaEventDisableTiming) != cudaSuccess) {
+        set_last_error("cumf_als_create: cannot create the upload stream");
+        return fail(CUMF_ECUDA);
+    }
+    cudaStream_t up = s->up_stream;
+    // initial factors (optional here; cumf_als_set_factors otherwise) go first: the X half-step needs them
+    if ((thetaTHost && cudaMemcpyAsync(s->theta.p, thetaTHost, sizeof(float) * (size_t)n * f, cudaMemcpyHostToDevice, up) != cudaSuccess) ||
+        (XTHost && cudaMemcpyAsync(s->x.p, XTHost, sizeof(float) * (size_t)m * f, cudaMemcpyHostToDevice, up) != cudaSuccess)) {
+        set_last_error("cumf_als_create: factor upload failed");
+        return fail(CUMF_ECUDA);
+    }
+    if ((rc = upload(s->csr_col, csrColIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
+    if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
+    cudaEventRecord(s->ev_csr, up);
+    if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
+    if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
+    cudaEventRecord(s->ev_csc, up);
     if (cooRowIndexHostPtr) {
-        if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn)) != CUMF_OK) return fail(rc);
+        if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
         s->train_cnt = (long)xn;
     }
     if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
@@ -609,20 +677,31 @@ extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHost
         // shard's share is the contiguous slice proportional to its X row range.
         const long long eff = ((long long)(nnz_test - 1) / 256) * 256;
         const long long t0 = eff * x_begin / m, t1 = eff * x_end / m;
-        if ((rc = upload(s->test_row, cooRowIndexTestHostPtr + t0, (size_t)(t1 - t0))) != CUMF_OK) return fail(rc);
-        if ((rc = upload(s->test_col, cooColIndexTestHostPtr + t0, (size_t)(t1 - t0))) != CUMF_OK) return fail(rc);
-        if ((rc = upload(s->test_val, cooValHostTestPtr + t0, (size_t)(t1 - t0))) != CUMF_OK) return fail(rc);
+        if ((rc = upload(s->test_row, cooRowIndexTestHostPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
+        if ((rc = upload(s->test_col, cooColIndexTestHostPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
+        if ((rc = upload(s->test_val, cooValHostTestPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
         s->test_cnt = (long)(t1 - t0);
     }
-    if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
-    if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
-    if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
-    if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
-    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
-    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
-    s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
+    cudaEventRecord(s->ev_rmse, up);
+    if (wait_uploads && cudaStreamSynchronize(s->up_stream) != cudaSuccess) {
+        set_last_error(std::string("cumf_als_create: upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+        return fail(CUMF_ECUDA);
+    }
     *out = s;
     return CUMF_OK;
+}
+
+extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                               const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                               const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                               const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                               const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                               long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                               int device, int solver, int path) {
+    return als_create_impl(out, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
+                           cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
+                           cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, x_begin, x_end,
+                           t_begin, t_end, device, solver, path, /*wait_uploads=*/true);
 }
 
 extern "C" int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost, const float* XTHost) {
@@ -630,6 +709,7 @@ extern "C" int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost,
     CUMF_CUDA_TRY(cudaSetDevice(s->device));
     CUMF_CUDA_TRY(cudaMemcpy(s->theta.p, thetaTHost, sizeof(float) * (size_t)s->n * s->f, cudaMemcpyHostToDevice));
     CUMF_CUDA_TRY(cudaMemcpy(s->x.p, XTHost, sizeof(float) * (size_t)s->m * s->f, cudaMemcpyHostToDevice));
+    s->theta_fresh = false;
     return CUMF_OK;
 }
 extern "C" int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float* XTHost) {
@@ -644,6 +724,8 @@ extern "C" float* cumf_als_x_ptr(cumf_als_solver* s) { return s ? s->x.as<float>
 
 extern "C" int cumf_als_update_x(cumf_als_solver* s, void* stream) {
     CUMF_REQUIRE(s, "null pointer");
+    CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_csr, 0));
+    s->theta_fresh = false;
     CUMF_TRY(cumf_update_factor(s->px, s->csr_col.as<int>(), s->csr_val.as<float>(), s->theta.as<float>(),
                                 s->x.as<float>(), s->lambda, s->solver, s->cg_iter, stream));
     s->launches += s->px->last_launches;
@@ -651,9 +733,11 @@ extern "C" int cumf_als_update_x(cumf_als_solver* s, void* stream) {
 }
 extern "C" int cumf_als_update_theta(cumf_als_solver* s, void* stream) {
     CUMF_REQUIRE(s, "null pointer");
+    CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_csc, 0));
     CUMF_TRY(cumf_update_factor(s->pt, s->csc_row.as<int>(), s->csc_val.as<float>(), s->x.as<float>(),
                                 s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream));
     s->launches += s->pt->last_launches;
+    s->theta_fresh = s->pt->sse_terms_valid;
     return CUMF_OK;
 }
 
@@ -662,11 +746,81 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
     cudaStream_t st = (cudaStream_t)stream;
     double h[2] = {0.0, 0.0};
     double* d = s->sse.as<double>();
+    CUMF_CUDA_TRY(cudaStreamWaitEvent(st, s->ev_csr, 0));
+    CUMF_CUDA_TRY(cudaStreamWaitEvent(st, s->ev_csc, 0));
+    CUMF_CUDA_TRY(cudaStreamWaitEvent(st, s->ev_rmse, 0));
     CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
-    if (train_sse && s->train_cnt > 0) {
-        // pairs cooRowIndex[i] with csrColIndex[i], csrVal[i] (als.cu:979-980)
-        CUMF_TRY(launch_sse(s->csr_val.as<float>(), s->coo_row.as<int>(), s->csr_col.as<int>(), s->theta.as<float>(),
-                            s->x.as<float>(), s->train_cnt, s->f, d, s->partials.as<double>(), sse_partial_capacity(), st));
+    if (train_sse && s->train_cnt > 0 && s->train_mode < 0) {
+        // The reference pairs cooRowIndex[i] with csrColIndex[i], csrVal[i] (als.cu:979-980).  When
+        // cooRowIndex is what the CSR row pointer says (every loader of the reference produces that), those samples
+        // are the matrix entries and can be walked row by row or column by column; otherwise keep the literal pairs.
+        s->train_mode = 0;
+        if (env_long("CUMF_SSE_LITERAL", 0) == 0) {
+            int* flag = reinterpret_cast<int*>(d);      // scratch: re-zeroed below
+            CUMF_TRY(launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(), flag, st));
+            int h_flag = 1;
+            CUMF_CUDA_TRY(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+            CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
+            s->launches += 1;
+            if (h_flag == 0) {
+                // gather from the smaller factor.  A row shard keeps the CSR walk: its sample set (the owned CSR rows)
+                // is then the same whatever the other ranks decide.
+                const bool whole = (s->xb == 0 && s->xe == s->m && s->tb == 0 && s->te == s->n);
+                s->train_mode = (whole && s->m <= s->n) ? 1 : 2;
+                s->coo_row.release();
+            }
+        }
+    }
+    bool train_done = false;
+    if (train_sse && s->train_cnt > 0 && s->train_mode != 0 && s->theta_fresh && s->pt->sse_terms_valid) {
+        // By-product path: the theta half-step left  T = sum_rows (x^T b + x^T r + reg x^T x)  and X has not changed
+        // since, so  train SSE = sum r^2 - T  (gram_tc.cu) with no further pass over the ratings.  The subtraction
+        // loses log10(sum r^2 / SSE) digits of the fp32 row terms (about 1.6 on rating data); the streaming kernel
+        // takes over when the fit is so tight that less than three digits would be left, or on any non-finite term.
+        if (s->sum_r2 < 0.0) {
+            CUMF_TRY(launch_sumsq(s->csc_val.as<float>(), (long)s->train_cnt, d, s->partials.as<double>(), sse_partial_capacity(), st));
+            double h_r2 = 0.0;
+            CUMF_CUDA_TRY(cudaMemcpyAsync(&h_r2, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+            s->sum_r2 = h_r2;
+            s->launches += 2;
+        }
+        CUMF_TRY(launch_sum_doubles(s->pt->sse_terms.as<double>(), s->pt->sse_terms_count, d, st));
+        double h_t = 0.0;
+        CUMF_CUDA_TRY(cudaMemcpyAsync(&h_t, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+        s->launches += 1;
+        const double sse_alg = s->sum_r2 - h_t;
+        if (std::isfinite(sse_alg) && sse_alg > 1e-3 * s->sum_r2) {
+            h[0] = sse_alg;
+            train_done = true;
+            if (env_long("CUMF_SSE_CHECK", 0) != 0) {
+                CUMF_TRY(launch_sse_chunks(s->pt->d_chunks.as<Chunk>(), (int)s->pt->chunks.size(), s->csc_row.as<int>(),
+                                           s->csc_val.as<float>(), s->theta.as<float>(), s->x.as<float>(), 1, s->f, d,
+                                           s->partials.as<double>(), sse_partial_capacity(), st));
+                double h_d = 0.0;
+                CUMF_CUDA_TRY(cudaMemcpyAsync(&h_d, d, sizeof(double), cudaMemcpyDeviceToHost, st));
+                CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+                printf("[CUMF_SSE_CHECK] train SSE by-product %.9e  streaming %.9e  rel diff %.3e  (sum r^2 %.6e)\n", sse_alg, h_d,
+                       (sse_alg - h_d) / h_d, s->sum_r2);
+            }
+        }
+        CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
+    }
+    if (train_sse && s->train_cnt > 0 && !train_done) {
+        if (s->train_mode == 1) {
+            CUMF_TRY(launch_sse_chunks(s->pt->d_chunks.as<Chunk>(), (int)s->pt->chunks.size(), s->csc_row.as<int>(),
+                                       s->csc_val.as<float>(), s->theta.as<float>(), s->x.as<float>(), 1, s->f, d,
+                                       s->partials.as<double>(), sse_partial_capacity(), st));
+        } else if (s->train_mode == 2) {
+            CUMF_TRY(launch_sse_chunks(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->csr_col.as<int>(),
+                                       s->csr_val.as<float>(), s->x.as<float>(), s->theta.as<float>(), 0, s->f, d,
+                                       s->partials.as<double>(), sse_partial_capacity(), st));
+        } else {
+            CUMF_TRY(launch_sse(s->csr_val.as<float>(), s->coo_row.as<int>(), s->csr_col.as<int>(), s->theta.as<float>(),
+                                s->x.as<float>(), s->train_cnt, s->f, d, s->partials.as<double>(), sse_partial_capacity(), st));
+        }
         s->launches += 2;
     }
     if (test_sse && s->test_cnt > 0) {
@@ -674,8 +828,11 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
                             s->x.as<float>(), s->test_cnt, s->f, d + 1, s->partials.as<double>(), sse_partial_capacity(), st));
         s->launches += 2;
     }
-    CUMF_CUDA_TRY(cudaMemcpyAsync(h, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    double hd[2] = {0.0, 0.0};
+    CUMF_CUDA_TRY(cudaMemcpyAsync(hd, d, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+    if (!train_done) h[0] = hd[0];
+    h[1] = hd[1];
     if (train_sse) *train_sse = h[0];
     if (test_sse) *test_sse = h[1];
     return CUMF_OK;
@@ -763,13 +920,13 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
     }
     cumf_als_solver* s = nullptr;
     const double t_setup = wall_seconds();
-    if (cumf_als_create(&s, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
+    // the host arrays outlive this call, so the uploads may still be in flight when the iterations start
+    if (als_create_impl(&s, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
                         cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
                         cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, 0, m, 0, n,
-                        DEVICEID, solver, path) != CUMF_OK)
+                        DEVICEID, solver, path, /*wait_uploads=*/false, thetaTHost, XTHost) != CUMF_OK)
         die("cumf_als_create");
-    if (cumf_als_set_factors(s, thetaTHost, XTHost) != CUMF_OK) die("cumf_als_set_factors");
-    if (debug) printf("\tsetup (upload + work plans) run %f seconds.\n", wall_seconds() - t_setup);
+    if (debug) printf("\tsetup (work plans; uploads continue in the background) run %f seconds.\n", wall_seconds() - t_setup);
     if (!quiet) printf("*******start iterations...\n");
     float final_rmse = 0.f;
     for (int iter = 0; iter < ITERS; ++iter) {
@@ -777,7 +934,7 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
         if (debug) printf("---------------------------ALS iteration %d, update X.----------------------------------\n", iter);
         if (cumf_als_update_x(s, nullptr) != CUMF_OK) die("update X");
         if (debug) {
-            cudaDeviceSynchronize();
+            cudaStreamSynchronize(0);
             if (solver == CUMF_SOLVER_CG) printf("\tCG solver with fp32.\n");
             printf("update X run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, m, f);
             t0 = wall_seconds();
@@ -785,13 +942,15 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
         }
         if (cumf_als_update_theta(s, nullptr) != CUMF_OK) die("update theta");
         if (debug) {
-            cudaDeviceSynchronize();
+            cudaStreamSynchronize(0);
             if (solver == CUMF_SOLVER_CG) printf("\tCG solver with fp32.\n");
             printf("update theta run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, n, f);
             printf("Calculate RMSE.\n");
         }
         double tr = 0.0, te = 0.0;
+        t0 = wall_seconds();
         if (cumf_als_sse(s, cooRowIndexHostPtr ? &tr : nullptr, &te, nullptr) != CUMF_OK) die("RMSE");
+        if (debug) printf("RMSE run %f seconds (train walk mode %d).\n", wall_seconds() - t0, s->train_mode);
         const float rmse_train = sqrtf((float)tr / (float)nnz);          // als.cu:991
         final_rmse = sqrtf((float)te / (float)nnz_test);                  // als.cu:1018
         if (!quiet) {

@@ -43,7 +43,7 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[NT/32]*/, int 
 template <int F, int S>
 __global__ void __launch_bounds__(((F * S + 31) / 32) * 32)
 cg_kernel(const float* __restrict__ A, float* __restrict__ x, const float* __restrict__ b, float cg_iter,
-          const SplitRow* __restrict__ sys_rows) {
+          const SplitRow* __restrict__ sys_rows, float lambda, double* __restrict__ sse_rows) {
     constexpr int SEG = F / S;
     constexpr int NT = ((F * S + 31) / 32) * 32;
     __shared__ __align__(16) float sp[F];
@@ -112,14 +112,22 @@ cg_kernel(const float* __restrict__ A, float* __restrict__ x, const float* __res
         p = fmaf(beta, p, r);                            // cg.cu:208-209
     }
     if (active && h == 0) x[xrow * F + i] = xi;          // cg.cu:230
+    if (sse_rows != nullptr) {
+        // x^T b + x^T r + reg x^T x: with sum r_j^2 it gives the row's squared error (see gram_tc.cu); only used
+        // for the compact batch of split rows, where the rating count comes with the row map
+        const float reg = sys_rows ? (float)sys_rows[sys].nnz * lambda : 0.f;
+        __syncthreads();
+        const float srow = block_sum<NT>(own * xi * (bi + r + reg * xi), red[1], tid);
+        if (tid == 0) sse_rows[sys] = (sys_rows && sys_rows[sys].nnz > 0) ? (double)srow : 0.0;
+    }
 }
 
 template <int F>
 int launch_one(const float* A, float* x, const float* b, int batch, float cg_iter, const SplitRow* rows,
-               cudaStream_t st) {
+               cudaStream_t st, float lambda, double* sse_rows) {
     constexpr int S = (F > 128) ? 2 : 1;
     constexpr int NT = ((F * S + 31) / 32) * 32;
-    cg_kernel<F, S><<<batch, NT, 0, st>>>(A, x, b, cg_iter, rows);
+    cg_kernel<F, S><<<batch, NT, 0, st>>>(A, x, b, cg_iter, rows, lambda, sse_rows);
     CUMF_CUDA_TRY(cudaGetLastError());
     return CUMF_OK;
 }
@@ -127,10 +135,10 @@ int launch_one(const float* A, float* x, const float* b, int batch, float cg_ite
 }  // namespace
 
 int launch_cg(const float* d_A, float* d_x, const float* d_b, int batch, int f, float cg_iter,
-              const SplitRow* d_sys_rows, cudaStream_t st) {
+              const SplitRow* d_sys_rows, cudaStream_t st, float lambda, double* d_sse_rows) {
     if (batch <= 0) return CUMF_OK;
     switch (f) {
-#define CUMF_CG_CASE(F) case F: return launch_one<F>(d_A, d_x, d_b, batch, cg_iter, d_sys_rows, st);
+#define CUMF_CG_CASE(F) case F: return launch_one<F>(d_A, d_x, d_b, batch, cg_iter, d_sys_rows, st, lambda, d_sse_rows);
         CUMF_CG_CASE(10) CUMF_CG_CASE(20) CUMF_CG_CASE(30) CUMF_CG_CASE(40) CUMF_CG_CASE(50)
         CUMF_CG_CASE(60) CUMF_CG_CASE(70) CUMF_CG_CASE(80) CUMF_CG_CASE(90) CUMF_CG_CASE(100)
         CUMF_CG_CASE(110) CUMF_CG_CASE(120) CUMF_CG_CASE(130) CUMF_CG_CASE(140) CUMF_CG_CASE(150)

@@ -87,7 +87,7 @@ int launch_split_reduce(const SplitRow* d_rows, int r0, int r1, int f, float lam
 // d_sys_rows (optional): system s reads/writes x at row d_sys_rows[s].row of d_x instead of row s
 // (used for the compact batch of split rows).
 int launch_cg(const float* d_A, float* d_x, const float* d_b, int batch, int f, float cg_iter,
-              const SplitRow* d_sys_rows, cudaStream_t st);
+              const SplitRow* d_sys_rows, cudaStream_t st, float lambda = 0.f, double* d_sse_rows = nullptr);
 // cuBLAS batched LU oracle.
 int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t st);
 // RMSE partial sums.
@@ -95,6 +95,12 @@ int launch_sse(const float* d_val, const int* d_row, const int* d_col, const flo
                const float* d_XT, long count, int f, double* d_sse_out, double* d_partials,
                int partial_capacity, cudaStream_t st);
 int sse_partial_capacity();
+int launch_sse_chunks(const Chunk* d_chunks, int nchunks, const int* d_idx, const float* d_val, const float* d_own,
+                      const float* d_other, int own_is_theta, int f, double* d_sse_out, double* d_partials,
+                      int partial_capacity, cudaStream_t st);
+int launch_sumsq(const float* d_v, long n, double* d_out, double* d_partials, int partial_capacity, cudaStream_t st);
+int launch_sum_doubles(const double* d_v, int n, double* d_out, cudaStream_t st);
+int launch_coo_check(const Chunk* d_chunks, int nchunks, const int* d_coo_row, int* d_flag, cudaStream_t st);
 
 // Fused tcgen05 path (gram_tc.cu).  Returns CUMF_EUNSUPPORTED when f is not handled.
 bool tc_path_supports(int f);
@@ -102,9 +108,10 @@ struct TcWork;  // opaque per-plan state of the fused kernel
 int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* d_chunks, const std::vector<SplitRow>& splits,
                    int rows_total, int f);
 void tc_plan_destroy(TcWork* w);
+int tc_plan_grid(const TcWork* w);
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,
                      const int* d_colidx, const float* d_val, const float* d_factor, float* d_out,
                      int f, float lambda, float cg_iter, float* d_scratchA, float* d_scratchB,
-                     cudaStream_t st, int* launches);
+                     cudaStream_t st, int* launches, double* d_sse_terms = nullptr);
 
 }  // namespace cumf

@@ -106,6 +106,12 @@ constexpr float kCgErrorF = 1.00000005e-4f;
 
 // stage flags: chunk = one row (or one piece of a split row); sub = one TMEM accumulation tile
 constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST = 4u, FLAG_SUB_LAST = 8u;
+// ... followed by what the MMA issuer would otherwise have to count at run time (the CTA partition is fixed per
+// plan, so the tile sequence of every CTA is known when the table is built):
+//   bit 4  TMEM buffer of the stage's tile (tile index within the CTA & 1)
+//   bit 5  solver warpgroup that drains it  (chunk index within the CTA & 1)   -> acc_full[bit5][bit4]
+//   bit 6  parity to wait for on acc_empty[bit4] before the tile's first MMA
+constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 6;
 
 // One k-step of work: 16 (or fewer) consecutive ratings of one chunk.  Precomputed per plan
 // (stage table), so every stage worker warp is autonomous.
@@ -191,6 +197,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_smem_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -273,20 +282,26 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
 __device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + KT - 1) / KT); }
 
 // stage table of a plan: one StageDesc per k-step, in chunk order (built once per plan)
+// chunk_meta[c] = (index of the chunk's first tile within its CTA) << 1 | (index of the chunk within its CTA & 1)
 __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ chunk_stage_base,
-                                        int nchunks, StageDesc* __restrict__ table) {
+                                        const int* __restrict__ chunk_meta, int nchunks, StageDesc* __restrict__ table) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const Chunk ck = chunks[c];
     const int steps = chunk_steps(ck);
+    const uint32_t wg = (uint32_t)chunk_meta[c] & 1u;
+    const uint32_t tile0 = (uint32_t)chunk_meta[c] >> 1;
     StageDesc* out = table + chunk_stage_base[c];
     for (int s = 0; s < steps; ++s) {
         const int pos = ck.begin + s * KT;
         const int cnt = max(0, min(KT, ck.end - pos));
         const bool last = (s == steps - 1);
+        const uint32_t tile = tile0 + (uint32_t)(s / SUB_STEPS);
         const uint32_t flags = (s == 0 ? FLAG_CHUNK_FIRST : 0u) | (last ? FLAG_CHUNK_LAST : 0u) |
                                ((s % SUB_STEPS) == 0 ? FLAG_SUB_FIRST : 0u) |
-                               ((last || (s % SUB_STEPS) == SUB_STEPS - 1) ? FLAG_SUB_LAST : 0u);
+                               ((last || (s % SUB_STEPS) == SUB_STEPS - 1) ? FLAG_SUB_LAST : 0u) |
+                               ((tile & 1u) << FLAG_BUF_SHIFT) | (wg << FLAG_WG_SHIFT) |
+                               ((((tile >> 1) & 1u) ^ 1u) << FLAG_EMPTY_PARITY_SHIFT);
         out[s] = StageDesc{pos, (uint32_t)cnt | (flags << 8)};
     }
 }
@@ -297,7 +312,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                       const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
                       const __grid_constant__ CUtensorMap factor_map, float* __restrict__ out, float lambda, float cg_iter,
-                      float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl) {
+                      float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl,
+                      double* __restrict__ sse_terms) {
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -343,21 +359,26 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             constexpr uint32_t idesc2 = make_idesc(128, N2);
             const uint32_t op_base0 = smem_u32(&sm.op_stage[0][0]);
             const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
-            int q = 0;              // accumulator tiles produced so far (one per sub-chunk)
-            int done = 0;           // chunks finished
+            const uint32_t empty_bar0 = smem_u32(&sm.empty_op[0]);
+            const uint32_t acc_full_bar0 = smem_u32(&sm.acc_full[0][0]);    // [wg][buf], 8 bytes each
             // one k-step: D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']   (+ D[:, 128:256] += lo'^T [hi | r] if !kSym)
-            auto issue_step = [&](int slot, uint32_t flags, int buf, int chunk_parity) {
+            // Everything the step needs beyond the slot number comes from the stage's flag word (see FLAG_*): no
+            // run-time tile / chunk counters in this warp, whose instruction stream bounds the k-step rate on long rows.
+            auto issue_step = [&](int slot, uint32_t m) {
                 // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and the
                 // whole ring lies below the field's 256 KB wrap, so plain addition is exact
                 const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
-                umma_f16(d_tmem, d_hi, d_hi, idesc1, (flags & FLAG_SUB_FIRST) ? 0u : 1u);
+                const uint32_t d_tmem = tmem_base + ((m >> FLAG_BUF_SHIFT) & 1u) * (uint32_t)ACC_COLS;
+                umma_f16(d_tmem, d_hi, d_hi, idesc1, (m & FLAG_SUB_FIRST) ? 0u : 1u);
                 if (!kSym) {
                     const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);    // rows 128.. : lo' | 0
                     umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
                 }
-                umma_commit(&sm.empty_op[slot]);          // operand stage reusable once the MMAs retire
-                if (flags & FLAG_SUB_LAST) umma_commit(&sm.acc_full[chunk_parity][buf]);   // chunk c belongs to solver warpgroup c & 1
+                umma_commit_addr(empty_bar0 + (uint32_t)slot * 8u);          // operand stage reusable once the MMAs retire
+                if (m & FLAG_SUB_LAST) umma_commit_addr(acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 3u) * 8u);   // acc_full[wg][buf]
+            };
+            auto wait_tile_free = [&](uint32_t m) {
+                if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
             };
             for (int n0 = 0; n0 < total_stages; n0 += S2) {
                 const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
@@ -368,20 +389,16 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                         const bool two = (n0 + slot + 1 < total_stages);
                         mbar_wait(&sm.full_op[slot], ph);
                         if (two) mbar_wait(&sm.full_op[slot + 1], ph);
-                        const uint32_t f0 = sm.meta_op[slot];
-                        const uint32_t f1 = two ? sm.meta_op[slot + 1] : 0u;
-                        const int q1 = q + ((f0 & FLAG_SUB_LAST) ? 1 : 0);
-                        const int done1 = done + ((f0 & FLAG_CHUNK_LAST) ? 1 : 0);
-                        if (f0 & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[q & 1], (((uint32_t)q >> 1) & 1u) ^ 1u);
-                        if (f1 & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[q1 & 1], (((uint32_t)q1 >> 1) & 1u) ^ 1u);
+                        const uint32_t m0 = sm.meta_op[slot];
+                        const uint32_t m1 = two ? sm.meta_op[slot + 1] : 0u;
+                        wait_tile_free(m0);
+                        wait_tile_free(m1);
                         tc_fence_after();
                         if (elect_one()) {
-                            issue_step(slot, f0, q & 1, done & 1);
-                            if (two) issue_step(slot + 1, f1, q1 & 1, done1 & 1);
+                            issue_step(slot, m0);
+                            if (two) issue_step(slot + 1, m1);
                         }
                         __syncwarp();
-                        q = q1 + ((f1 & FLAG_SUB_LAST) ? 1 : 0);
-                        done = done1 + ((f1 & FLAG_CHUNK_LAST) ? 1 : 0);
                     }
                 }
             }
@@ -522,6 +539,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             int q = 0;
             uint32_t seen0 = 0, seen1 = 0;                // tiles this warpgroup has taken from TMEM buffer 0 / 1
             uint32_t spb = 0;                             // which copy of sp the next broadcast uses
+            double sse_acc = 0.0;                         // sum over this warpgroup's rows of x^T b + x^T r + reg x^T x
             Chunk ck_next = chunks[c_begin];
             for (int c = c_begin; c < c_end; ++c) {
                 const Chunk ck = ck_next;
@@ -631,7 +649,16 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     p = fmaf(beta, p, r);
                 }
                 if (active) xrow[i] = xi;
+                if (sse_terms != nullptr) {
+                    // Squared error of the row's ratings under the x just computed, without touching them again:
+                    //   sum_j (r_j - x.theta_j)^2 = sum r_j^2 - 2 x^T b + x^T G x,   G = A - reg I,   A x = b - r
+                    //                             = sum r_j^2 - (x^T b + x^T r + reg x^T x)
+                    // with r the CG residual carried above.  The caller holds sum r_j^2 (a constant of the data).
+                    const float srow = wg_sum(own * xi * (bi + r + reg * xi), sm.red[wg][1], quad, lane, bar_id);
+                    if (ck.end > ck.begin) sse_acc += (double)srow;     // empty rows: no ratings, no error (x is NaN there)
+                }
             }
+            if (sse_terms != nullptr && i == 0) sse_terms[blockIdx.x * 2 + wg] = sse_acc;
         }
     }
 
@@ -651,6 +678,8 @@ struct TcWork {
     DevBuf cta_ptr;                     // first chunk of every CTA (+1)
     DevBuf cta_stage_ptr;               // first stage (k-step) of every CTA (+1)
     DevBuf stage_tab;                   // StageDesc per k-step, chunk order
+    DevBuf chunk_stage_base, chunk_meta; // inputs of the table fill; kept until destroy (cudaFree would synchronise the
+                                        // device, i.e. wait for rating uploads still in flight on another stream)
     int grid = 0;
     int nchunks = 0;
     bool sym = false;                   // long chunks: the tensor core forms half of the cross term, the epilogue transposes
@@ -690,6 +719,8 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
 }
 
 void tc_plan_destroy(TcWork* w);
+
+int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
 
 bool tc_path_supports(int f) {
     const char* off = getenv("CUMF_DISABLE_TC");
@@ -749,26 +780,37 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
         const long long sym_min_steps = 64;
         w->sym = (m && *m) ? (*m == '1') : (n > 0 && (long long)stage_base[n] >= sym_min_steps * n);
     }
-    DevBuf d_base;
+    // what the MMA issuer would otherwise count: first tile of every chunk within its CTA, chunk parity within its CTA
+    std::vector<int> chunk_meta(std::max(n, 1), 0);
+    for (int b = 0; b < grid; ++b) {
+        long long tile = 0;
+        for (int c = ptr[b]; c < ptr[b + 1]; ++c) {
+            chunk_meta[c] = (int)(((tile & 0x3fffffffLL) << 1) | ((c - ptr[b]) & 1));   // only tile & 3 is consumed
+            tile += (stage_base[c + 1] - stage_base[c] + SUB_STEPS - 1) / SUB_STEPS;
+        }
+    }
+    DevBuf& d_base = w->chunk_stage_base;
     int rc = w->cta_ptr.alloc(sizeof(int) * (grid + 1));
     if (rc == CUMF_OK) rc = w->cta_stage_ptr.alloc(sizeof(int) * (grid + 1));
     if (rc == CUMF_OK) rc = w->stage_tab.alloc(sizeof(StageDesc) * (size_t)std::max(1, stage_base[n]));
     if (rc == CUMF_OK) rc = d_base.alloc(sizeof(int) * (n + 1));
+    if (rc == CUMF_OK) rc = w->chunk_meta.alloc(sizeof(int) * std::max(n, 1));
     if (rc == CUMF_OK &&
         (cudaMemcpy(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
+         cudaMemcpy(w->chunk_meta.p, chunk_meta.data(), sizeof(int) * std::max(n, 1), cudaMemcpyHostToDevice) != cudaSuccess ||
          cudaMemcpy(w->cta_stage_ptr.p, sptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
          cudaMemcpy(d_base.p, stage_base.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice) != cudaSuccess)) {
         set_last_error("tc_plan_create: upload failed");
         rc = CUMF_ECUDA;
     }
     if (rc == CUMF_OK && n > 0) {
-        fill_stage_table_kernel<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), n, w->stage_tab.as<StageDesc>());
-        if (cudaDeviceSynchronize() != cudaSuccess) {
+        fill_stage_table_kernel<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n,
+                                                          w->stage_tab.as<StageDesc>());
+        if (cudaStreamSynchronize(0) != cudaSuccess) {      // not the device: uploads may be running on another stream
             set_last_error(std::string("tc_plan_create: stage table: ") + cudaGetErrorString(cudaGetLastError()));
             rc = CUMF_ECUDA;
         }
     }
-    d_base.release();
     if (rc != CUMF_OK) { tc_plan_destroy(w); return rc; }
     *out = w;
     return CUMF_OK;
@@ -779,12 +821,14 @@ void tc_plan_destroy(TcWork* w) {
     w->cta_ptr.release();
     w->cta_stage_ptr.release();
     w->stage_tab.release();
+    w->chunk_stage_base.release();
+    w->chunk_meta.release();
     delete w;
 }
 
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d_colidx, const float* d_val,
                      const float* d_factor, float* d_out, int f, float lambda, float cg_iter, float* d_scratchA,
-                     float* d_scratchB, cudaStream_t st, int* launches) {
+                     float* d_scratchB, cudaStream_t st, int* launches, double* d_sse_terms) {
     if (!w || f != F) {
         set_last_error("tc_update_factor: bad plan");
         return CUMF_EINVAL;
@@ -807,7 +851,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     auto kernel = w->sym ? als_fused_f100_kernel<true> : als_fused_f100_kernel<false>;
     kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
                                              w->cta_stage_ptr.as<int>(), d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter,
-                                             d_scratchA, d_scratchB, desc_tmpl);
+                                             d_scratchA, d_scratchB, desc_tmpl, d_sse_terms);
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;
     return CUMF_OK;
