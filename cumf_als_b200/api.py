@@ -63,6 +63,7 @@ SIGNATURES = {
                                                                    C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                                                    C.c_int, C.c_int, C.c_int]),
     "cumf_als_destroy": (C.c_int, [_vp]),
+    "cumf_als_collect_train_sse": (C.c_int, [_vp, C.c_int]),
     "cumf_als_set_factors": (C.c_int, [_vp, _vp, _vp]),
     "cumf_als_get_factors": (C.c_int, [_vp, _vp, _vp]),
     "cumf_als_theta_ptr": (_vp, [_vp]),
@@ -280,6 +281,10 @@ class AlsSolver:
         self._h = _vp()
         _check(lib.cumf_als_create(C.byref(self._h), *[_hp(a) for a in arrs], m, n, f, self.nnz, self.nnz_test, lam,
                                    xb, xe, tb, te, device, solver, path), "cumf_als_create")
+
+    def collect_train_sse(self, on: bool = True) -> bool:
+        """Train SSE as a by-product of update_theta (cumf_als_collect_train_sse); returns whether it is active."""
+        return load_library().cumf_als_collect_train_sse(self._h, int(on)) == 1
 
     def set_factors(self, thetaT: np.ndarray, XT: np.ndarray) -> None:
         t, x = _host(thetaT, np.float32), _host(XT, np.float32)

@@ -572,7 +572,7 @@ struct cumf_als_solver {
     int train_mode = -1;
     // train RMSE from the theta half-step's by-product (plan.sse_terms): needs the whole matrix on this GPU, the fused
     // CG path, cooRow == CSR rows, and X untouched since that half-step
-    bool theta_fresh = false;
+    bool theta_fresh = false, can_collect_sse = false;
     double sum_r2 = -1.0;               // sum of squared train ratings (computed on first use)
     cumf_plan* px = nullptr;
     cumf_plan* pt = nullptr;
@@ -642,7 +642,7 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
     s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
     // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
-    s->pt->collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
+    s->can_collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
                           solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr && env_long("CUMF_SSE_DIRECT", 0) == 0);
     if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
     if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
@@ -702,6 +702,16 @@ extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHost
                            cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
                            cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, x_begin, x_end,
                            t_begin, t_end, device, solver, path, /*wait_uploads=*/true);
+}
+
+// Ask the theta half-steps to leave the train-SSE by-product (costs one more block reduction per row, about 4 % of
+// that half-step; saves the streaming pass over all ratings in cumf_als_sse).  cumf_doALS turns it on because it
+// evaluates the RMSE after every iteration; a caller that only looks at the RMSE now and then leaves it off.
+extern "C" int cumf_als_collect_train_sse(cumf_als_solver* s, int on) {
+    CUMF_REQUIRE(s && s->pt, "null pointer");
+    s->pt->collect_sse = (on != 0) && s->can_collect_sse;
+    if (!s->pt->collect_sse) { s->pt->sse_terms_valid = false; s->theta_fresh = false; }
+    return s->pt->collect_sse ? 1 : 0;
 }
 
 extern "C" int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost, const float* XTHost) {
@@ -926,6 +936,7 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
                         cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, 0, m, 0, n,
                         DEVICEID, solver, path, /*wait_uploads=*/false, thetaTHost, XTHost) != CUMF_OK)
         die("cumf_als_create");
+    cumf_als_collect_train_sse(s, 1);
     if (debug) printf("\tsetup (work plans; uploads continue in the background) run %f seconds.\n", wall_seconds() - t_setup);
     if (!quiet) printf("*******start iterations...\n");
     float final_rmse = 0.f;

@@ -170,6 +170,12 @@ int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const 
                     long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
                     int device, int solver, int path);
 int cumf_als_destroy(cumf_als_solver* s);
+/* Train RMSE as a by-product of the theta half-step: when on (returns 1 if the solver can do it: whole matrix on this
+ * GPU, fused CG path, cooRowIndex == CSR rows), cumf_als_update_theta also accumulates, per row, x^T b + x^T r + reg x^T x
+ * from the CG state, and cumf_als_sse returns  sum r^2 - that  for the train set instead of streaming over the ratings
+ * (als.cu:967-991) -- valid while X is unchanged since that half-step; otherwise, and whenever the subtraction would
+ * keep fewer than three digits, the streaming kernel runs.  Off by default; cumf_doALS turns it on.                    */
+int cumf_als_collect_train_sse(cumf_als_solver* s, int on);
 int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost, const float* XTHost);
 int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float* XTHost);
 /* device pointers of the resident full factor replicas (for NCCL all-gather by the caller) */

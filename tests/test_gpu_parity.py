@@ -454,3 +454,65 @@ def test_partial_gram_engines_two_shares_on_one_gpu(cuda, f, path):
     # ~1e-3 per row after two iterations -- the spread the reference shows between its own runs (test_oracle.py)
     assert rel_fro(engs[0].x.cpu().numpy(), X_o) < 30 * TOL
     assert rel_fro(theta.cpu().numpy(), th_o) < 30 * TOL
+
+
+# ---- train RMSE: by-product of the theta half-step, chunked streaming walk, literal COO pairs --------------------
+def _direct_sse(r, theta, X, row=None):
+    """sum (val - <theta[col], X[row]>)^2 over the CSR entries, float64 on the host (row defaults to the CSR rows)."""
+    row = r.coo_row if row is None else row
+    pred = np.einsum("ij,ij->i", theta[r.csr_indices].astype(np.float64), X[row].astype(np.float64))
+    return float(((r.csr_data - pred) ** 2).sum())
+
+
+def test_train_sse_byproduct_vs_streaming_vs_host(cuda, monkeypatch):
+    """f = 100 fused path: after a theta half-step the train SSE comes from x^T b + x^T r + reg x^T x collected in the
+    CG epilogue (no pass over the ratings); after an X half-step it is the chunked streaming kernel.  Both against a
+    float64 evaluation on the host; includes columns split across CTAs (CUMF_SPLIT_NNZ)."""
+    monkeypatch.setenv("CUMF_SPLIT_NNZ", "256")
+    r = synth_ratings(900, 1400, 150000, 4000, seed=33)
+    f, lam = 100, 0.05
+    theta0, X0 = init_factors(r.m, r.n, f, seed=5)
+    args = (r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row, r.test_row,
+            r.test_col, r.test_val, r.m, r.n, f, lam)
+    s = c.AlsSolver(*args, path=c.PATH_TC)
+    s.set_factors(theta0, X0)
+    assert s.collect_train_sse(True)
+    for it in range(3):
+        s.update_x()
+        tr_stream, _ = s.sse()                      # X changed since the last theta half-step: streaming walk
+        th, X = s.get_factors()
+        assert tr_stream == pytest.approx(_direct_sse(r, th, X), rel=2e-6)
+        s.update_theta()
+        tr_by, te = s.sse()                         # by-product
+        th, X = s.get_factors()
+        want = _direct_sse(r, th, X)
+        # measured on the Netflix-shaped workload: -1e-5 .. -3e-5 relative (fp16-split Gram, fp32 row terms)
+        assert tr_by == pytest.approx(want, rel=1e-4), (it, tr_by, want)
+        assert np.sqrt(tr_by / r.nnz) == pytest.approx(np.sqrt(want / r.nnz), rel=TOL)
+    s.close()
+    monkeypatch.setenv("CUMF_SSE_DIRECT", "1")      # same run with the streaming kernel only
+    d = c.AlsSolver(*args, path=c.PATH_TC)
+    d.set_factors(theta0, X0)
+    d.iterate(3)
+    tr_d, te_d = d.sse()
+    assert tr_d == pytest.approx(want, rel=2e-6) and te_d == pytest.approx(te, rel=1e-9)
+    d.close()
+
+
+def test_train_sse_keeps_literal_pairs_when_coo_disagrees_with_csr(cuda):
+    """als.cu:979-980 pairs cooRowIndex[i] with csrColIndex[i]/csrVal[i]; a cooRowIndex that is not the CSR row
+    expansion must be honoured literally (no row/column walk, no by-product)."""
+    r = synth_ratings(300, 500, 20000, 800, seed=44)
+    f, lam = 100, 0.05
+    theta0, X0 = init_factors(r.m, r.n, f, seed=6)
+    coo = r.coo_row.copy()
+    coo[::97] = (coo[::97] + 7) % r.m
+    s = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, coo, r.test_row,
+                    r.test_col, r.test_val, r.m, r.n, f, lam, path=c.PATH_TC)
+    s.set_factors(theta0, X0)
+    s.iterate(1)
+    tr, _ = s.sse()
+    th, X = s.get_factors()
+    assert tr == pytest.approx(_direct_sse(r, th, X, row=coo), rel=2e-6)
+    assert abs(tr - _direct_sse(r, th, X)) > 1e-3 * tr          # and it is not the matrix walk
+    s.close()
