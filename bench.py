@@ -266,6 +266,18 @@ def run_ours(args, w):
         for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row",
                      "test_row", "test_col", "test_val"):
             setattr(r, name, pin(getattr(r, name)))
+        # pinned host -> device copy rate of this box (the e2e number moves with it: 2.2 GB of ratings per call)
+        probe = torch.from_numpy(r.csr_data).cuda()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        src = torch.from_numpy(r.csr_data)
+        probe.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        probe.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = r.csr_data.nbytes / 1e9 / (e0.elapsed_time(e1) / 1e3)
+        del probe
         if args.warmup > 0:   # allocator / driver warm-up outside the timed call, as in the reference arm
             c.do_als(*r.doals_args(), pin(theta0), pin(X0), r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz,
                      r.nnz_test, lam, 1, 1, 1, local_rank)
@@ -279,6 +291,7 @@ def run_ours(args, w):
                r.test_row.nbytes + r.test_col.nbytes + r.test_val.nbytes + th.nbytes + X.nbytes)
         line["e2e"] = {"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": h2d // args.steps,
                        "d2h_bytes_per_step": (th.nbytes + X.nbytes) // args.steps, "wall_s": wall,
+                       "pinned_h2d_gbs_this_box": h2d_gbs,
                        "final_test_rmse": fin,
                        "what": "doALS(host pointers, ITERS=steps): upload + iterations + per-iteration RMSE + download; "
                                "one untimed 1-iteration call first (both arms)"}

@@ -382,7 +382,7 @@ extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float
         double* terms = nullptr;
         p->sse_terms_valid = false;
         if (p->collect_sse) {
-            const int want = 2 * tc_plan_grid(p->tc) + ns;
+            const int want = tc_sse_terms_per_cta() * tc_plan_grid(p->tc) + ns;
             if (p->sse_terms_count != want) {
                 p->sse_terms.release();
                 CUMF_TRY(p->sse_terms.alloc(sizeof(double) * std::max(1, want)));
@@ -401,7 +401,7 @@ extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float
             CUMF_TRY(launch_split_reduce(d_splits, 0, ns, f, lambda, /*compact=*/1, 0, p->tt.as<float>(),
                                          p->rhs.as<float>(), p->scratchA.as<float>(), p->scratchB.as<float>(), st));
             CUMF_TRY(launch_cg(p->tt.as<float>(), d_out, p->rhs.as<float>(), ns, f, cgIter, d_splits, st, lambda,
-                               terms ? terms + 2 * tc_plan_grid(p->tc) : nullptr));
+                               terms ? terms + tc_sse_terms_per_cta() * tc_plan_grid(p->tc) : nullptr));
             launches += 2;
         }
         p->sse_terms_valid = (terms != nullptr);

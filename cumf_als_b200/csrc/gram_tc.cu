@@ -67,7 +67,6 @@ constexpr int LO_ROW = FP + 16;           // 128: first lo' row
 constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B): SBO
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
 constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 8192
-constexpr int NUM_THREADS = 640;          // 5 warpgroups: (idle x3 + MMA), 2 x stage workers, 2 x epilogue/solver
 constexpr int MMA_WARP = 3;
 constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
 constexpr int STAGE_WARPS = 8;
@@ -75,8 +74,24 @@ static_assert(S1 % STAGE_WARPS == 0 && STAGE_WARPS == S2, "every ring slot has e
 constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
 // setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
 // 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
-constexpr int REGS_LAUNCH = 96, REGS_PROD = 48, REGS_STAGE = 64, REGS_EPI = 152;
-static_assert(128 * (REGS_PROD + 2 * REGS_STAGE + 2 * REGS_EPI) <= NUM_THREADS * REGS_LAUNCH, "setmaxnreg budgets exceed the CTA register pool");
+// Shape of the CTA.  The solver side is parametrised (number of solver warpgroups, how many columns of row i stay in
+// registers vs. the thread's shared-memory row) because a 3-warpgroup / 64-register-column shape was tried for the
+// short-row launches, where the in-kernel CG costs 4 of 14 ms (tools/cg_share.py): it was slower (theta side 16.3 ms
+// instead of 14.0) -- the CG is not latency-bound but shares the shared-memory pipe with the staging and the MMA
+// operand reads, and coefficients in shared memory add to exactly that.  Both launches therefore use 2 warpgroups with
+// the whole row in registers; the parameters stay for the next attempt (profiles/README.md).
+template <bool kSym> struct Cfg {
+    static constexpr int kWG = 2;                                  // solver warpgroups
+    static constexpr int kRegCols = F;                             // columns of row i held in registers
+    static constexpr int kSmemCols = F - kRegCols;                 // columns of row i held in shared memory
+    static constexpr int kThreads = (12 + 4 * kWG) * 32;           // 640
+    static constexpr int kRegsLaunch = 96;
+    static constexpr int kRegsProd = 48, kRegsStage = 64, kRegsEpi = 152;
+    static_assert(128 * (kRegsProd + 2 * kRegsStage + kWG * kRegsEpi) <= kThreads * kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
+    static_assert(kThreads * kRegsLaunch <= 65536, "launch registers");
+};
+constexpr int MAX_WG = 3;
+constexpr int SM_ROW_STRIDE = 36;         // floats per row of the shared-memory part: 36 = 4 (mod 32) keeps LDS.128 conflict-free
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 constexpr int TMEM_COLS = 512;
 // accumulator tile, one MMA per k-step:  D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']
@@ -109,9 +124,9 @@ constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST =
 // ... followed by what the MMA issuer would otherwise have to count at run time (the CTA partition is fixed per
 // plan, so the tile sequence of every CTA is known when the table is built):
 //   bit 4  TMEM buffer of the stage's tile (tile index within the CTA & 1)
-//   bit 5  solver warpgroup that drains it  (chunk index within the CTA & 1)   -> acc_full[bit5][bit4]
-//   bit 6  parity to wait for on acc_empty[bit4] before the tile's first MMA
-constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 6;
+//   bits 5-6  solver warpgroup that drains it (chunk index within the CTA mod #warpgroups) -> acc_full[wg][bit4]
+//   bit 7  parity to wait for on acc_empty[bit4] before the tile's first MMA
+constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 7;
 
 // One k-step of work: 16 (or fewer) consecutive ratings of one chunk.  Precomputed per plan
 // (stage table), so every stage worker warp is autonomous.
@@ -126,17 +141,20 @@ struct __align__(128) Smem {   // dynamic shared memory, used in place
     unsigned char op_stage[S2][OP_STAGE_BYTES];     // 61440
     float stage_vals[S1][KT];    // the ratings of the stage in flight in each fp32 slot (zero beyond cnt)
     uint32_t meta_op[S2];        // stage flags forwarded to the MMA warp
-    float tr[2][(TR_ROWS + 1) * F];   // per solver warpgroup: TR_ROWS rows of G (+ the rating row) for the transpose
-    float sp[2][2][128];         // CG direction vector per solver warpgroup, double buffered
-    float red[2][3][4];          // cross-warp partial sums
+    // per solver warpgroup: kSym -> TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats);
+    //                        !kSym -> columns [64,100) of the 100 rows of [A] it is solving (3 x 3600 floats)
+    float solver_scratch[3 * F * SM_ROW_STRIDE];
+    float sp[MAX_WG][2][128];    // CG direction vector per solver warpgroup, double buffered
+    float red[MAX_WG][3][4];     // cross-warp partial sums
     unsigned long long full_f32[S1], full_op[S2], empty_op[S2];
     // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
     // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
     // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
-    unsigned long long acc_full[2][2], acc_empty[2];
+    unsigned long long acc_full[MAX_WG][2], acc_empty[2];
     uint32_t tmem_base;
 };
 
+static_assert(3 * F * SM_ROW_STRIDE >= 2 * (TR_ROWS + 1) * F, "solver_scratch holds either use");
 static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt into");
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -194,9 +212,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void umma_commit_addr(uint32_t bar_smem_addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem_addr) : "memory");
 }
@@ -246,13 +261,17 @@ __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, in
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// drain one TMEM accumulator tile into / onto the register copy of row i:
-//   kSym:  G = P/2 + S/2048 and its rating column (symmetrised later);   !kSym:  [A|b] = P + S/2048 directly
+// drain one TMEM accumulator tile into / onto this thread's copy of row i:
+//   kSym:  G = P/2 + S/2048 and its rating column (symmetrised later);   !kSym:  [A|b] = P + S/2048 directly.
+// Columns [0, kRegCols) live in registers, the rest in the thread's own shared-memory row `arow` (!kSym only).
 template <bool kFirst, bool kSym>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float& b) {
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[Cfg<kSym>::kRegCols], float& b, float* arow, bool active) {
     constexpr float kP = kSym ? 0.5f : 1.0f;
+    constexpr int RC = Cfg<kSym>::kRegCols;
+    constexpr int RC16 = (RC / 16) * 16;        // 96 (all in registers) or 64
+    static_assert(RC == F || RC == RC16, "register part ends on a 16-column boundary");
 #pragma unroll
-    for (int cc = 0; cc < 96; cc += 16) {
+    for (int cc = 0; cc < RC16; cc += 16) {
         uint32_t p[16], s[16];
         tmem_ld16(taddr + cc, p);
         tmem_ld16(taddr + SCOL + cc, s);
@@ -263,16 +282,44 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
             a[cc + j] = kFirst ? v : a[cc + j] + v;
         }
     }
+#pragma unroll
+    for (int cc = RC16; cc < 96; cc += 16) {    // !kSym: columns 64..95 go to shared memory
+        uint32_t p[16], s[16];
+        tmem_ld16(taddr + cc, p);
+        tmem_ld16(taddr + SCOL + cc, s);
+        tmem_ld_wait();
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 v = make_float4(fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j])),
+                                       fmaf(__uint_as_float(s[j + 1]), kLoInv, kP * __uint_as_float(p[j + 1])),
+                                       fmaf(__uint_as_float(s[j + 2]), kLoInv, kP * __uint_as_float(p[j + 2])),
+                                       fmaf(__uint_as_float(s[j + 3]), kLoInv, kP * __uint_as_float(p[j + 3])));
+                float4* dst = reinterpret_cast<float4*>(arow + (cc - RC) + j);
+                if (!kFirst) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *dst = v;
+            }
+        }
+    }
     uint32_t p[4], s[4], bh[4], bl[4];
     tmem_ld4(taddr + 96, p);
     tmem_ld4(taddr + SCOL + 96, s);
     tmem_ld4(taddr + BCOL_HI, bh);      // hi^T r_hi, hi^T r_lo'
     if (!kSym) tmem_ld4(taddr + BCOL_LO, bl);      // lo'^T r_hi
     tmem_ld_wait();
+    float v4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float v = fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j]));
-        a[96 + j] = kFirst ? v : a[96 + j] + v;
+    for (int j = 0; j < 4; ++j) v4[j] = fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j]));
+    if constexpr (RC == F) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[96 + j] = kFirst ? v4[j] : a[96 + j] + v4[j];
+    } else {
+        if (active) {
+            float4* dst = reinterpret_cast<float4*>(arow + (96 - RC));
+            float4 v = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            if (!kFirst) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            *dst = v;
+        }
     }
     const float tb = kSym ? fmaf(__uint_as_float(bh[1]), kLoInv, 0.5f * __uint_as_float(bh[0]))
                           : fmaf(__uint_as_float(bh[1]) + __uint_as_float(bl[0]), kLoInv, __uint_as_float(bh[0]));
@@ -282,15 +329,15 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float&
 __device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + KT - 1) / KT); }
 
 // stage table of a plan: one StageDesc per k-step, in chunk order (built once per plan)
-// chunk_meta[c] = (index of the chunk's first tile within its CTA) << 1 | (index of the chunk within its CTA & 1)
+// chunk_meta[c] = (index of the chunk's first tile within its CTA) << 2 | (index of the chunk within its CTA mod #solver warpgroups)
 __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ chunk_stage_base,
                                         const int* __restrict__ chunk_meta, int nchunks, StageDesc* __restrict__ table) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const Chunk ck = chunks[c];
     const int steps = chunk_steps(ck);
-    const uint32_t wg = (uint32_t)chunk_meta[c] & 1u;
-    const uint32_t tile0 = (uint32_t)chunk_meta[c] >> 1;
+    const uint32_t wg = (uint32_t)chunk_meta[c] & 3u;
+    const uint32_t tile0 = (uint32_t)chunk_meta[c] >> 2;
     StageDesc* out = table + chunk_stage_base[c];
     for (int s = 0; s < steps; ++s) {
         const int pos = ck.begin + s * KT;
@@ -307,7 +354,7 @@ __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const 
 }
 
 template <bool kSym>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(Cfg<kSym>::kThreads, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
@@ -319,6 +366,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
+    using C = Cfg<kSym>;
+    constexpr int NUM_THREADS = C::kThreads;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int c_begin = cta_chunk_ptr[blockIdx.x], c_end = cta_chunk_ptr[blockIdx.x + 1];
@@ -336,7 +385,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         for (int s = 0; s < S1; ++s) mbar_init(&sm.full_f32[s], 1);
         for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(&sm.acc_full[0][b], 1); mbar_init(&sm.acc_full[1][b], 1); mbar_init(&sm.acc_empty[b], 4);
+            for (int g = 0; g < MAX_WG; ++g) mbar_init(&sm.acc_full[g][b], 1);
+            mbar_init(&sm.acc_empty[b], 4);
         }
         fence_mbar_init();
     }
@@ -349,7 +399,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
 
     // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough)
     if (warp < 4) {
-        reg_dec<REGS_PROD>();
+        reg_dec<C::kRegsProd>();
         if (n_chunks > 0 && warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
             // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
@@ -375,7 +425,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
                 }
                 umma_commit_addr(empty_bar0 + (uint32_t)slot * 8u);          // operand stage reusable once the MMAs retire
-                if (m & FLAG_SUB_LAST) umma_commit_addr(acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 3u) * 8u);   // acc_full[wg][buf]
+                if (m & FLAG_SUB_LAST) umma_commit_addr(acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u);   // acc_full[wg][buf]: index 2 wg + buf
             };
             auto wait_tile_free = [&](uint32_t m) {
                 if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
@@ -404,7 +454,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             }
         }
     } else if (warp < FIRST_EPI_WARP) {
-        reg_dec<REGS_STAGE>();
+        reg_dec<C::kRegsStage>();
         if (n_chunks > 0) {
             // ============ autonomous stage workers: warp w owns stages w, w+8, w+16, ... ===========
             // own-stage t (global stage n = w + 8t) lives in fp32 slot w + 8(t&1) and operand slot w.
@@ -527,15 +577,17 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             }
         }
     } else {
-        reg_inc<REGS_EPI>();
+        reg_inc<C::kRegsEpi>();
         if (n_chunks > 0) {
             // ========================= epilogue + solver warpgroups =============================
-            const int wg = (warp - FIRST_EPI_WARP) >> 2;  // this warpgroup takes chunks with (index & 1) == wg
+            const int wg = (warp - FIRST_EPI_WARP) >> 2;  // this warpgroup takes chunks with (index % kWG) == wg
             const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
             const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
             const bool active = i < F;
             const int bar_id = 1 + wg;
-            // tiles appear in chunk-list order: both warpgroups walk the list, each drains only its chunks
+            // !kSym: this thread's columns [kRegCols, F) of row i (only threads i < F own a row)
+            float* arow = sm.solver_scratch + (wg * F + (active ? i : 0)) * SM_ROW_STRIDE;
+            // tiles appear in chunk-list order: all warpgroups walk the list, each drains only its chunks
             int q = 0;
             uint32_t seen0 = 0, seen1 = 0;                // tiles this warpgroup has taken from TMEM buffer 0 / 1
             uint32_t spb = 0;                             // which copy of sp the next broadcast uses
@@ -545,8 +597,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const Chunk ck = ck_next;
                 if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
                 const int tiles = (chunk_steps(ck) + SUB_STEPS - 1) / SUB_STEPS;
-                if (((c - c_begin) & 1) != wg) { q += tiles; continue; }
-                float a[F];
+                if (((c - c_begin) % C::kWG) != wg) { q += tiles; continue; }
+                float a[C::kRegCols];
                 float bi = 0.f;
                 // warm start x_u (cg.cu:47): requested before the tile waits so its latency is hidden behind them
                 float* xrow = out + (size_t)ck.row * F;
@@ -560,8 +612,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     // tile = (hi^T hi)/2 + (hi^T lo')/2048 over <= SUB_STEPS k-steps; the tiles of one chunk
                     // are summed here in fp32 (round-to-nearest), which bounds the length of the tensor core's
                     // own (truncating) accumulation chain
-                    if (tile == 0) drain_tile<true, kSym>(taddr, a, bi);
-                    else drain_tile<false, kSym>(taddr, a, bi);
+                    if (tile == 0) drain_tile<true, kSym>(taddr, a, bi, arow, active);
+                    else drain_tile<false, kSym>(taddr, a, bi, arow, active);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);       // accumulator drained
@@ -570,8 +622,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 // ---- [A | b] = G + G^T: rows of G go through shared memory, TR_ROWS at a time.  Thread i adds
                 // G[j][i] to its G[i][j]; where row j was symmetrised in an earlier pass (i < base) the buffer
                 // already holds the finished A[j][i], which is taken as is (A is symmetric bit for bit).
-                if (kSym) {
-                    float* tb = sm.tr[wg];
+                if constexpr (kSym) {
+                    float* tb = sm.solver_scratch + wg * (TR_ROWS + 1) * F;
 #pragma unroll
                     for (int pass = 0; pass < 2; ++pass) {
                         constexpr int kRowFloat4 = F / 4;
@@ -604,7 +656,9 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     if (active) {
                         float4* dst = reinterpret_cast<float4*>(scratchA + (size_t)ck.slot * F * F + (size_t)i * F);
 #pragma unroll
-                        for (int j = 0; j < F; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                        for (int j = 0; j < C::kRegCols; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+#pragma unroll
+                        for (int j = 0; j < C::kSmemCols; j += 4) dst[(C::kRegCols + j) >> 2] = *reinterpret_cast<const float4*>(arow + j);
                         scratchB[(size_t)ck.slot * F + i] = bi;
                     }
                     continue;
@@ -617,10 +671,17 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 auto spmv = [&](const float* sp, float self) -> float {   // four independent FMA chains, summed pairwise
                     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < F; j += 4) {
+                    for (int j = 0; j < C::kRegCols; j += 4) {
                         const float4 pv = *reinterpret_cast<const float4*>(sp + j);
                         y0 = fmaf(a[j], pv.x, y0); y1 = fmaf(a[j + 1], pv.y, y1);
                         y2 = fmaf(a[j + 2], pv.z, y2); y3 = fmaf(a[j + 3], pv.w, y3);
+                    }
+#pragma unroll
+                    for (int j = 0; j < C::kSmemCols; j += 4) {     // same chains, coefficients from this thread's smem row
+                        const float4 av = *reinterpret_cast<const float4*>(arow + j);
+                        const float4 pv = *reinterpret_cast<const float4*>(sp + C::kRegCols + j);
+                        y0 = fmaf(av.x, pv.x, y0); y1 = fmaf(av.y, pv.y, y1);
+                        y2 = fmaf(av.z, pv.z, y2); y3 = fmaf(av.w, pv.w, y3);
                     }
                     return fmaf(reg, self, (y0 + y1) + (y2 + y3));
                 };
@@ -658,7 +719,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     if (ck.end > ck.begin) sse_acc += (double)srow;     // empty rows: no ratings, no error (x is NaN there)
                 }
             }
-            if (sse_terms != nullptr && i == 0) sse_terms[blockIdx.x * 2 + wg] = sse_acc;
+            if (sse_terms != nullptr && i == 0) sse_terms[blockIdx.x * MAX_WG + wg] = sse_acc;
         }
     }
 
@@ -721,6 +782,7 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
 void tc_plan_destroy(TcWork* w);
 
 int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
+int tc_sse_terms_per_cta() { return MAX_WG; }
 
 bool tc_path_supports(int f) {
     const char* off = getenv("CUMF_DISABLE_TC");
@@ -782,10 +844,11 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     }
     // what the MMA issuer would otherwise count: first tile of every chunk within its CTA, chunk parity within its CTA
     std::vector<int> chunk_meta(std::max(n, 1), 0);
+    const int n_wg = w->sym ? Cfg<true>::kWG : Cfg<false>::kWG;
     for (int b = 0; b < grid; ++b) {
         long long tile = 0;
         for (int c = ptr[b]; c < ptr[b + 1]; ++c) {
-            chunk_meta[c] = (int)(((tile & 0x3fffffffLL) << 1) | ((c - ptr[b]) & 1));   // only tile & 3 is consumed
+            chunk_meta[c] = (int)(((tile & 0x1fffffffLL) << 2) | ((c - ptr[b]) % n_wg));   // only tile & 3 is consumed
             tile += (stage_base[c + 1] - stage_base[c] + SUB_STEPS - 1) / SUB_STEPS;
         }
     }
@@ -849,7 +912,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
     const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
     auto kernel = w->sym ? als_fused_f100_kernel<true> : als_fused_f100_kernel<false>;
-    kernel<<<w->grid, NUM_THREADS, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
+    kernel<<<w->grid, w->sym ? Cfg<true>::kThreads : Cfg<false>::kThreads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
                                              w->cta_stage_ptr.as<int>(), d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter,
                                              d_scratchA, d_scratchB, desc_tmpl, d_sse_terms);
     CUMF_CUDA_TRY(cudaGetLastError());
