@@ -42,6 +42,8 @@ WORKLOADS = {
     "netflix": dict(m=17770, n=480189, nnz=99072112, nnz_test=1408395, f=100, lam=0.048, seed=1002, ref_batches=(1, 3)),
     "netflix_f200": dict(m=17770, n=480189, nnz=99072112, nnz_test=1408395, f=200, lam=0.048, seed=1002, ref_batches=(1, 10)),
     "ml10m": dict(m=71567, n=65133, nnz=9000048, nnz_test=1000006, f=10, lam=0.05, seed=1001, ref_batches=(1, 1)),
+    # BASELINE configs[3] (README.md:77-79: ./main 1000990 624961 100 252800275 4003960 1.4 6 3)
+    "yahoo": dict(m=1000990, n=624961, nnz=252800275, nnz_test=4003960, f=100, lam=1.4, seed=1004, ref_batches=(6, 3)),
     "tiny": dict(m=2000, n=5000, nnz=400000, nnz_test=20000, f=100, lam=0.048, seed=1, ref_batches=(1, 1)),
 }
 
@@ -240,7 +242,8 @@ def run_ours(args, w):
             "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
                        "lambda": lam, "solver": "cg6", "path": "tcgen05-fused" if fused else "simt-unfused",
                        "sharding": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, all-gather",
-                       "l2": "inputs exceed L2 (theta 192 MB, ratings 1.2 GB per orientation): no flush"},
+                       "l2": f"inputs exceed L2 (factors {(r.m + r.n) * f * 4 / 1e6:.0f} MB, ratings {r.nnz * 12 / 1e9:.1f} GB per "
+                             f"orientation): no flush"},
             "x_ms": tm["x_ms"] / max(tm["iterations"], 1), "theta_ms": tm["theta_ms"] / max(tm["iterations"], 1),
             "train_rmse": train_rmse, "test_rmse": test_rmse,
             "gpu_launches": int(tm["launches"]),

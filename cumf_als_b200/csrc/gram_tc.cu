@@ -805,7 +805,8 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     if (grid > n) grid = std::max(1, n);
     // contiguous, cost-balanced partition of the (row-ordered) chunk list: cost = MMA k-steps
     // plus a per-chunk epilogue/solve term, so every CTA streams one contiguous rating range.
-    const long long per_chunk = 96;
+    const char* rc_env = getenv("CUMF_TC_ROW_COST");
+    const long long per_chunk = (rc_env && *rc_env) ? atoll(rc_env) : 96;
     std::vector<long long> prefix(n + 1, 0);
     for (int c = 0; c < n; ++c) {
         const long long nnz = chunks[c].end - chunks[c].begin;

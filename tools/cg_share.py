@@ -25,6 +25,28 @@ for _ in range(2):      # two real iterations first: X0 = 0 would make the theta
         plan, idx, val, fac, out = sides[name]
         c.update_factor(plan, idx, val, fac, out, lam, c.SOLVER_CG, 6.0)
 torch.cuda.synchronize()
+import os  # noqa: E402
+if os.environ.get("SWEEP_ROW_COST"):
+    # per-row cost (in ratings) used to cut the chunk list into per-CTA ranges: the slowest CTA sets the kernel time
+    for cost in os.environ["SWEEP_ROW_COST"].split(","):
+        os.environ["CUMF_TC_ROW_COST"] = cost
+        for name, (rp, rows, idx, val, fac, out) in {"X": (r.csr_indptr, r.m, sides["X"][1], sides["X"][2], theta, X),
+                                                     "theta": (r.csc_indptr, r.n, sides["theta"][1], sides["theta"][2], X, theta)}.items():
+            plan = c.Plan(rp, 0, rows, f, c.PATH_TC)
+            keep = out.clone()
+            best = 1e9
+            for rep in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                c.update_factor(plan, idx, val, fac, out, lam, c.SOLVER_CG, 6.0)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+                out.copy_(keep)
+            print(f"row cost {cost:>5s}  {name:6s} {best:7.3f} ms", flush=True)
+            plan.close()
+    sys.exit(0)
 for name, (plan, idx, val, fac, out) in sides.items():
     for cg in (6.0, 3.0, 0.0, 6.0):
         keep = out.clone()
