@@ -93,6 +93,18 @@ template <bool kSym> struct Cfg {
 constexpr int MAX_WG = 3;
 constexpr int SM_ROW_STRIDE = 36;         // floats per row of the shared-memory part: 36 = 4 (mod 32) keeps LDS.128 conflict-free
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
+// "direct" staging (kDirect): the opposing factor is pre-split once per half-step into an fp16 table
+//   row j = [ hi_j (100) | 0 (12) | r slots (2) | 0 (14) | lo'_j (100) | 0 (28) ]      256 halfs = 512 B
+// (+ one all-zero row behind the last), and TMA tile::gather4 with CU_TENSOR_MAP_SWIZZLE_128B drops the 16 gathered
+// rows of a k-step straight into the UMMA **MN-major** SWIZZLE_128B canonical layout: four 64-element chunks per
+// row, 8 rows x 128 B per swizzle atom.  No fp32 staging ring, no conversion pass: per k-step the shared-memory pipe
+// carries 8 KB of TMA writes + the UMMA operand reads instead of 6.4 + 6.4 + 6.5 KB of staging traffic on top of them.
+constexpr int DS = 16;                    // direct stage ring depth (two slots per stage-worker warp)
+constexpr int DSTAGE_BYTES = 8192;        // 16 rows x 512 B
+constexpr int SPLIT_COLS = 256;           // fp16 elements per row of the pre-split table
+constexpr int SPLIT_ROW_BYTES = SPLIT_COLS * 2;
+constexpr int SPLIT_CHUNK = 64;           // elements per 128-byte swizzle line
+static_assert(DSTAGE_BYTES == KT * SPLIT_ROW_BYTES, "one stage = 16 gathered rows");
 constexpr int TMEM_COLS = 512;
 // accumulator tile, one MMA per k-step:  D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']
 //   lanes 0..99 (features i):  [0,112) P[i][:] = hi_i . hi_j | 112 hi_i . r_hi | 113 hi_i . r_lo' | [128,240) S[i][:] = hi_i . lo'_j
@@ -136,17 +148,25 @@ struct StageDesc {
 };
 static_assert(sizeof(StageDesc) == 8, "StageDesc is loaded as one 8-byte word");
 
-struct __align__(128) Smem {   // dynamic shared memory, used in place
+struct ConvStaging {
     unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 106496
-    unsigned char op_stage[S2][OP_STAGE_BYTES];     // 61440
-    float stage_vals[S1][KT];    // the ratings of the stage in flight in each fp32 slot (zero beyond cnt)
-    uint32_t meta_op[S2];        // stage flags forwarded to the MMA warp
+    unsigned char op_stage[S2][OP_STAGE_BYTES];     // 65536
+};
+union Staging {
+    ConvStaging conv;                               // !kDirect: fp32 gather ring + converted fp16 operand ring
+    unsigned char direct[DS][DSTAGE_BYTES];         // kDirect: one ring, TMA destination == UMMA operand (131072)
+};
+static_assert(DS >= S1 && DS >= S2, "barrier / metadata arrays are sized for the direct ring");
+struct __align__(1024) Smem {   // dynamic shared memory, used in place (SWIZZLE_128B atoms need 1024-byte alignment)
+    Staging stg;
+    float stage_vals[DS][KT];    // the ratings of the stage in flight in each gather slot (zero beyond cnt)
+    uint32_t meta_op[DS];        // stage flags forwarded to the MMA warp
     // per solver warpgroup: kSym -> TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats);
     //                        !kSym -> columns [64,100) of the 100 rows of [A] it is solving (3 x 3600 floats)
     float solver_scratch[3 * F * SM_ROW_STRIDE];
     float sp[MAX_WG][2][128];    // CG direction vector per solver warpgroup, double buffered
     float red[MAX_WG][3][4];     // cross-warp partial sums
-    unsigned long long full_f32[S1], full_op[S2], empty_op[S2];
+    unsigned long long full_f32[DS], full_op[DS], empty_op[DS];
     // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
     // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
     // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
@@ -169,15 +189,18 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Watchdog: a protocol error (or a fault in another role's warp) must not leave the GPU spinning for ever -- after
+// 2^24 unsuccessful polls (>= 0.3 s; a healthy wait is microseconds) the CTA traps and the launch fails loudly.
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done;
+    uint32_t done, polls = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && ++polls > (1u << 24)) __trap();
     } while (!done);
 }
 // TMA tile::gather4: four rows (row coordinates r0..r3, column coordinate 0) of the 2-D tensor described
@@ -188,6 +211,14 @@ __device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* t
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+// same, for the pre-split fp16 table: four 64-element (128-byte) pieces starting at column `col`
+__device__ __forceinline__ void tma_gather4_col(void* smem_dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2, int r3,
+                                                unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -245,8 +276,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint64_t 
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format F16 (0),
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool mn_major = false) {
+    return (1u << 4) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major SWIZZLE_128B descriptor of a direct stage (cute::UMMA::make_umma_desc<Major::MN>, LayoutType::B128:
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): leading offset = distance between 64-element chunks,
+// stride offset = distance between 8-row k-groups, layout type 2 at [61,64).
+__host__ __device__ constexpr uint64_t smem_desc_template_direct(int lbo_bytes, int sbo_bytes) {
+    return ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
 // ---- solver warpgroup helpers ---------------------------------------------------------------
@@ -353,14 +390,55 @@ __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const 
     }
 }
 
-template <bool kSym>
+// ---- direct staging: pre-split of the opposing factor --------------------------------------------
+// out[row] (32 x 16 bytes) = [ hi (13 pieces, elements >= 100 zero) | 0 x 3 | lo' (13 pieces) | 0 x 3 ]; row == rows is
+// the all-zero padding row.  Same arithmetic as the in-kernel conversion of the fp32 staging path, so both stagings feed
+// the tensor core identical operands.
+__global__ void __launch_bounds__(256) split_factor_kernel(const float* __restrict__ fac, int rows, uint4* __restrict__ out) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t row = gid >> 5;
+    const int g = (int)(gid & 31);
+    if (row > (size_t)rows) return;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    const int gg = g & 15, c0 = gg * 8;
+    if (row < (size_t)rows && c0 < F) {
+        const float4* src = reinterpret_cast<const float4*>(fac + row * F + c0);
+        const float4 a = __ldg(src);
+        const float4 b = (c0 + 4 < F) ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            const float h0 = __uint_as_float(__float_as_uint(v[k]) & 0xFFFFE000u);
+            const float h1 = __uint_as_float(__float_as_uint(v[k + 1]) & 0xFFFFE000u);
+            const __half2 hh = (g < 16) ? __floats2half2_rn(h0, h1)                                               // exact
+                                        : __floats2half2_rn((v[k] - h0) * kLoScale, (v[k + 1] - h1) * kLoScale);
+            w[k >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        o = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    out[gid] = o;
+}
+
+// largest column id a plan touches (+1 = rows of the opposing factor that can be gathered)
+__global__ void max_index_kernel(const int* __restrict__ idx, long long n, int* __restrict__ out) {
+    int m = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) m = max(m, __ldg(idx + i));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(out, m);
+}
+
+// kDirect: `factor_map` describes the pre-split fp16 table (box {64, 1}, SWIZZLE_128B), `zero_row` is the index of its
+// all-zero row (the padding of ragged k-steps), `dcfg` = k-group byte stride | chunk byte stride << 16 inside a stage.
+template <bool kSym, bool kDirect>
 __global__ void __launch_bounds__(Cfg<kSym>::kThreads, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
                       const __grid_constant__ CUtensorMap factor_map, float* __restrict__ out, float lambda, float cg_iter,
                       float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl,
-                      double* __restrict__ sse_terms) {
+                      double* __restrict__ sse_terms, int zero_row, uint32_t dcfg) {
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -376,14 +454,14 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     const int total_stages = cta_stage_ptr[blockIdx.x + 1] - s_begin;
 
     // ---- one-time setup --------------------------------------------------------------------
-    if ((smem_u32(smem_raw) & 127u) != 0u) __trap();     // TMA destinations need 128 B, UMMA descriptors 16 B
-    {   // zero the operand ring: padded feature rows and the spare rows stay zero for ever
-        uint4* p = reinterpret_cast<uint4*>(&sm.op_stage[0][0]);
+    // TMA destinations need 128 B, UMMA descriptors 16 B, SWIZZLE_128B atoms 1024 B
+    if ((smem_u32(smem_raw) & (kDirect ? 1023u : 127u)) != 0u) __trap();
+    if constexpr (!kDirect) {   // zero the operand ring: padded feature rows and the spare rows stay zero for ever
+        uint4* p = reinterpret_cast<uint4*>(&sm.stg.conv.op_stage[0][0]);
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int s = 0; s < S1; ++s) mbar_init(&sm.full_f32[s], 1);
-        for (int s = 0; s < S2; ++s) { mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
+        for (int s = 0; s < DS; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
             for (int g = 0; g < MAX_WG; ++g) mbar_init(&sm.acc_full[g][b], 1);
             mbar_init(&sm.acc_empty[b], 4);
@@ -405,48 +483,58 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
             // divergent path); one elected lane issues the tcgen05 instructions.  The loop is unrolled over
             // the 8 operand slots so every shared-memory descriptor is base + compile-time constant.
-            constexpr uint32_t idesc1 = make_idesc(128, kSym ? N1_SYM : N1);
-            constexpr uint32_t idesc2 = make_idesc(128, N2);
-            const uint32_t op_base0 = smem_u32(&sm.op_stage[0][0]);
+            constexpr uint32_t idesc1 = make_idesc(128, kSym ? N1_SYM : N1, kDirect);
+            constexpr uint32_t idesc2 = make_idesc(128, N2, kDirect);
+            const uint32_t op_base0 = kDirect ? smem_u32(&sm.stg.direct[0][0]) : smem_u32(&sm.stg.conv.op_stage[0][0]);
             const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
+            // operand rows 128.. (lo' | 0): 16 eight-row groups further (K-major), or two 64-element chunks further (direct)
+            const uint32_t lo_off16 = kDirect ? ((2u * (dcfg >> 16)) >> 4) : (uint32_t)(((LO_ROW / 8) * OP_GROUP_BYTES) >> 4);
             const uint32_t empty_bar0 = smem_u32(&sm.empty_op[0]);
             const uint32_t acc_full_bar0 = smem_u32(&sm.acc_full[0][0]);    // [wg][buf], 8 bytes each
+            static_assert(OP_STAGE_BYTES == DSTAGE_BYTES && DS == 2 * S2, "the direct ring is two passes of the 8-slot unrolled body");
             // one k-step: D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']   (+ D[:, 128:256] += lo'^T [hi | r] if !kSym)
             // Everything the step needs beyond the slot number comes from the stage's flag word (see FLAG_*): no
             // run-time tile / chunk counters in this warp, whose instruction stream bounds the k-step rate on long rows.
-            auto issue_step = [&](int slot, uint32_t m) {
+            // dpass / ebar: descriptor and empty barrier of the pass's first slot (the direct ring has two halves).
+            auto issue_step = [&](uint64_t dpass, uint32_t ebar, int slot, uint32_t m) {
                 // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and the
                 // whole ring lies below the field's 256 KB wrap, so plain addition is exact
-                const uint64_t d_hi = dbase + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
+                const uint64_t d_hi = dpass + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
                 const uint32_t d_tmem = tmem_base + ((m >> FLAG_BUF_SHIFT) & 1u) * (uint32_t)ACC_COLS;
                 umma_f16(d_tmem, d_hi, d_hi, idesc1, (m & FLAG_SUB_FIRST) ? 0u : 1u);
                 if (!kSym) {
-                    const uint64_t d_lo = dbase + (uint64_t)((slot * OP_STAGE_BYTES + (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);    // rows 128.. : lo' | 0
+                    const uint64_t d_lo = d_hi + (uint64_t)lo_off16;                          // rows 128.. : lo' | 0
                     umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
                 }
-                umma_commit_addr(empty_bar0 + (uint32_t)slot * 8u);          // operand stage reusable once the MMAs retire
+                umma_commit_addr(ebar + (uint32_t)slot * 8u);                // operand stage reusable once the MMAs retire
                 if (m & FLAG_SUB_LAST) umma_commit_addr(acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u);   // acc_full[wg][buf]: index 2 wg + buf
             };
             auto wait_tile_free = [&](uint32_t m) {
                 if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
             };
             for (int n0 = 0; n0 < total_stages; n0 += S2) {
-                const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
+                // !kDirect: 8 operand slots, one pass = one trip round the ring.  kDirect: 16 slots, passes alternate halves.
+                const uint32_t half = kDirect ? (((uint32_t)n0 / S2) & 1u) : 0u;
+                const uint32_t ph = kDirect ? (((uint32_t)n0 / DS) & 1u) : (((uint32_t)n0 / S2) & 1u);
+                const uint64_t dpass = dbase + (uint64_t)(half * (uint32_t)((S2 * OP_STAGE_BYTES) >> 4));
+                const uint32_t ebar = empty_bar0 + half * (uint32_t)(S2 * 8);
+                unsigned long long* full = &sm.full_op[half * S2];
+                const uint32_t* meta = &sm.meta_op[half * S2];
                 // two k-steps per pass: their barrier waits and flag reads overlap, one elected region issues both
 #pragma unroll
                 for (int slot = 0; slot < S2; slot += 2) {
                     if (n0 + slot < total_stages) {
                         const bool two = (n0 + slot + 1 < total_stages);
-                        mbar_wait(&sm.full_op[slot], ph);
-                        if (two) mbar_wait(&sm.full_op[slot + 1], ph);
-                        const uint32_t m0 = sm.meta_op[slot];
-                        const uint32_t m1 = two ? sm.meta_op[slot + 1] : 0u;
+                        mbar_wait(&full[slot], ph);
+                        if (two) mbar_wait(&full[slot + 1], ph);
+                        const uint32_t m0 = meta[slot];
+                        const uint32_t m1 = two ? meta[slot + 1] : 0u;
                         wait_tile_free(m0);
                         wait_tile_free(m1);
                         tc_fence_after();
                         if (elect_one()) {
-                            issue_step(slot, m0);
-                            if (two) issue_step(slot + 1, m1);
+                            issue_step(dpass, ebar, slot, m0);
+                            if (two) issue_step(dpass, ebar, slot + 1, m1);
                         }
                         __syncwarp();
                     }
@@ -458,19 +546,79 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         if (n_chunks > 0) {
             // ============ autonomous stage workers: warp w owns stages w, w+8, w+16, ... ===========
             // own-stage t (global stage n = w + 8t) lives in fp32 slot w + 8(t&1) and operand slot w.
+            // kDirect: one ring; own-stage t lives in slot w + 8(t&1), which is also the MMA operand.
             const int sw = warp - FIRST_STAGE_WARP;
-            unsigned char* obase = &sm.op_stage[sw][0];
+            [[maybe_unused]] unsigned char* obase = &sm.stg.conv.op_stage[sw][0];
             const int own = (total_stages > sw) ? (total_stages - sw + STAGE_WARPS - 1) / STAGE_WARPS : 0;
             auto load_desc = [&](int t) -> StageDesc {
                 return (t < own) ? stage_tab[s_begin + sw + STAGE_WARPS * t] : StageDesc{0, 0u};
             };
             // lane k < 16 fetches column index and rating k of a stage (coalesced 64-byte reads)
             auto load_idx = [&](const StageDesc& d) -> int {
-                return (lane < (int)(d.info & 0xffu)) ? __ldg(colidx + d.pos + lane) : 0;
+                return (lane < (int)(d.info & 0xffu)) ? __ldg(colidx + d.pos + lane) : (kDirect ? zero_row : 0);
             };
             auto load_val = [&](const StageDesc& d) -> float {
                 return (lane < (int)(d.info & 0xffu)) ? __ldg(val + d.pos + lane) : 0.f;
             };
+            if constexpr (kDirect) {
+                const uint32_t kg_stride = dcfg & 0xffffu, ch_stride = dcfg >> 16;
+                // arm the slot's mbarrier and launch the 16 gathers of one stage (warp-collective): lane L < 16 fetches
+                // 64-element chunk L >> 2 of rows 4 (L & 3) .. + 3 -> four consecutive 128-byte swizzle lines.  Rows past
+                // cnt carry the index of the table's all-zero row, so every stage is a full 8 KB.
+                auto issue_direct = [&](int slot, int my_idx, float my_val) {
+                    if (lane < KT) sm.stage_vals[slot][lane] = my_val;
+                    const int src = (lane & 3) * GROUP_ROWS;
+                    const int i0 = __shfl_sync(0xffffffffu, my_idx, src + 0);
+                    const int i1 = __shfl_sync(0xffffffffu, my_idx, src + 1);
+                    const int i2 = __shfl_sync(0xffffffffu, my_idx, src + 2);
+                    const int i3 = __shfl_sync(0xffffffffu, my_idx, src + 3);
+                    if (lane == 0) mbar_arrive_expect_tx(&sm.full_f32[slot], (uint32_t)DSTAGE_BYTES);
+                    __syncwarp();
+                    if (lane < KT) {
+                        const uint32_t c = (uint32_t)lane >> 2, q = (uint32_t)lane & 3u;
+                        tma_gather4_col(&sm.stg.direct[slot][(q >> 1) * kg_stride + c * ch_stride + (q & 1u) * 512u], &factor_map,
+                                        (int)c * SPLIT_CHUNK, i0, i1, i2, i3, &sm.full_f32[slot]);
+                    }
+                };
+                StageDesc d0 = load_desc(0), d1 = load_desc(1), d2 = load_desc(2), d3 = load_desc(3);
+                {
+                    const int ia = load_idx(d0); const float va = load_val(d0);
+                    const int ib = load_idx(d1); const float vb = load_val(d1);
+                    if (own > 0) issue_direct(sw, ia, va);
+                    if (own > 1) issue_direct(sw + STAGE_WARPS, ib, vb);
+                }
+                int idx2 = load_idx(d2);
+                float val2 = load_val(d2);
+                for (int t = 0; t < own; ++t) {
+                    // software prefetch: descriptor of t+4, indices/ratings of t+3 (consumed next iteration)
+                    const StageDesc d4 = load_desc(t + 4);
+                    const int idx3 = load_idx(d3);
+                    const float val3 = load_val(d3);
+                    const int slot = sw + STAGE_WARPS * (t & 1);
+                    const uint32_t par = ((uint32_t)t >> 1) & 1u;     // this is use number t >> 1 of the slot
+                    mbar_wait(&sm.full_f32[slot], par);               // the 16 rows have landed
+                    if (lane < KT) {
+                        // the ratings ride along as operand columns 112 (r_hi) and 113 (r_lo') of gathered row k = lane:
+                        // chunk 1, element 48 -> 16-byte piece 6 of the row's 128-byte line, XOR-swizzled with the line number
+                        const float r0 = sm.stage_vals[slot][lane];
+                        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
+                        const uint32_t k = (uint32_t)lane;
+                        unsigned char* ob = &sm.stg.direct[slot][(k >> 3) * kg_stride + ch_stride + (k & 7u) * 128u + ((6u ^ (k & 7u)) << 4)];
+                        *reinterpret_cast<__half2*>(ob) = __floats2half2_rn(h0, (r0 - h0) * kLoScale);
+                    }
+                    if (lane == 0) sm.meta_op[slot] = d0.info >> 8;
+                    fence_proxy_async();                  // the generic-proxy rating writes ordered before the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.full_op[slot]);
+                    if (t + 2 < own) {
+                        // own-stage t+2 reuses this slot: the MMAs of stage t must have retired (tcgen05.commit -> empty_op)
+                        mbar_wait(&sm.empty_op[slot], par);
+                        issue_direct(slot, idx2, val2);
+                    }
+                    d0 = d1; d1 = d2; d2 = d3; d3 = d4;
+                    idx2 = idx3; val2 = val3;
+                }
+            } else {
             // arm the slot's mbarrier and launch the gathers of one stage (warp-collective)
             auto issue = [&](int fs, const StageDesc& d, int my_idx, float my_val) {
                 const int cnt = (int)(d.info & 0xffu);
@@ -485,7 +633,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     mbar_arrive_expect_tx(&sm.full_f32[fs], (uint32_t)((cnt + GROUP_ROWS - 1) / GROUP_ROWS) * GROUP_ROWS * ROW_BYTES);
                 __syncwarp();
                 if (lane < KT / GROUP_ROWS && lane * GROUP_ROWS < cnt)
-                    tma_gather4(&sm.f32_stage[fs][lane * GROUP_BYTES], &factor_map, i0, i1, i2, i3, &sm.full_f32[fs]);
+                    tma_gather4(&sm.stg.conv.f32_stage[fs][lane * GROUP_BYTES], &factor_map, i0, i1, i2, i3, &sm.full_f32[fs]);
             };
 
             // prologue: descriptors of own-stages 0..3, gathers of 0 and 1 in flight, indices of 2 ready
@@ -508,7 +656,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const int fs = sw + STAGE_WARPS * (t & 1);
                 const uint32_t cnt = d0.info & 0xffu;
                 const uint32_t flags = d0.info >> 8;
-                const unsigned char* fbase = &sm.f32_stage[fs][0];
+                const unsigned char* fbase = &sm.stg.conv.f32_stage[fs][0];
                 mbar_wait(&sm.full_f32[fs], ((uint32_t)t >> 1) & 1u);
                 mbar_wait(&sm.empty_op[sw], ((uint32_t)t & 1u) ^ 1u);
                 if (cnt < KT) {
@@ -575,6 +723,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 d0 = d1; d1 = d2; d2 = d3; d3 = d4;
                 idx2 = idx3; val2 = val3;
             }
+            }   // !kDirect
         }
     } else {
         reg_inc<C::kRegsEpi>();
@@ -746,23 +895,56 @@ struct TcWork {
     bool sym = false;                   // long chunks: the tensor core forms half of the cross term, the epilogue transposes
     CUtensorMap factor_map;             // 2-D view [rows][F] fp32 of the opposing factor, box {F, 1}
     const float* mapped_factor = nullptr;
+    // direct staging (CUMF_TC_DIRECT=1): fp16 pre-split copy of the opposing factor, refreshed before every launch
+    bool direct = false;
+    long long idx_span = 0;             // ratings the plan's chunks cover (largest chunk end)
+    const int* scanned_colidx = nullptr;
+    int factor_rows = 0;                // largest column id + 1 found in scanned_colidx[0, idx_span)
+    DevBuf split_tab;                   // [factor_rows + 1][256] fp16, last row zero
+    DevBuf max_idx;
+    CUtensorMap split_map;              // 2-D view [factor_rows + 1][256] fp16, box {64, 1}, SWIZZLE_128B
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
-static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn tensor_map_encoder() {
     static EncodeFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
             set_last_error("cuTensorMapEncodeTiled is not available from this driver");
-            return CUMF_ECUDA;
+            return nullptr;
         }
         encode = (EncodeFn)fn;
     }
+    return encode;
+}
+
+// pre-split fp16 table [rows][256]: tile::gather4 fetches four {64, 1} boxes (one 128-byte swizzle line per row);
+// coordinates beyond `rows` are out of bounds and read as zero
+static int encode_split_map(CUtensorMap* map, const void* d_table, long long rows) {
+    EncodeFn encode = tensor_map_encoder();
+    if (!encode) return CUMF_ECUDA;
+    const cuuint64_t gdim[2] = {(cuuint64_t)SPLIT_COLS, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)SPLIT_ROW_BYTES};
+    const cuuint32_t box[2] = {(cuuint32_t)SPLIT_CHUNK, 1u};
+    const cuuint32_t estride[2] = {1u, 1u};
+    const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_table), gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_last_error("cuTensorMapEncodeTiled (split table) failed with CUresult " + std::to_string((int)rc));
+        return CUMF_ECUDA;
+    }
+    return CUMF_OK;
+}
+
+static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
+    EncodeFn encode = tensor_map_encoder();
+    if (!encode) return CUMF_ECUDA;
     // The row count only bounds the coordinates the hardware accepts; the gathered indices are CSR column ids
     // of rows that exist, so a generous bound is safe.
     const cuuint64_t gdim[2] = {(cuuint64_t)F, (cuuint64_t)1 << 31};
@@ -837,6 +1019,11 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     TcWork* w = new TcWork();
     w->grid = grid;
     w->nchunks = n;
+    {
+        const char* d = getenv("CUMF_TC_DIRECT");
+        w->direct = d && *d == '1';
+        for (int c = 0; c < n; ++c) w->idx_span = std::max<long long>(w->idx_span, chunks[c].end);
+    }
     {   // per-chunk epilogue cost (transpose) vs per-k-step MMA saving: the symmetric mode pays from ~32 k-steps per chunk;
         // measured on Netflix: X side (348 k-steps/chunk) 9.6 -> 8.6 ms, theta side (13 k-steps/chunk) 14.8 -> 16.2 ms
         const char* m = getenv("CUMF_TC_SYM");
@@ -887,6 +1074,8 @@ void tc_plan_destroy(TcWork* w) {
     w->stage_tab.release();
     w->chunk_stage_base.release();
     w->chunk_meta.release();
+    w->split_tab.release();
+    w->max_idx.release();
     delete w;
 }
 
@@ -901,21 +1090,63 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     const size_t smem = sizeof(Smem);
     static bool attr_set = false;
     if (!attr_set) {
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    if (w->mapped_factor != d_factor) {
-        CUMF_REQUIRE((reinterpret_cast<uintptr_t>(d_factor) & 15u) == 0, "the factor matrix must be 16-byte aligned for TMA");
-        CUMF_TRY(encode_factor_map(&w->factor_map, d_factor));
-        w->mapped_factor = d_factor;
+    CUMF_REQUIRE((reinterpret_cast<uintptr_t>(d_factor) & 15u) == 0, "the factor matrix must be 16-byte aligned for TMA");
+    const int threads = w->sym ? Cfg<true>::kThreads : Cfg<false>::kThreads;
+    if (w->direct) {
+        // rows of the opposing factor the plan can gather = largest column id + 1 (one scan per plan and index array)
+        if (w->scanned_colidx != d_colidx) {
+            if (!w->max_idx.p) CUMF_TRY(w->max_idx.alloc(sizeof(int)));
+            CUMF_CUDA_TRY(cudaMemsetAsync(w->max_idx.p, 0, sizeof(int), st));
+            max_index_kernel<<<592, 256, 0, st>>>(d_colidx, w->idx_span, w->max_idx.as<int>());
+            int h_max = 0;
+            CUMF_CUDA_TRY(cudaMemcpyAsync(&h_max, w->max_idx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+            *launches += 1;
+            const int rows = h_max + 1;
+            if (rows != w->factor_rows || !w->split_tab.p) {
+                w->split_tab.release();
+                CUMF_TRY(w->split_tab.alloc((size_t)(rows + 1) * SPLIT_ROW_BYTES));
+                CUMF_TRY(encode_split_map(&w->split_map, w->split_tab.p, (long long)rows + 1));
+                w->factor_rows = rows;
+            }
+            w->scanned_colidx = d_colidx;
+        }
+        const size_t pieces = (size_t)(w->factor_rows + 1) * 32;
+        split_factor_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(d_factor, w->factor_rows, w->split_tab.as<uint4>());
+        CUMF_CUDA_TRY(cudaGetLastError());
+        *launches += 1;
+        // bring-up knobs: stage arrangement (0: k-group-major, chunks 1 KB apart; 1: chunk-major, k-groups 1 KB apart) and
+        // explicit descriptor offsets
+        const char* a = getenv("CUMF_TC_DIRECT_ARR");
+        const bool chunk_major = a && *a == '1';
+        const uint32_t kg = chunk_major ? 1024u : 4096u, ch = chunk_major ? 2048u : 1024u;
+        const char* lbo_env = getenv("CUMF_TC_DIRECT_LBO");
+        const char* sbo_env = getenv("CUMF_TC_DIRECT_SBO");
+        const int lbo = (lbo_env && *lbo_env) ? atoi(lbo_env) : (int)ch;
+        const int sbo = (sbo_env && *sbo_env) ? atoi(sbo_env) : (int)kg;
+        const uint64_t desc_tmpl = smem_desc_template_direct(lbo, sbo);
+        auto kernel = w->sym ? als_fused_f100_kernel<true, true> : als_fused_f100_kernel<false, true>;
+        kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
+                                               d_colidx, d_val, w->split_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
+                                               desc_tmpl, d_sse_terms, w->factor_rows, kg | (ch << 16));
+    } else {
+        if (w->mapped_factor != d_factor) {
+            CUMF_TRY(encode_factor_map(&w->factor_map, d_factor));
+            w->mapped_factor = d_factor;
+        }
+        const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
+        const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
+        auto kernel = w->sym ? als_fused_f100_kernel<true, false> : als_fused_f100_kernel<false, false>;
+        kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
+                                               d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
+                                               desc_tmpl, d_sse_terms, 0, 0u);
     }
-    const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
-    const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
-    auto kernel = w->sym ? als_fused_f100_kernel<true> : als_fused_f100_kernel<false>;
-    kernel<<<w->grid, w->sym ? Cfg<true>::kThreads : Cfg<false>::kThreads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(),
-                                             w->cta_stage_ptr.as<int>(), d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter,
-                                             d_scratchA, d_scratchB, desc_tmpl, d_sse_terms);
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;
     return CUMF_OK;

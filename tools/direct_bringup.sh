@@ -1,0 +1,53 @@
+#!/usr/bin/env bash
+# tools/direct_bringup.sh -- one GPU-box round trip for the direct-staging variant of the fused kernel:
+# layout probe -> Gram parity (finds the working descriptor variant) -> stress -> bench A/B -> parity tests -> ncu.
+# Every step runs under its own timeout and logs to gpurun_out/; nothing here is a bench value of record.
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/direct
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > "$OUT/gpu.txt" 2>&1
+
+echo "== probe" | tee "$OUT/probe.log"
+for v in "0" "1" "0 4096 1024" "1 1024 2048"; do
+  timeout -s KILL 60 tools/mn_major_probe $v >> "$OUT/probe.log" 2>&1
+  echo "   exit $?" >> "$OUT/probe.log"
+done
+tail -n 40 "$OUT/probe.log"
+
+echo "== bring-up (Gram parity, direct vs fp32 staging)"
+CFG=""
+for cfg in "ARR=0" "ARR=1" "ARR=0 LBO=4096 SBO=1024" "ARR=1 LBO=1024 SBO=2048"; do
+  envs="CUMF_TC_DIRECT=1"
+  for kv in $cfg; do envs="$envs CUMF_TC_DIRECT_${kv}"; done
+  echo "-- $envs" | tee -a "$OUT/bringup.log"
+  if env $envs timeout -s KILL 150 python tools/tc_bringup.py direct >> "$OUT/bringup.log" 2>&1; then
+    CFG="$envs"
+    break
+  fi
+done
+tail -n 25 "$OUT/bringup.log"
+echo "working config: ${CFG:-none}" | tee "$OUT/config.txt"
+
+echo "== bench, fp32 staging (baseline of this box)"
+timeout -s KILL 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > "$OUT/bench_conv.json" 2> "$OUT/bench_conv.err"
+cat "$OUT/bench_conv.json"
+
+if [ -n "$CFG" ]; then
+  echo "== stress (many chunks per CTA, split rows): direct vs SIMT"
+  env $CFG timeout -s KILL 150 python tools/tc_bringup.py stress > "$OUT/stress.log" 2>&1; echo "exit $?" >> "$OUT/stress.log"
+  env $CFG CUMF_TC_CTAS=3 timeout -s KILL 150 python tools/tc_bringup.py stress >> "$OUT/stress.log" 2>&1; echo "exit $?" >> "$OUT/stress.log"
+  cat "$OUT/stress.log"
+  echo "== bench, direct staging"
+  env $CFG timeout -s KILL 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > "$OUT/bench_direct.json" 2> "$OUT/bench_direct.err"
+  cat "$OUT/bench_direct.json"; tail -n 5 "$OUT/bench_direct.err"
+  echo "== parity tests with direct staging"
+  env $CFG timeout -s KILL 420 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > "$OUT/pytest_direct.log" 2>&1
+  tail -n 8 "$OUT/pytest_direct.log"
+  echo "== ncu (direct)"
+  env $CFG timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:als_fused -s 2 -c 2 -f \
+      -o "$OUT/direct_full" python tools/profile_fused.py > "$OUT/ncu.log" 2>&1
+  tail -n 3 "$OUT/ncu.log"
+  ls -la "$OUT"
+fi
+echo "== done"

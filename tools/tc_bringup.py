@@ -55,6 +55,35 @@ def main():
             u = 9
             print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", tt[u][0, :6])
             print("  row 9 ref[1,:6]", ref[u][1, :6], "\n  row 9 got[1,:6]", tt[u][1, :6])
+    elif which == "direct":
+        # direct staging (pre-split fp16 table, swizzled MN-major gather) against the fp32-staging kernel: both feed the
+        # tensor core identical operands in the same order, so materialised [A|b] must agree bit for bit
+        outs = {}
+        for mode in ("0", "1"):
+            os.environ["CUMF_TC_DIRECT"] = mode
+            tt = torch.full((m, f, f), float("nan"), device="cuda")
+            rhs = torch.full((m, f), float("nan"), device="cuda")
+            c.gram(0, m, tt, dev(rowptr), dev(colidx), lam, m, f, dev(factor), rhs=rhs, val=dev(val), path=c.PATH_TC)
+            torch.cuda.synchronize()
+            outs[mode] = (tt.cpu().numpy(), rhs.cpu().numpy())
+        print("direct arr =", os.environ.get("CUMF_TC_DIRECT_ARR", "0"), "lbo/sbo =", os.environ.get("CUMF_TC_DIRECT_LBO"),
+              os.environ.get("CUMF_TC_DIRECT_SBO"))
+        worst = 0.0
+        for u in range(m):
+            scale = max(np.abs(ref[u]).max(), 1e-30)
+            e_conv = np.abs(outs["0"][0][u] - ref[u]).max() / scale
+            e_dir = np.abs(outs["1"][0][u] - ref[u]).max() / scale
+            same = np.array_equal(outs["0"][0][u], outs["1"][0][u]) and np.array_equal(outs["0"][1][u], outs["1"][1][u])
+            rb = np.abs(outs["1"][1][u] - rhs_ref[u]).max() / max(np.abs(rhs_ref[u]).max(), 1e-30)
+            worst = max(worst, e_dir if np.isfinite(e_dir) else 1e9, rb if np.isfinite(rb) else 1e9)
+            print(f"  row {u:2d} len {lengths[u]:5d}: err vs oracle  fp32-staging {e_conv:.3e}  direct {e_dir:.3e}  rhs {rb:.1e}  bit-identical {same}")
+        print("DIRECT GRAM", "OK" if worst < 1e-5 else "WRONG", f"(worst {worst:.3e})")
+        if worst >= 1e-5:
+            u = 9
+            print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", outs["1"][0][u][0, :6])
+            print("  row 9 ref[1,:6]", ref[u][1, :6], "\n  row 9 got[1,:6]", outs["1"][0][u][1, :6])
+            print("  row 9 rhs ref[:6]", rhs_ref[u][:6], "\n  row 9 rhs got[:6]", outs["1"][1][u][:6])
+            sys.exit(3)
     elif which == "stress":
         # many chunks per CTA (CUMF_TC_CTAS small), multi-tile rows, split rows: fused vs SIMT
         rng = np.random.default_rng(7)
