@@ -167,6 +167,66 @@ def cpu_baseline(r, theta0, X0, w, budget_s: float = 15.0):
             "sample": "oracle/als_cpu.c (OpenMP) on " + "; ".join(sample_desc) + "; scaled by rating share"}
 
 
+def e2e_sharded(args, r, theta0, X0, f, lam, path, rank, local_rank, world, barrier):
+    """e2e at N > 1: cumf_als_b200.dist.ShardedAls over one AlsSolver per rank, from pinned HOST buffers -- every rank
+    uploads its CSR/CSC shard + the factors, runs K iterations with the row-block exchange and the per-iteration
+    all-reduced RMSE doALS prints (als.cu:991, 1018), and downloads the factors; max wall clock over ranks."""
+    import torch
+    import torch.distributed as dist
+    import cumf_als_b200 as c
+    from cumf_als_b200.data import nnz_balanced_ranges
+    from cumf_als_b200.dist import GpuEngine, ShardedAls
+
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row",
+                 "test_row", "test_col", "test_val"):
+        setattr(r, name, pin(getattr(r, name)))
+    th0, x0 = pin(theta0), pin(X0)
+    x_ranges = nnz_balanced_ranges(r.csr_indptr, world)
+    t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
+
+    def call(iters):
+        s2 = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
+                         r.test_row, r.test_col, r.test_val, r.m, r.n, f, lam, x_range=x_ranges[rank],
+                         theta_range=t_ranges[rank], device=local_rank, path=path)
+        s2.set_factors(th0, x0)
+        sh = ShardedAls(GpuEngine(s2, local_rank), x_ranges, t_ranges, r.nnz, r.nnz_test)
+        fin = None
+        for _ in range(iters):
+            sh.step()
+            fin = sh.rmse()
+        out = s2.get_factors()
+        s2.close()
+        return fin, out
+
+    if args.warmup > 0:
+        call(1)
+    barrier()
+    t0 = time.perf_counter()
+    fin, _ = call(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    # bytes this rank moved: its rating shards + both full factors in, both full factors out; summed over ranks
+    xr0, xr1 = x_ranges[rank]
+    tr0, tr1 = t_ranges[rank]
+    xn = int(r.csr_indptr[xr1] - r.csr_indptr[xr0])      # CSR shard: column ids + values + COO rows (12 B per rating)
+    tn = int(r.csc_indptr[tr1] - r.csc_indptr[tr0])      # CSC shard: row ids + values (8 B per rating)
+    eff = ((r.nnz_test - 1) // 256) * 256                # test samples the reference's launch covers (als.cu:1006)
+    test_share = eff * xr1 // r.m - eff * xr0 // r.m
+    stats = [wall, float(xn * 12 + tn * 8 + test_share * 12 + th0.nbytes + x0.nbytes), float(th0.nbytes + x0.nbytes)]
+    if world > 1:
+        wt = torch.tensor([stats[0]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        bt = torch.tensor(stats[1:], device="cuda", dtype=torch.float64)
+        dist.all_reduce(bt)
+        stats = [float(wt.item()), float(bt[0].item()), float(bt[1].item())]
+    return {"value": args.steps / stats[0], "unit": "iterations/s", "h2d_bytes_per_step": int(stats[1]) // args.steps,
+            "d2h_bytes_per_step": int(stats[2]) // args.steps, "wall_s": stats[0],
+            "final_test_rmse": fin[1] if fin else None,
+            "what": "per rank: AlsSolver(host shard) + set_factors + K x (ShardedAls.step + all-reduced RMSE) + get_factors, "
+                    "pinned host buffers; max wall clock over ranks; one untimed 1-iteration call first"}
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -298,6 +358,15 @@ def run_ours(args, w):
                        "final_test_rmse": fin,
                        "what": "doALS(host pointers, ITERS=steps): upload + iterations + per-iteration RMSE + download; "
                                "one untimed 1-iteration call first (both arms)"}
+    # e2e at N > 1: the sharded public API from pinned host buffers (CUMF_BENCH_SHARDED_E2E=1 exercises it on one GPU)
+    force_sharded = os.environ.get("CUMF_BENCH_SHARDED_E2E") == "1"
+    if (world > 1 or force_sharded) and not args.no_e2e:
+        try:
+            e2e = e2e_sharded(args, r, theta0, X0, f, lam, path, rank, local_rank, world, barrier)
+        except Exception as exc:        # the resident numbers above stay valid; every rank fails the same way
+            e2e = {"error": f"{type(exc).__name__}: {exc}"}
+        if rank == 0:
+            line["e2e_sharded" if world == 1 else "e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(r, theta0, X0, w)
     if rank == 0:

@@ -99,12 +99,21 @@ constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated i
 // rows of a k-step straight into the UMMA **MN-major** SWIZZLE_128B canonical layout: four 64-element chunks per
 // row, 8 rows x 128 B per swizzle atom.  No fp32 staging ring, no conversion pass: per k-step the shared-memory pipe
 // carries 8 KB of TMA writes + the UMMA operand reads instead of 6.4 + 6.4 + 6.5 KB of staging traffic on top of them.
-constexpr int DS = 16;                    // direct stage ring depth (two slots per stage-worker warp)
-constexpr int DSTAGE_BYTES = 8192;        // 16 rows x 512 B
+// A direct stage holds 32 ratings = two 16-row MMA k-groups: one barrier round trip, one flag word and one commit of the
+// MMA-issuing warp (whose instruction stream bounds long rows) per 32 ratings instead of per 16.
+constexpr int DKT = 32;                   // ratings per direct stage
+constexpr int DS = 8;                     // direct stage ring depth: one slot per stage-worker warp
 constexpr int SPLIT_COLS = 256;           // fp16 elements per row of the pre-split table
 constexpr int SPLIT_ROW_BYTES = SPLIT_COLS * 2;
 constexpr int SPLIT_CHUNK = 64;           // elements per 128-byte swizzle line
-static_assert(DSTAGE_BYTES == KT * SPLIT_ROW_BYTES, "one stage = 16 gathered rows");
+constexpr int DGROUP_BYTES = KT * SPLIT_ROW_BYTES;    // 8192: one MMA k-group (16 rows)
+constexpr int DSTAGE_BYTES = DKT * SPLIT_ROW_BYTES;   // 16384
+constexpr int DSUB_STEPS = 8;             // direct stages per TMEM tile: the same 256 ratings as SUB_STEPS x KT
+// inside a k-group: 8-row swizzle atoms of one 64-element chunk are 1 KB, the four chunks of 8 rows 4 KB
+// (the CUTLASS tile_to_shape order of Layout_MN_SW128_Atom; tools/mn_major_probe.cu checks it against the hardware)
+constexpr int D_CHUNK_STRIDE = 1024;      // -> descriptor leading byte offset
+constexpr int D_KG_STRIDE = 4096;         // -> descriptor stride byte offset
+static_assert(DSUB_STEPS * DKT == SUB_STEPS * KT, "both stagings cut the accumulation chains at the same ratings");
 constexpr int TMEM_COLS = 512;
 // accumulator tile, one MMA per k-step:  D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']
 //   lanes 0..99 (features i):  [0,112) P[i][:] = hi_i . hi_j | 112 hi_i . r_hi | 113 hi_i . r_lo' | [128,240) S[i][:] = hi_i . lo'_j
@@ -138,7 +147,9 @@ constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST =
 //   bit 4  TMEM buffer of the stage's tile (tile index within the CTA & 1)
 //   bits 5-6  solver warpgroup that drains it (chunk index within the CTA mod #warpgroups) -> acc_full[wg][bit4]
 //   bit 7  parity to wait for on acc_empty[bit4] before the tile's first MMA
+//   bit 8  (direct stages) the stage holds more than 16 ratings: its second MMA k-group is fetched and issued
 constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 7;
+constexpr uint32_t FLAG_TWO_GROUPS = 256u;
 
 // One k-step of work: 16 (or fewer) consecutive ratings of one chunk.  Precomputed per plan
 // (stage table), so every stage worker warp is autonomous.
@@ -156,17 +167,18 @@ union Staging {
     ConvStaging conv;                               // !kDirect: fp32 gather ring + converted fp16 operand ring
     unsigned char direct[DS][DSTAGE_BYTES];         // kDirect: one ring, TMA destination == UMMA operand (131072)
 };
-static_assert(DS >= S1 && DS >= S2, "barrier / metadata arrays are sized for the direct ring");
+constexpr int NBAR = S1;                  // stage barriers / metadata slots (the larger of the rings)
+static_assert(NBAR >= DS && NBAR >= S2, "barrier / metadata arrays cover every ring");
 struct __align__(1024) Smem {   // dynamic shared memory, used in place (SWIZZLE_128B atoms need 1024-byte alignment)
     Staging stg;
-    float stage_vals[DS][KT];    // the ratings of the stage in flight in each gather slot (zero beyond cnt)
-    uint32_t meta_op[DS];        // stage flags forwarded to the MMA warp
+    float stage_vals[NBAR][DKT]; // the ratings of the stage in flight in each gather slot (zero beyond cnt)
+    uint32_t meta_op[NBAR];      // stage flags forwarded to the MMA warp
     // per solver warpgroup: kSym -> TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats);
     //                        !kSym -> columns [64,100) of the 100 rows of [A] it is solving (3 x 3600 floats)
     float solver_scratch[3 * F * SM_ROW_STRIDE];
     float sp[MAX_WG][2][128];    // CG direction vector per solver warpgroup, double buffered
     float red[MAX_WG][3][4];     // cross-warp partial sums
-    unsigned long long full_f32[DS], full_op[DS], empty_op[DS];
+    unsigned long long full_f32[NBAR], full_op[NBAR], empty_op[NBAR];
     // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
     // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
     // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
@@ -363,29 +375,31 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[Cfg<kSym>:
     b = kFirst ? tb : b + tb;
 }
 
-__device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + KT - 1) / KT); }
+template <int kRows> __device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + kRows - 1) / kRows); }
 
-// stage table of a plan: one StageDesc per k-step, in chunk order (built once per plan)
+// stage table of a plan: one StageDesc per stage (kRows ratings), in chunk order (built once per plan)
 // chunk_meta[c] = (index of the chunk's first tile within its CTA) << 2 | (index of the chunk within its CTA mod #solver warpgroups)
+template <int kRows, int kSub>
 __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ chunk_stage_base,
                                         const int* __restrict__ chunk_meta, int nchunks, StageDesc* __restrict__ table) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const Chunk ck = chunks[c];
-    const int steps = chunk_steps(ck);
+    const int steps = chunk_steps<kRows>(ck);
     const uint32_t wg = (uint32_t)chunk_meta[c] & 3u;
     const uint32_t tile0 = (uint32_t)chunk_meta[c] >> 2;
     StageDesc* out = table + chunk_stage_base[c];
     for (int s = 0; s < steps; ++s) {
-        const int pos = ck.begin + s * KT;
-        const int cnt = max(0, min(KT, ck.end - pos));
+        const int pos = ck.begin + s * kRows;
+        const int cnt = max(0, min(kRows, ck.end - pos));
         const bool last = (s == steps - 1);
-        const uint32_t tile = tile0 + (uint32_t)(s / SUB_STEPS);
+        const uint32_t tile = tile0 + (uint32_t)(s / kSub);
         const uint32_t flags = (s == 0 ? FLAG_CHUNK_FIRST : 0u) | (last ? FLAG_CHUNK_LAST : 0u) |
-                               ((s % SUB_STEPS) == 0 ? FLAG_SUB_FIRST : 0u) |
-                               ((last || (s % SUB_STEPS) == SUB_STEPS - 1) ? FLAG_SUB_LAST : 0u) |
+                               ((s % kSub) == 0 ? FLAG_SUB_FIRST : 0u) |
+                               ((last || (s % kSub) == kSub - 1) ? FLAG_SUB_LAST : 0u) |
                                ((tile & 1u) << FLAG_BUF_SHIFT) | (wg << FLAG_WG_SHIFT) |
-                               ((((tile >> 1) & 1u) ^ 1u) << FLAG_EMPTY_PARITY_SHIFT);
+                               ((((tile >> 1) & 1u) ^ 1u) << FLAG_EMPTY_PARITY_SHIFT) |
+                               (cnt > KT ? FLAG_TWO_GROUPS : 0u);
         out[s] = StageDesc{pos, (uint32_t)cnt | (flags << 8)};
     }
 }
@@ -430,7 +444,7 @@ __global__ void max_index_kernel(const int* __restrict__ idx, long long n, int* 
 }
 
 // kDirect: `factor_map` describes the pre-split fp16 table (box {64, 1}, SWIZZLE_128B), `zero_row` is the index of its
-// all-zero row (the padding of ragged k-steps), `dcfg` = k-group byte stride | chunk byte stride << 16 inside a stage.
+// all-zero row (the padding of ragged k-groups).
 template <bool kSym, bool kDirect>
 __global__ void __launch_bounds__(Cfg<kSym>::kThreads, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
@@ -438,7 +452,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                       const int* __restrict__ colidx, const float* __restrict__ val,
                       const __grid_constant__ CUtensorMap factor_map, float* __restrict__ out, float lambda, float cg_iter,
                       float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl,
-                      double* __restrict__ sse_terms, int zero_row, uint32_t dcfg) {
+                      double* __restrict__ sse_terms, int zero_row) {
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -461,7 +475,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int s = 0; s < DS; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
+        for (int s = 0; s < NBAR; ++s) { mbar_init(&sm.full_f32[s], 1); mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < 2; ++b) {
             for (int g = 0; g < MAX_WG; ++g) mbar_init(&sm.acc_full[g][b], 1);
             mbar_init(&sm.acc_empty[b], 4);
@@ -475,9 +489,13 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough)
+    // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough).
+    // Direct staging: the workers only issue gathers (48 registers), the issuer keeps the descriptors of its 8 x 4 MMAs
+    // per ring trip in registers (80) -- with 48 ptxas spills them into the loop that bounds the kernel.
+    constexpr int kRegsProd = kDirect ? 80 : C::kRegsProd, kRegsStage = kDirect ? 48 : C::kRegsStage;
+    static_assert(128 * (kRegsProd + 2 * kRegsStage + C::kWG * C::kRegsEpi) <= C::kThreads * C::kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
     if (warp < 4) {
-        reg_dec<C::kRegsProd>();
+        reg_dec<kRegsProd>();
         if (n_chunks > 0 && warp == MMA_WARP) {
             // ================================ MMA issuer ========================================
             // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
@@ -485,56 +503,55 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             // the 8 operand slots so every shared-memory descriptor is base + compile-time constant.
             constexpr uint32_t idesc1 = make_idesc(128, kSym ? N1_SYM : N1, kDirect);
             constexpr uint32_t idesc2 = make_idesc(128, N2, kDirect);
+            constexpr int STAGE_BYTES = kDirect ? DSTAGE_BYTES : OP_STAGE_BYTES;
+            // operand rows 128.. (lo' | 0): 16 eight-row groups further (K-major), or two 64-element chunks further (direct)
+            constexpr uint32_t LO_OFF16 = (uint32_t)((kDirect ? 2 * D_CHUNK_STRIDE : (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);
+            static_assert(DS == S2, "both rings have one slot per stage-worker warp: the 8-slot unrolled loop serves both");
             const uint32_t op_base0 = kDirect ? smem_u32(&sm.stg.direct[0][0]) : smem_u32(&sm.stg.conv.op_stage[0][0]);
             const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
-            // operand rows 128.. (lo' | 0): 16 eight-row groups further (K-major), or two 64-element chunks further (direct)
-            const uint32_t lo_off16 = kDirect ? ((2u * (dcfg >> 16)) >> 4) : (uint32_t)(((LO_ROW / 8) * OP_GROUP_BYTES) >> 4);
+            // this warp's own copy of the TMEM base: the kernel-wide value is spilled around the role branches, and a local
+            // memory reload inside the elected region sits on the critical path of every pass
+            const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(&sm.tmem_base);
             const uint32_t empty_bar0 = smem_u32(&sm.empty_op[0]);
             const uint32_t acc_full_bar0 = smem_u32(&sm.acc_full[0][0]);    // [wg][buf], 8 bytes each
-            static_assert(OP_STAGE_BYTES == DSTAGE_BYTES && DS == 2 * S2, "the direct ring is two passes of the 8-slot unrolled body");
-            // one k-step: D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']   (+ D[:, 128:256] += lo'^T [hi | r] if !kSym)
+            // one k-group: D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']   (+ D[:, 128:256] += lo'^T [hi | r] if !kSym)
             // Everything the step needs beyond the slot number comes from the stage's flag word (see FLAG_*): no
             // run-time tile / chunk counters in this warp, whose instruction stream bounds the k-step rate on long rows.
-            // dpass / ebar: descriptor and empty barrier of the pass's first slot (the direct ring has two halves).
-            auto issue_step = [&](uint64_t dpass, uint32_t ebar, int slot, uint32_t m) {
+            auto issue_step = [&](int slot, uint32_t m) {
                 // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and the
                 // whole ring lies below the field's 256 KB wrap, so plain addition is exact
-                const uint64_t d_hi = dpass + (uint64_t)((slot * OP_STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
+                const uint64_t d_hi = dbase + (uint64_t)((slot * STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
                 const uint32_t d_tmem = tmem_base + ((m >> FLAG_BUF_SHIFT) & 1u) * (uint32_t)ACC_COLS;
                 umma_f16(d_tmem, d_hi, d_hi, idesc1, (m & FLAG_SUB_FIRST) ? 0u : 1u);
-                if (!kSym) {
-                    const uint64_t d_lo = d_hi + (uint64_t)lo_off16;                          // rows 128.. : lo' | 0
-                    umma_f16(d_tmem + SCOL, d_lo, d_hi, idesc2, 1u);
+                if (!kSym) umma_f16(d_tmem + SCOL, d_hi + (uint64_t)LO_OFF16, d_hi, idesc2, 1u);      // rows 128.. : lo' | 0
+                if (kDirect && (m & FLAG_TWO_GROUPS)) {       // ratings 16..31 of the stage: the next 8 KB k-group
+                    const uint64_t d_hi2 = d_hi + (uint64_t)(DGROUP_BYTES >> 4);
+                    umma_f16(d_tmem, d_hi2, d_hi2, idesc1, 1u);
+                    if (!kSym) umma_f16(d_tmem + SCOL, d_hi2 + (uint64_t)LO_OFF16, d_hi2, idesc2, 1u);
                 }
-                umma_commit_addr(ebar + (uint32_t)slot * 8u);                // operand stage reusable once the MMAs retire
+                umma_commit_addr(empty_bar0 + (uint32_t)slot * 8u);          // operand stage reusable once the MMAs retire
                 if (m & FLAG_SUB_LAST) umma_commit_addr(acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u);   // acc_full[wg][buf]: index 2 wg + buf
             };
             auto wait_tile_free = [&](uint32_t m) {
                 if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
             };
             for (int n0 = 0; n0 < total_stages; n0 += S2) {
-                // !kDirect: 8 operand slots, one pass = one trip round the ring.  kDirect: 16 slots, passes alternate halves.
-                const uint32_t half = kDirect ? (((uint32_t)n0 / S2) & 1u) : 0u;
-                const uint32_t ph = kDirect ? (((uint32_t)n0 / DS) & 1u) : (((uint32_t)n0 / S2) & 1u);
-                const uint64_t dpass = dbase + (uint64_t)(half * (uint32_t)((S2 * OP_STAGE_BYTES) >> 4));
-                const uint32_t ebar = empty_bar0 + half * (uint32_t)(S2 * 8);
-                unsigned long long* full = &sm.full_op[half * S2];
-                const uint32_t* meta = &sm.meta_op[half * S2];
-                // two k-steps per pass: their barrier waits and flag reads overlap, one elected region issues both
+                const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
+                // two stages per pass: their barrier waits and flag reads overlap, one elected region issues both
 #pragma unroll
                 for (int slot = 0; slot < S2; slot += 2) {
                     if (n0 + slot < total_stages) {
                         const bool two = (n0 + slot + 1 < total_stages);
-                        mbar_wait(&full[slot], ph);
-                        if (two) mbar_wait(&full[slot + 1], ph);
-                        const uint32_t m0 = meta[slot];
-                        const uint32_t m1 = two ? meta[slot + 1] : 0u;
+                        mbar_wait(&sm.full_op[slot], ph);
+                        if (two) mbar_wait(&sm.full_op[slot + 1], ph);
+                        const uint32_t m0 = sm.meta_op[slot];
+                        const uint32_t m1 = two ? sm.meta_op[slot + 1] : 0u;
                         wait_tile_free(m0);
                         wait_tile_free(m1);
                         tc_fence_after();
                         if (elect_one()) {
-                            issue_step(dpass, ebar, slot, m0);
-                            if (two) issue_step(dpass, ebar, slot + 1, m1);
+                            issue_step(slot, m0);
+                            if (two) issue_step(slot + 1, m1);
                         }
                         __syncwarp();
                     }
@@ -542,7 +559,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             }
         }
     } else if (warp < FIRST_EPI_WARP) {
-        reg_dec<C::kRegsStage>();
+        reg_dec<kRegsStage>();
         if (n_chunks > 0) {
             // ============ autonomous stage workers: warp w owns stages w, w+8, w+16, ... ===========
             // own-stage t (global stage n = w + 8t) lives in fp32 slot w + 8(t&1) and operand slot w.
@@ -561,62 +578,63 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 return (lane < (int)(d.info & 0xffu)) ? __ldg(val + d.pos + lane) : 0.f;
             };
             if constexpr (kDirect) {
-                const uint32_t kg_stride = dcfg & 0xffffu, ch_stride = dcfg >> 16;
-                // arm the slot's mbarrier and launch the 16 gathers of one stage (warp-collective): lane L < 16 fetches
-                // 64-element chunk L >> 2 of rows 4 (L & 3) .. + 3 -> four consecutive 128-byte swizzle lines.  Rows past
-                // cnt carry the index of the table's all-zero row, so every stage is a full 8 KB.
-                auto issue_direct = [&](int slot, int my_idx, float my_val) {
-                    if (lane < KT) sm.stage_vals[slot][lane] = my_val;
-                    const int src = (lane & 3) * GROUP_ROWS;
+                // One ring slot per worker warp: own-stage t (global stage n = w + 8t) is use number t of slot w.
+                unsigned char* sbase = &sm.stg.direct[sw][0];
+                // arm the slot's mbarrier and launch the gathers of one stage (warp-collective): lane L fetches 64-element
+                // chunk (L >> 2) & 3 of rows 4 (L & 3) .. + 3 of k-group L >> 4 -> four consecutive 128-byte swizzle lines.
+                // Rows past cnt inside a fetched k-group carry the index of the table's all-zero row.
+                auto issue_direct = [&](const StageDesc& d, int my_idx, float my_val) {
+                    const uint32_t groups = ((d.info >> 8) & FLAG_TWO_GROUPS) ? 2u : 1u;
+                    sm.stage_vals[sw][lane] = my_val;
+                    const int src = (lane & 16) + (lane & 3) * GROUP_ROWS;
                     const int i0 = __shfl_sync(0xffffffffu, my_idx, src + 0);
                     const int i1 = __shfl_sync(0xffffffffu, my_idx, src + 1);
                     const int i2 = __shfl_sync(0xffffffffu, my_idx, src + 2);
                     const int i3 = __shfl_sync(0xffffffffu, my_idx, src + 3);
-                    if (lane == 0) mbar_arrive_expect_tx(&sm.full_f32[slot], (uint32_t)DSTAGE_BYTES);
+                    if (lane == 0) mbar_arrive_expect_tx(&sm.full_f32[sw], groups * (uint32_t)DGROUP_BYTES);
                     __syncwarp();
-                    if (lane < KT) {
-                        const uint32_t c = (uint32_t)lane >> 2, q = (uint32_t)lane & 3u;
-                        tma_gather4_col(&sm.stg.direct[slot][(q >> 1) * kg_stride + c * ch_stride + (q & 1u) * 512u], &factor_map,
-                                        (int)c * SPLIT_CHUNK, i0, i1, i2, i3, &sm.full_f32[slot]);
-                    }
+                    const uint32_t g = (uint32_t)lane >> 4, c = ((uint32_t)lane >> 2) & 3u, q = (uint32_t)lane & 3u;
+                    if (g < groups)
+                        tma_gather4_col(sbase + g * DGROUP_BYTES + (q >> 1) * D_KG_STRIDE + c * D_CHUNK_STRIDE + (q & 1u) * 512u,
+                                        &factor_map, (int)c * SPLIT_CHUNK, i0, i1, i2, i3, &sm.full_f32[sw]);
                 };
-                StageDesc d0 = load_desc(0), d1 = load_desc(1), d2 = load_desc(2), d3 = load_desc(3);
-                {
-                    const int ia = load_idx(d0); const float va = load_val(d0);
-                    const int ib = load_idx(d1); const float vb = load_val(d1);
-                    if (own > 0) issue_direct(sw, ia, va);
-                    if (own > 1) issue_direct(sw + STAGE_WARPS, ib, vb);
+                StageDesc d0 = load_desc(0), d1 = load_desc(1), d2 = load_desc(2);
+                int idx1 = load_idx(d1);
+                float val1 = load_val(d1);
+                if (own > 0) {
+                    const int ia = load_idx(d0);
+                    const float va = load_val(d0);
+                    issue_direct(d0, ia, va);
                 }
-                int idx2 = load_idx(d2);
-                float val2 = load_val(d2);
                 for (int t = 0; t < own; ++t) {
-                    // software prefetch: descriptor of t+4, indices/ratings of t+3 (consumed next iteration)
-                    const StageDesc d4 = load_desc(t + 4);
-                    const int idx3 = load_idx(d3);
-                    const float val3 = load_val(d3);
-                    const int slot = sw + STAGE_WARPS * (t & 1);
-                    const uint32_t par = ((uint32_t)t >> 1) & 1u;     // this is use number t >> 1 of the slot
-                    mbar_wait(&sm.full_f32[slot], par);               // the 16 rows have landed
-                    if (lane < KT) {
+                    // software prefetch: descriptor of t+3, indices/ratings of t+2 (consumed next iteration)
+                    const StageDesc d3 = load_desc(t + 3);
+                    const int idx2 = load_idx(d2);
+                    const float val2 = load_val(d2);
+                    const uint32_t par = (uint32_t)t & 1u;            // this is use number t of the slot
+                    const uint32_t flags = d0.info >> 8;
+                    mbar_wait(&sm.full_f32[sw], par);                 // the rows have landed
+                    if (lane < KT || (flags & FLAG_TWO_GROUPS)) {
                         // the ratings ride along as operand columns 112 (r_hi) and 113 (r_lo') of gathered row k = lane:
                         // chunk 1, element 48 -> 16-byte piece 6 of the row's 128-byte line, XOR-swizzled with the line number
-                        const float r0 = sm.stage_vals[slot][lane];
+                        const float r0 = sm.stage_vals[sw][lane];
                         const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
-                        const uint32_t k = (uint32_t)lane;
-                        unsigned char* ob = &sm.stg.direct[slot][(k >> 3) * kg_stride + ch_stride + (k & 7u) * 128u + ((6u ^ (k & 7u)) << 4)];
+                        const uint32_t k = (uint32_t)lane & 15u;
+                        unsigned char* ob = sbase + ((uint32_t)lane >> 4) * DGROUP_BYTES + (k >> 3) * D_KG_STRIDE + D_CHUNK_STRIDE +
+                                            (k & 7u) * 128u + ((6u ^ (k & 7u)) << 4);
                         *reinterpret_cast<__half2*>(ob) = __floats2half2_rn(h0, (r0 - h0) * kLoScale);
                     }
-                    if (lane == 0) sm.meta_op[slot] = d0.info >> 8;
+                    if (lane == 0) sm.meta_op[sw] = flags;
                     fence_proxy_async();                  // the generic-proxy rating writes ordered before the tensor core's reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.full_op[slot]);
-                    if (t + 2 < own) {
-                        // own-stage t+2 reuses this slot: the MMAs of stage t must have retired (tcgen05.commit -> empty_op)
-                        mbar_wait(&sm.empty_op[slot], par);
-                        issue_direct(slot, idx2, val2);
+                    if (lane == 0) mbar_arrive(&sm.full_op[sw]);
+                    if (t + 1 < own) {
+                        // own-stage t+1 reuses the slot: the MMAs of stage t must have retired (tcgen05.commit -> empty_op)
+                        mbar_wait(&sm.empty_op[sw], par);
+                        issue_direct(d1, idx1, val1);
                     }
-                    d0 = d1; d1 = d2; d2 = d3; d3 = d4;
-                    idx2 = idx3; val2 = val3;
+                    d0 = d1; d1 = d2; d2 = d3;
+                    idx1 = idx2; val1 = val2;
                 }
             } else {
             // arm the slot's mbarrier and launch the gathers of one stage (warp-collective)
@@ -745,7 +763,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             for (int c = c_begin; c < c_end; ++c) {
                 const Chunk ck = ck_next;
                 if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
-                const int tiles = (chunk_steps(ck) + SUB_STEPS - 1) / SUB_STEPS;
+                const int tiles = kDirect ? (chunk_steps<DKT>(ck) + DSUB_STEPS - 1) / DSUB_STEPS
+                                          : (chunk_steps<KT>(ck) + SUB_STEPS - 1) / SUB_STEPS;
                 if (((c - c_begin) % C::kWG) != wg) { q += tiles; continue; }
                 float a[C::kRegCols];
                 float bi = 0.f;
@@ -985,6 +1004,11 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     if (grid < 1) grid = 1;
     const int n = (int)chunks.size();
     if (grid > n) grid = std::max(1, n);
+    // staging variant: "direct" (pre-split fp16 table gathered straight into the UMMA operand, 32-rating stages) or the
+    // fp32 ring + in-kernel conversion (16-rating stages)
+    const char* denv = getenv("CUMF_TC_DIRECT");
+    const bool direct = denv && *denv == '1';
+    const int kt = direct ? DKT : KT, sub = direct ? DSUB_STEPS : SUB_STEPS;
     // contiguous, cost-balanced partition of the (row-ordered) chunk list: cost = MMA k-steps
     // plus a per-chunk epilogue/solve term, so every CTA streams one contiguous rating range.
     const char* rc_env = getenv("CUMF_TC_ROW_COST");
@@ -992,7 +1016,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     std::vector<long long> prefix(n + 1, 0);
     for (int c = 0; c < n; ++c) {
         const long long nnz = chunks[c].end - chunks[c].begin;
-        prefix[c + 1] = prefix[c] + ((nnz + KT - 1) / KT) * KT + per_chunk;
+        prefix[c + 1] = prefix[c] + ((nnz + KT - 1) / KT) * KT + per_chunk;     // MMA k-groups of 16 ratings in both stagings
     }
     std::vector<int> ptr(grid + 1, 0);
     for (int b = 1; b < grid; ++b) {
@@ -1006,7 +1030,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     std::vector<int> stage_base(n + 1, 0);
     for (int c = 0; c < n; ++c) {
         const long long nnz = chunks[c].end - chunks[c].begin;
-        const long long steps = std::max<long long>(1, (nnz + KT - 1) / KT);
+        const long long steps = std::max<long long>(1, (nnz + kt - 1) / kt);
         if (stage_base[c] + steps > 0x7fffffffLL) {
             set_last_error("tc_plan_create: too many k-steps for one shard");
             return CUMF_EINVAL;
@@ -1019,11 +1043,8 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     TcWork* w = new TcWork();
     w->grid = grid;
     w->nchunks = n;
-    {
-        const char* d = getenv("CUMF_TC_DIRECT");
-        w->direct = d && *d == '1';
-        for (int c = 0; c < n; ++c) w->idx_span = std::max<long long>(w->idx_span, chunks[c].end);
-    }
+    w->direct = direct;
+    for (int c = 0; c < n; ++c) w->idx_span = std::max<long long>(w->idx_span, chunks[c].end);
     {   // per-chunk epilogue cost (transpose) vs per-k-step MMA saving: the symmetric mode pays from ~32 k-steps per chunk;
         // measured on Netflix: X side (348 k-steps/chunk) 9.6 -> 8.6 ms, theta side (13 k-steps/chunk) 14.8 -> 16.2 ms
         const char* m = getenv("CUMF_TC_SYM");
@@ -1037,7 +1058,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
         long long tile = 0;
         for (int c = ptr[b]; c < ptr[b + 1]; ++c) {
             chunk_meta[c] = (int)(((tile & 0x1fffffffLL) << 2) | ((c - ptr[b]) % n_wg));   // only tile & 3 is consumed
-            tile += (stage_base[c + 1] - stage_base[c] + SUB_STEPS - 1) / SUB_STEPS;
+            tile += (stage_base[c + 1] - stage_base[c] + sub - 1) / sub;
         }
     }
     DevBuf& d_base = w->chunk_stage_base;
@@ -1055,8 +1076,12 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
         rc = CUMF_ECUDA;
     }
     if (rc == CUMF_OK && n > 0) {
-        fill_stage_table_kernel<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n,
-                                                          w->stage_tab.as<StageDesc>());
+        if (direct)
+            fill_stage_table_kernel<DKT, DSUB_STEPS><<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n,
+                                                                               w->stage_tab.as<StageDesc>());
+        else
+            fill_stage_table_kernel<KT, SUB_STEPS><<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n,
+                                                                             w->stage_tab.as<StageDesc>());
         if (cudaStreamSynchronize(0) != cudaSuccess) {      // not the device: uploads may be running on another stream
             set_last_error(std::string("tc_plan_create: stage table: ") + cudaGetErrorString(cudaGetLastError()));
             rc = CUMF_ECUDA;
@@ -1121,20 +1146,11 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         split_factor_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(d_factor, w->factor_rows, w->split_tab.as<uint4>());
         CUMF_CUDA_TRY(cudaGetLastError());
         *launches += 1;
-        // bring-up knobs: stage arrangement (0: k-group-major, chunks 1 KB apart; 1: chunk-major, k-groups 1 KB apart) and
-        // explicit descriptor offsets
-        const char* a = getenv("CUMF_TC_DIRECT_ARR");
-        const bool chunk_major = a && *a == '1';
-        const uint32_t kg = chunk_major ? 1024u : 4096u, ch = chunk_major ? 2048u : 1024u;
-        const char* lbo_env = getenv("CUMF_TC_DIRECT_LBO");
-        const char* sbo_env = getenv("CUMF_TC_DIRECT_SBO");
-        const int lbo = (lbo_env && *lbo_env) ? atoi(lbo_env) : (int)ch;
-        const int sbo = (sbo_env && *sbo_env) ? atoi(sbo_env) : (int)kg;
-        const uint64_t desc_tmpl = smem_desc_template_direct(lbo, sbo);
+        const uint64_t desc_tmpl = smem_desc_template_direct(D_CHUNK_STRIDE, D_KG_STRIDE);
         auto kernel = w->sym ? als_fused_f100_kernel<true, true> : als_fused_f100_kernel<false, true>;
         kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->split_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
-                                               desc_tmpl, d_sse_terms, w->factor_rows, kg | (ch << 16));
+                                               desc_tmpl, d_sse_terms, w->factor_rows);
     } else {
         if (w->mapped_factor != d_factor) {
             CUMF_TRY(encode_factor_map(&w->factor_map, d_factor));
@@ -1145,7 +1161,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         auto kernel = w->sym ? als_fused_f100_kernel<true, false> : als_fused_f100_kernel<false, false>;
         kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
-                                               desc_tmpl, d_sse_terms, 0, 0u);
+                                               desc_tmpl, d_sse_terms, 0);
     }
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;

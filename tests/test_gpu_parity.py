@@ -327,7 +327,9 @@ def test_tc_half_step_vs_simt(cuda, monkeypatch, split):
         cuda.cuda.synchronize()
         outs[name] = x.cpu().numpy()
         if name == "tc":
-            assert plan.last_launches == (1 if not split else 3)
+            # fused kernel (+ split-row reduce + CG); direct staging adds the index scan (first call) and the pre-split pass
+            base = 1 if not split else 3
+            assert plan.last_launches in (base, base + 2)
         plan.close()
     rows = np.linalg.norm(outs["tc"].astype(np.float64) - outs["simt"], axis=1) / np.linalg.norm(outs["simt"].astype(np.float64), axis=1)
     assert np.median(rows) < 1e-5 and rel_fro(outs["tc"], outs["simt"]) < TOL, (np.median(rows), rows.max())

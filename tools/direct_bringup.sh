@@ -8,25 +8,10 @@ OUT=gpurun_out/direct
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > "$OUT/gpu.txt" 2>&1
 
-echo "== probe" | tee "$OUT/probe.log"
-for v in "0" "1" "0 4096 1024" "1 1024 2048"; do
-  timeout -s KILL 60 tools/mn_major_probe $v >> "$OUT/probe.log" 2>&1
-  echo "   exit $?" >> "$OUT/probe.log"
-done
-tail -n 40 "$OUT/probe.log"
-
 echo "== bring-up (Gram parity, direct vs fp32 staging)"
 CFG=""
-for cfg in "ARR=0" "ARR=1" "ARR=0 LBO=4096 SBO=1024" "ARR=1 LBO=1024 SBO=2048"; do
-  envs="CUMF_TC_DIRECT=1"
-  for kv in $cfg; do envs="$envs CUMF_TC_DIRECT_${kv}"; done
-  echo "-- $envs" | tee -a "$OUT/bringup.log"
-  if env $envs timeout -s KILL 150 python tools/tc_bringup.py direct >> "$OUT/bringup.log" 2>&1; then
-    CFG="$envs"
-    break
-  fi
-done
-tail -n 25 "$OUT/bringup.log"
+if CUMF_TC_DIRECT=1 timeout -s KILL 150 python tools/tc_bringup.py direct > "$OUT/bringup.log" 2>&1; then CFG="CUMF_TC_DIRECT=1"; fi
+tail -n 16 "$OUT/bringup.log"
 echo "working config: ${CFG:-none}" | tee "$OUT/config.txt"
 
 echo "== bench, fp32 staging (baseline of this box)"
