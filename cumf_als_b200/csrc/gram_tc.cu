@@ -173,6 +173,7 @@ struct __align__(1024) Smem {   // dynamic shared memory, used in place (SWIZZLE
     Staging stg;
     float stage_vals[NBAR][DKT]; // the ratings of the stage in flight in each gather slot (zero beyond cnt)
     uint32_t meta_op[NBAR];      // stage flags forwarded to the MMA warp
+    __align__(16) int stage_idx[DS][DKT];   // direct staging: the column ids of the stage being fetched into each slot
     // per solver warpgroup: kSym -> TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats);
     //                        !kSym -> columns [64,100) of the 100 rows of [A] it is solving (3 x 3600 floats)
     float solver_scratch[3 * F * SM_ROW_STRIDE];
@@ -586,17 +587,29 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 auto issue_direct = [&](const StageDesc& d, int my_idx, float my_val) {
                     const uint32_t groups = ((d.info >> 8) & FLAG_TWO_GROUPS) ? 2u : 1u;
                     sm.stage_vals[sw][lane] = my_val;
-                    const int src = (lane & 16) + (lane & 3) * GROUP_ROWS;
-                    const int i0 = __shfl_sync(0xffffffffu, my_idx, src + 0);
-                    const int i1 = __shfl_sync(0xffffffffu, my_idx, src + 1);
-                    const int i2 = __shfl_sync(0xffffffffu, my_idx, src + 2);
-                    const int i3 = __shfl_sync(0xffffffffu, my_idx, src + 3);
-                    if (lane == 0) mbar_arrive_expect_tx(&sm.full_f32[sw], groups * (uint32_t)DGROUP_BYTES);
+                    sm.stage_idx[sw][lane] = my_idx;
                     __syncwarp();
-                    const uint32_t g = (uint32_t)lane >> 4, c = ((uint32_t)lane >> 2) & 3u, q = (uint32_t)lane & 3u;
-                    if (g < groups)
-                        tma_gather4_col(sbase + g * DGROUP_BYTES + (q >> 1) * D_KG_STRIDE + c * D_CHUNK_STRIDE + (q & 1u) * 512u,
-                                        &factor_map, (int)c * SPLIT_CHUNK, i0, i1, i2, i3, &sm.full_f32[sw]);
+                    // One lane issues all gathers from an unrolled loop: the four row coordinates of a quad are loaded once
+                    // (LDS.128) and reused by its four chunks, so successive UTMALDG differ only in destination and column.
+                    // (Issuing from 32 divergent lanes costs an ELECT + 6 R2UR.BROADCAST round per instruction: ~60 cycles each,
+                    // 2000 cycles per stage -- half of a worker's time in the ncu source view.)
+                    if (elect_one()) {       // elect.sync: ptxas then keeps the operands in uniform registers (no per-issue ELECT round)
+                        mbar_arrive_expect_tx(&sm.full_f32[sw], groups * (uint32_t)DGROUP_BYTES);
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            if ((uint32_t)g < groups) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int4 ix = *reinterpret_cast<const int4*>(&sm.stage_idx[sw][g * KT + q * GROUP_ROWS]);
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c)
+                                        tma_gather4_col(sbase + g * DGROUP_BYTES + (q >> 1) * D_KG_STRIDE + c * D_CHUNK_STRIDE + (q & 1) * 512,
+                                                        &factor_map, c * SPLIT_CHUNK, ix.x, ix.y, ix.z, ix.w, &sm.full_f32[sw]);
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
                 };
                 StageDesc d0 = load_desc(0), d1 = load_desc(1), d2 = load_desc(2);
                 int idx1 = load_idx(d1);
