@@ -68,27 +68,34 @@ constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B)
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
 constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 8192
 constexpr int MMA_WARP = 3;
-constexpr int FIRST_STAGE_WARP = 4;       // warps 4..11 stage operands
-constexpr int STAGE_WARPS = 8;
-static_assert(S1 % STAGE_WARPS == 0 && STAGE_WARPS == S2, "every ring slot has exactly one staging warp as its consumer / producer");
-constexpr int FIRST_EPI_WARP = 12;        // warps 12..15 and 16..19: epilogue + solver warpgroups
-// setmaxnreg budgets per warpgroup.  The CTA's register pool is what the launch allocated:
-// 640 threads x 96 registers = 61440, so the budgets must satisfy 128*(P + 2S + 2E) <= 61440.
-// Shape of the CTA.  The solver side is parametrised (number of solver warpgroups, how many columns of row i stay in
-// registers vs. the thread's shared-memory row) because a 3-warpgroup / 64-register-column shape was tried for the
-// short-row launches, where the in-kernel CG costs 4 of 14 ms (tools/cg_share.py): it was slower (theta side 16.3 ms
-// instead of 14.0) -- the CG is not latency-bound but shares the shared-memory pipe with the staging and the MMA
-// operand reads, and coefficients in shared memory add to exactly that.  Both launches therefore use 2 warpgroups with
-// the whole row in registers; the parameters stay for the next attempt (profiles/README.md).
-template <bool kSym> struct Cfg {
-    static constexpr int kWG = 2;                                  // solver warpgroups
-    static constexpr int kRegCols = F;                             // columns of row i held in registers
-    static constexpr int kSmemCols = F - kRegCols;                 // columns of row i held in shared memory
-    static constexpr int kThreads = (12 + 4 * kWG) * 32;           // 640
-    static constexpr int kRegsLaunch = 96;
-    static constexpr int kRegsProd = 48, kRegsStage = 64, kRegsEpi = 152;
-    static_assert(128 * (kRegsProd + 2 * kRegsStage + kWG * kRegsEpi) <= kThreads * kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
+constexpr int REG_COLS = F;               // columns of row i of [A] a solver thread holds in registers (all of them)
+// Shape of the CTA (20 or 16 warps; the roles are fixed per warp, the setmaxnreg budgets per warpgroup).  The register
+// pool is what the launch allocated (threads x launch registers), the budgets must fit into it.
+//   fp32 staging, and direct staging for long rows (kSym):  warps 0-2 idle | 3 MMA issuer | 4-11 stage workers | 12-19 two
+//     solver warpgroups; 640 threads x 96 registers = 61440 >= 128 (P + 2 S + 2 E).
+//   direct staging for short rows (!kSym, "wide"): the launch is bound by the per-row drain + CG (ncu: the solver
+//     warpgroups are 85 % busy, the issuer waits for free TMEM tiles), and the direct workers only issue gathers, so
+//     three of them share the issuer's warpgroup and a THIRD solver warpgroup takes their place:
+//     warps 0-2 stage workers (4 ring slots each) | 3 MMA issuer | 4-15 three solver warpgroups;
+//     512 threads x 128 registers = 65536 = 128 (56 + 3 x 152).
+// (An earlier 3-warpgroup shape that kept columns [64,100) of every row in shared memory to fit the register file was
+// slower -- the CG shares the shared-memory pipe with staging and operand reads; here every row stays in registers.)
+template <bool kSym, bool kDirect> struct Cfg {
+    static constexpr bool kWide = kDirect && !kSym;
+    static constexpr int kWG = kWide ? 3 : 2;                      // solver warpgroups
+    static constexpr int kFirstWorker = kWide ? 0 : 4;
+    static constexpr int kWorkers = kWide ? 3 : 8;                 // stage worker warps
+    static constexpr int kSlotsPerWorker = kWide ? 4 : 1;          // direct ring: slots owned by one worker
+    static constexpr int kSlots = kWorkers * kSlotsPerWorker;      // direct ring depth (stages of 32 ratings)
+    static constexpr int kFirstEpiWarp = kWide ? 4 : 12;
+    static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;          // 640 / 512
+    static constexpr int kRegsLaunch = kWide ? 128 : 96;
+    static constexpr int kRegsProd = kWide ? 56 : (kDirect ? 80 : 48);       // warpgroup 0 (issuer; + the workers if kWide)
+    static constexpr int kRegsStage = kDirect ? 48 : 64;                     // warpgroups 1, 2 (workers; absent if kWide)
+    static constexpr int kRegsEpi = 152;
+    static_assert(128 * (kRegsProd + (kWide ? 0 : 2 * kRegsStage) + kWG * kRegsEpi) <= kThreads * kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
     static_assert(kThreads * kRegsLaunch <= 65536, "launch registers");
+    static_assert(!kDirect || kSlots <= 16, "ring barriers");
 };
 constexpr int MAX_WG = 3;
 constexpr int SM_ROW_STRIDE = 36;         // floats per row of the shared-memory part: 36 = 4 (mod 32) keeps LDS.128 conflict-free
@@ -159,36 +166,37 @@ struct StageDesc {
 };
 static_assert(sizeof(StageDesc) == 8, "StageDesc is loaded as one 8-byte word");
 
-struct ConvStaging {
-    unsigned char f32_stage[S1][STAGE_F32_BYTES];   // 106496
-    unsigned char op_stage[S2][OP_STAGE_BYTES];     // 65536
-};
-union Staging {
-    ConvStaging conv;                               // !kDirect: fp32 gather ring + converted fp16 operand ring
-    unsigned char direct[DS][DSTAGE_BYTES];         // kDirect: one ring, TMA destination == UMMA operand (131072)
-};
-constexpr int NBAR = S1;                  // stage barriers / metadata slots (the larger of the rings)
-static_assert(NBAR >= DS && NBAR >= S2, "barrier / metadata arrays cover every ring");
-struct __align__(1024) Smem {   // dynamic shared memory, used in place (SWIZZLE_128B atoms need 1024-byte alignment)
-    Staging stg;
+// fp32 staging: fp32 gather ring (S1 x 6.5 KB) followed by the converted fp16 operand ring (S2 x 8 KB)
+constexpr int CONV_RING_BYTES = S1 * STAGE_F32_BYTES + S2 * OP_STAGE_BYTES;     // 172032
+constexpr int NBAR = 16;                  // stage barriers / metadata slots (the largest ring)
+static_assert(NBAR >= S1 && NBAR >= S2, "barrier / metadata arrays cover every ring");
+// dynamic shared memory, used in place (SWIZZLE_128B atoms need 1024-byte alignment)
+template <int kRingBytes, int kScratchFloats> struct __align__(1024) SmemT {
+    unsigned char ring[kRingBytes];   // kDirect: kSlots x 16 KB, TMA destination == UMMA operand; else the two rings above
     float stage_vals[NBAR][DKT]; // the ratings of the stage in flight in each gather slot (zero beyond cnt)
     uint32_t meta_op[NBAR];      // stage flags forwarded to the MMA warp
-    __align__(16) int stage_idx[DS][DKT];   // direct staging: the column ids of the stage being fetched into each slot
-    // per solver warpgroup: kSym -> TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats);
-    //                        !kSym -> columns [64,100) of the 100 rows of [A] it is solving (3 x 3600 floats)
-    float solver_scratch[3 * F * SM_ROW_STRIDE];
+    __align__(16) int stage_idx[NBAR][DKT];   // direct staging: the column ids of the stage being fetched into each slot
+    // per solver warpgroup, kSym only: TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats)
+    float solver_scratch[kScratchFloats];
     float sp[MAX_WG][2][128];    // CG direction vector per solver warpgroup, double buffered
     float red[MAX_WG][3][4];     // cross-warp partial sums
     unsigned long long full_f32[NBAR], full_op[NBAR], empty_op[NBAR];
     // acc_full[w][buf]: tile in TMEM buffer `buf` complete, for solver warpgroup w.  One barrier per
-    // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the two
+    // (consumer, buffer): a parity wait is only sound if its waiter observes every phase, and the
     // warpgroups take turns irregularly on the buffers (tiles per chunk vary).
     unsigned long long acc_full[MAX_WG][2], acc_empty[2];
     uint32_t tmem_base;
+    __device__ __forceinline__ unsigned char* f32_stage(int slot) { return ring + slot * STAGE_F32_BYTES; }
+    __device__ __forceinline__ unsigned char* op_stage(int slot) { return ring + S1 * STAGE_F32_BYTES + slot * OP_STAGE_BYTES; }
+    __device__ __forceinline__ unsigned char* dstage(int slot) { return ring + slot * DSTAGE_BYTES; }
 };
-
-static_assert(3 * F * SM_ROW_STRIDE >= 2 * (TR_ROWS + 1) * F, "solver_scratch holds either use");
-static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt into");
+template <bool kSym, bool kDirect> struct SmemFor {
+    using C = Cfg<kSym, kDirect>;
+    static constexpr int kRing = kDirect ? C::kSlots * DSTAGE_BYTES : CONV_RING_BYTES;
+    static constexpr int kScratch = kSym ? 2 * (TR_ROWS + 1) * F : 4;
+    using type = SmemT<kRing, kScratch>;
+    static_assert(sizeof(type) <= 232448, "Smem exceeds the 227 KB a CTA can opt into");
+};
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -315,9 +323,9 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 //   kSym:  G = P/2 + S/2048 and its rating column (symmetrised later);   !kSym:  [A|b] = P + S/2048 directly.
 // Columns [0, kRegCols) live in registers, the rest in the thread's own shared-memory row `arow` (!kSym only).
 template <bool kFirst, bool kSym>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[Cfg<kSym>::kRegCols], float& b, float* arow, bool active) {
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[REG_COLS], float& b, float* arow, bool active) {
     constexpr float kP = kSym ? 0.5f : 1.0f;
-    constexpr int RC = Cfg<kSym>::kRegCols;
+    constexpr int RC = REG_COLS;
     constexpr int RC16 = (RC / 16) * 16;        // 96 (all in registers) or 64
     static_assert(RC == F || RC == RC16, "register part ends on a 16-column boundary");
 #pragma unroll
@@ -447,7 +455,7 @@ __global__ void max_index_kernel(const int* __restrict__ idx, long long n, int* 
 // kDirect: `factor_map` describes the pre-split fp16 table (box {64, 1}, SWIZZLE_128B), `zero_row` is the index of its
 // all-zero row (the padding of ragged k-groups).
 template <bool kSym, bool kDirect>
-__global__ void __launch_bounds__(Cfg<kSym>::kThreads, 1)
+__global__ void __launch_bounds__(Cfg<kSym, kDirect>::kThreads, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
@@ -457,9 +465,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
+    using C = Cfg<kSym, kDirect>;
+    using Smem = typename SmemFor<kSym, kDirect>::type;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
-    using C = Cfg<kSym>;
     constexpr int NUM_THREADS = C::kThreads;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -472,7 +481,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     // TMA destinations need 128 B, UMMA descriptors 16 B, SWIZZLE_128B atoms 1024 B
     if ((smem_u32(smem_raw) & (kDirect ? 1023u : 127u)) != 0u) __trap();
     if constexpr (!kDirect) {   // zero the operand ring: padded feature rows and the spare rows stay zero for ever
-        uint4* p = reinterpret_cast<uint4*>(&sm.stg.conv.op_stage[0][0]);
+        uint4* p = reinterpret_cast<uint4*>(sm.op_stage(0));
         for (int i = tid; i < S2 * OP_STAGE_BYTES / 16; i += NUM_THREADS) p[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
@@ -490,14 +499,12 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 
-    // register budget per warpgroup (see REGS_*: the increases below block until the decreases freed enough).
-    // Direct staging: the workers only issue gathers (48 registers), the issuer keeps the descriptors of its 8 x 4 MMAs
-    // per ring trip in registers (80) -- with 48 ptxas spills them into the loop that bounds the kernel.
-    constexpr int kRegsProd = kDirect ? 80 : C::kRegsProd, kRegsStage = kDirect ? 48 : C::kRegsStage;
-    static_assert(128 * (kRegsProd + 2 * kRegsStage + C::kWG * C::kRegsEpi) <= C::kThreads * C::kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
-    if (warp < 4) {
-        reg_dec<kRegsProd>();
-        if (n_chunks > 0 && warp == MMA_WARP) {
+    // register budget per warpgroup (Cfg: the increases below block until the decreases freed enough)
+    if (warp < C::kFirstEpiWarp) {
+        if (warp < 4) reg_dec<C::kRegsProd>(); else reg_dec<C::kRegsStage>();
+    }
+    if (warp == MMA_WARP) {
+        if (n_chunks > 0) {
             // ================================ MMA issuer ========================================
             // The whole warp runs the loop (uniform control flow: waits, flag reads, bookkeeping stay off the
             // divergent path); one elected lane issues the tcgen05 instructions.  The loop is unrolled over
@@ -507,8 +514,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             constexpr int STAGE_BYTES = kDirect ? DSTAGE_BYTES : OP_STAGE_BYTES;
             // operand rows 128.. (lo' | 0): 16 eight-row groups further (K-major), or two 64-element chunks further (direct)
             constexpr uint32_t LO_OFF16 = (uint32_t)((kDirect ? 2 * D_CHUNK_STRIDE : (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);
-            static_assert(DS == S2, "both rings have one slot per stage-worker warp: the 8-slot unrolled loop serves both");
-            const uint32_t op_base0 = kDirect ? smem_u32(&sm.stg.direct[0][0]) : smem_u32(&sm.stg.conv.op_stage[0][0]);
+            const uint32_t op_base0 = kDirect ? smem_u32(sm.dstage(0)) : smem_u32(sm.op_stage(0));
             const uint64_t dbase = make_smem_desc(op_base0, desc_tmpl);     // descriptor of slot 0, row 0
             // this warp's own copy of the TMEM base: the kernel-wide value is spilled around the role branches, and a local
             // memory reload inside the elected region sits on the critical path of every pass
@@ -536,37 +542,54 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             auto wait_tile_free = [&](uint32_t m) {
                 if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
             };
-            for (int n0 = 0; n0 < total_stages; n0 += S2) {
-                const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
-                // two stages per pass: their barrier waits and flag reads overlap, one elected region issues both
+            if constexpr (!C::kWide) {
+                // 8 operand slots, the loop is unrolled over them so every shared-memory descriptor is base + constant
+                static_assert(C::kWide || !kDirect || C::kSlots == S2, "the unrolled loop serves 8-slot rings");
+                for (int n0 = 0; n0 < total_stages; n0 += S2) {
+                    const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
+                    // two stages per pass: their barrier waits and flag reads overlap, one elected region issues both
 #pragma unroll
-                for (int slot = 0; slot < S2; slot += 2) {
-                    if (n0 + slot < total_stages) {
-                        const bool two = (n0 + slot + 1 < total_stages);
-                        mbar_wait(&sm.full_op[slot], ph);
-                        if (two) mbar_wait(&sm.full_op[slot + 1], ph);
-                        const uint32_t m0 = sm.meta_op[slot];
-                        const uint32_t m1 = two ? sm.meta_op[slot + 1] : 0u;
-                        wait_tile_free(m0);
-                        wait_tile_free(m1);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            issue_step(slot, m0);
-                            if (two) issue_step(slot + 1, m1);
+                    for (int slot = 0; slot < S2; slot += 2) {
+                        if (n0 + slot < total_stages) {
+                            const bool two = (n0 + slot + 1 < total_stages);
+                            mbar_wait(&sm.full_op[slot], ph);
+                            if (two) mbar_wait(&sm.full_op[slot + 1], ph);
+                            const uint32_t m0 = sm.meta_op[slot];
+                            const uint32_t m1 = two ? sm.meta_op[slot + 1] : 0u;
+                            wait_tile_free(m0);
+                            wait_tile_free(m1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                issue_step(slot, m0);
+                                if (two) issue_step(slot + 1, m1);
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
+                }
+            } else {
+                // short rows: the solver warpgroups bound the launch, not this warp -- a plain loop over a 12-slot ring
+                int slot = 0;
+                uint32_t ph = 0;
+                for (int n = 0; n < total_stages; ++n) {
+                    mbar_wait(&sm.full_op[slot], ph);
+                    const uint32_t m = sm.meta_op[slot];
+                    wait_tile_free(m);
+                    tc_fence_after();
+                    if (elect_one()) issue_step(slot, m);
+                    __syncwarp();
+                    if (++slot == C::kSlots) { slot = 0; ph ^= 1u; }
                 }
             }
         }
-    } else if (warp < FIRST_EPI_WARP) {
-        reg_dec<kRegsStage>();
+    } else if (warp >= C::kFirstWorker && warp < C::kFirstWorker + C::kWorkers) {
         if (n_chunks > 0) {
             // ============ autonomous stage workers: warp w owns stages w, w+8, w+16, ... ===========
             // own-stage t (global stage n = w + 8t) lives in fp32 slot w + 8(t&1) and operand slot w.
             // kDirect: one ring; own-stage t lives in slot w + 8(t&1), which is also the MMA operand.
-            const int sw = warp - FIRST_STAGE_WARP;
-            [[maybe_unused]] unsigned char* obase = &sm.stg.conv.op_stage[sw][0];
+            constexpr int STAGE_WARPS = C::kWorkers;
+            const int sw = warp - C::kFirstWorker;
+            [[maybe_unused]] unsigned char* obase = sm.op_stage(sw);
             const int own = (total_stages > sw) ? (total_stages - sw + STAGE_WARPS - 1) / STAGE_WARPS : 0;
             auto load_desc = [&](int t) -> StageDesc {
                 return (t < own) ? stage_tab[s_begin + sw + STAGE_WARPS * t] : StageDesc{0, 0u};
@@ -579,75 +602,83 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 return (lane < (int)(d.info & 0xffu)) ? __ldg(val + d.pos + lane) : 0.f;
             };
             if constexpr (kDirect) {
-                // One ring slot per worker warp: own-stage t (global stage n = w + 8t) is use number t of slot w.
-                unsigned char* sbase = &sm.stg.direct[sw][0];
-                // arm the slot's mbarrier and launch the gathers of one stage (warp-collective): lane L fetches 64-element
-                // chunk (L >> 2) & 3 of rows 4 (L & 3) .. + 3 of k-group L >> 4 -> four consecutive 128-byte swizzle lines.
-                // Rows past cnt inside a fetched k-group carry the index of the table's all-zero row.
-                auto issue_direct = [&](const StageDesc& d, int my_idx, float my_val) {
-                    const uint32_t groups = ((d.info >> 8) & FLAG_TWO_GROUPS) ? 2u : 1u;
-                    sm.stage_vals[sw][lane] = my_val;
-                    sm.stage_idx[sw][lane] = my_idx;
+                // Worker w owns ring slots w + W j (j < R): own-stage t (global stage n = w + W t) lives in slot n mod (W R) =
+                // w + W (t mod R) and is use number t / R of that slot -- every barrier has one producer and one consumer.
+                constexpr int R = C::kSlotsPerWorker;
+                // arm the slot's mbarrier and launch the gathers of one stage (warp-collective).  Rows past cnt inside a
+                // fetched k-group carry the index of the table's all-zero row; a stage of <= 16 ratings fetches one k-group.
+                auto issue_direct = [&](int slot, uint32_t flags, int my_idx, float my_val) {
+                    const uint32_t groups = (flags & FLAG_TWO_GROUPS) ? 2u : 1u;
+                    unsigned char* sbase = sm.dstage(slot);
+                    sm.stage_vals[slot][lane] = my_val;
+                    sm.stage_idx[slot][lane] = my_idx;
+                    if (lane == 0) sm.meta_op[slot] = flags;      // the issuer reads it after this stage's full_op arrive
                     __syncwarp();
                     // One lane issues all gathers from an unrolled loop: the four row coordinates of a quad are loaded once
-                    // (LDS.128) and reused by its four chunks, so successive UTMALDG differ only in destination and column.
-                    // (Issuing from 32 divergent lanes costs an ELECT + 6 R2UR.BROADCAST round per instruction: ~60 cycles each,
-                    // 2000 cycles per stage -- half of a worker's time in the ncu source view.)
-                    if (elect_one()) {       // elect.sync: ptxas then keeps the operands in uniform registers (no per-issue ELECT round)
-                        mbar_arrive_expect_tx(&sm.full_f32[sw], groups * (uint32_t)DGROUP_BYTES);
+                    // (LDS.128) and reused by its four 64-element chunks, so successive UTMALDG differ only in destination and
+                    // column.  (Issuing from 32 divergent lanes costs an ELECT + 6 R2UR.BROADCAST round per instruction: ~60
+                    // cycles each, half of a worker's time in the ncu source view.)  elect.sync, not `lane == 0`: ptxas then
+                    // keeps the operands in uniform registers.
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&sm.full_f32[slot], groups * (uint32_t)DGROUP_BYTES);
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
                             if ((uint32_t)g < groups) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
-                                    const int4 ix = *reinterpret_cast<const int4*>(&sm.stage_idx[sw][g * KT + q * GROUP_ROWS]);
+                                    const int4 ix = *reinterpret_cast<const int4*>(&sm.stage_idx[slot][g * KT + q * GROUP_ROWS]);
 #pragma unroll
                                     for (int c = 0; c < 4; ++c)
                                         tma_gather4_col(sbase + g * DGROUP_BYTES + (q >> 1) * D_KG_STRIDE + c * D_CHUNK_STRIDE + (q & 1) * 512,
-                                                        &factor_map, c * SPLIT_CHUNK, ix.x, ix.y, ix.z, ix.w, &sm.full_f32[sw]);
+                                                        &factor_map, c * SPLIT_CHUNK, ix.x, ix.y, ix.z, ix.w, &sm.full_f32[slot]);
                                 }
                             }
                         }
                     }
                     __syncwarp();
                 };
-                StageDesc d0 = load_desc(0), d1 = load_desc(1), d2 = load_desc(2);
-                int idx1 = load_idx(d1);
-                float val1 = load_val(d1);
-                if (own > 0) {
-                    const int ia = load_idx(d0);
-                    const float va = load_val(d0);
-                    issue_direct(d0, ia, va);
+                // prologue: own-stages 0 .. R-1 into their (free) slots
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    if (j < own) {
+                        const StageDesc d = load_desc(j);
+                        const int ia = load_idx(d);
+                        const float va = load_val(d);
+                        issue_direct(sw + STAGE_WARPS * j, d.info >> 8, ia, va);
+                    }
                 }
+                StageDesc dn = load_desc(R);              // descriptor of the stage the next refill fetches
+                int slot_j = 0;                           // t mod R
+                uint32_t par = 0;                         // (t / R) & 1
                 for (int t = 0; t < own; ++t) {
-                    // software prefetch: descriptor of t+3, indices/ratings of t+2 (consumed next iteration)
-                    const StageDesc d3 = load_desc(t + 3);
-                    const int idx2 = load_idx(d2);
-                    const float val2 = load_val(d2);
-                    const uint32_t par = (uint32_t)t & 1u;            // this is use number t of the slot
-                    const uint32_t flags = d0.info >> 8;
-                    mbar_wait(&sm.full_f32[sw], par);                 // the rows have landed
+                    // software prefetch: descriptor of own-stage t+R+1, indices/ratings of t+R (consumed after the waits below)
+                    const StageDesc dcur = dn;
+                    dn = load_desc(t + R + 1);
+                    const int nidx = load_idx(dcur);
+                    const float nval = load_val(dcur);
+                    const int slot = sw + STAGE_WARPS * slot_j;
+                    unsigned char* sbase = sm.dstage(slot);
+                    mbar_wait(&sm.full_f32[slot], par);               // the rows have landed
+                    const uint32_t flags = sm.meta_op[slot];          // this warp's own write at issue time
                     if (lane < KT || (flags & FLAG_TWO_GROUPS)) {
                         // the ratings ride along as operand columns 112 (r_hi) and 113 (r_lo') of gathered row k = lane:
                         // chunk 1, element 48 -> 16-byte piece 6 of the row's 128-byte line, XOR-swizzled with the line number
-                        const float r0 = sm.stage_vals[sw][lane];
+                        const float r0 = sm.stage_vals[slot][lane];
                         const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
                         const uint32_t k = (uint32_t)lane & 15u;
                         unsigned char* ob = sbase + ((uint32_t)lane >> 4) * DGROUP_BYTES + (k >> 3) * D_KG_STRIDE + D_CHUNK_STRIDE +
                                             (k & 7u) * 128u + ((6u ^ (k & 7u)) << 4);
                         *reinterpret_cast<__half2*>(ob) = __floats2half2_rn(h0, (r0 - h0) * kLoScale);
                     }
-                    if (lane == 0) sm.meta_op[sw] = flags;
                     fence_proxy_async();                  // the generic-proxy rating writes ordered before the tensor core's reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.full_op[sw]);
-                    if (t + 1 < own) {
-                        // own-stage t+1 reuses the slot: the MMAs of stage t must have retired (tcgen05.commit -> empty_op)
-                        mbar_wait(&sm.empty_op[sw], par);
-                        issue_direct(d1, idx1, val1);
+                    if (lane == 0) mbar_arrive(&sm.full_op[slot]);
+                    if (t + R < own) {
+                        // own-stage t+R reuses the slot: the MMAs of stage t must have retired (tcgen05.commit -> empty_op)
+                        mbar_wait(&sm.empty_op[slot], par);
+                        issue_direct(slot, dcur.info >> 8, nidx, nval);
                     }
-                    d0 = d1; d1 = d2; d2 = d3;
-                    idx1 = idx2; val1 = val2;
+                    if (++slot_j == R) { slot_j = 0; par ^= 1u; }
                 }
             } else {
             // arm the slot's mbarrier and launch the gathers of one stage (warp-collective)
@@ -664,7 +695,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     mbar_arrive_expect_tx(&sm.full_f32[fs], (uint32_t)((cnt + GROUP_ROWS - 1) / GROUP_ROWS) * GROUP_ROWS * ROW_BYTES);
                 __syncwarp();
                 if (lane < KT / GROUP_ROWS && lane * GROUP_ROWS < cnt)
-                    tma_gather4(&sm.stg.conv.f32_stage[fs][lane * GROUP_BYTES], &factor_map, i0, i1, i2, i3, &sm.full_f32[fs]);
+                    tma_gather4(sm.f32_stage(fs) + lane * GROUP_BYTES, &factor_map, i0, i1, i2, i3, &sm.full_f32[fs]);
             };
 
             // prologue: descriptors of own-stages 0..3, gathers of 0 and 1 in flight, indices of 2 ready
@@ -687,7 +718,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const int fs = sw + STAGE_WARPS * (t & 1);
                 const uint32_t cnt = d0.info & 0xffu;
                 const uint32_t flags = d0.info >> 8;
-                const unsigned char* fbase = &sm.stg.conv.f32_stage[fs][0];
+                const unsigned char* fbase = sm.f32_stage(fs);
                 mbar_wait(&sm.full_f32[fs], ((uint32_t)t >> 1) & 1u);
                 mbar_wait(&sm.empty_op[sw], ((uint32_t)t & 1u) ^ 1u);
                 if (cnt < KT) {
@@ -756,11 +787,11 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             }
             }   // !kDirect
         }
-    } else {
+    } else if (warp >= C::kFirstEpiWarp) {
         reg_inc<C::kRegsEpi>();
         if (n_chunks > 0) {
             // ========================= epilogue + solver warpgroups =============================
-            const int wg = (warp - FIRST_EPI_WARP) >> 2;  // this warpgroup takes chunks with (index % kWG) == wg
+            const int wg = (warp - C::kFirstEpiWarp) >> 2;  // this warpgroup takes chunks with (index % kWG) == wg
             const int quad = warp & 3;                    // TMEM lane quadrant this warp may read (warp id % 4)
             const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
             const bool active = i < F;
@@ -779,7 +810,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 const int tiles = kDirect ? (chunk_steps<DKT>(ck) + DSUB_STEPS - 1) / DSUB_STEPS
                                           : (chunk_steps<KT>(ck) + SUB_STEPS - 1) / SUB_STEPS;
                 if (((c - c_begin) % C::kWG) != wg) { q += tiles; continue; }
-                float a[C::kRegCols];
+                float a[REG_COLS];
                 float bi = 0.f;
                 // warm start x_u (cg.cu:47): requested before the tile waits so its latency is hidden behind them
                 float* xrow = out + (size_t)ck.row * F;
@@ -837,9 +868,9 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     if (active) {
                         float4* dst = reinterpret_cast<float4*>(scratchA + (size_t)ck.slot * F * F + (size_t)i * F);
 #pragma unroll
-                        for (int j = 0; j < C::kRegCols; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+                        for (int j = 0; j < REG_COLS; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
 #pragma unroll
-                        for (int j = 0; j < C::kSmemCols; j += 4) dst[(C::kRegCols + j) >> 2] = *reinterpret_cast<const float4*>(arow + j);
+                        for (int j = 0; j < (F - REG_COLS); j += 4) dst[(REG_COLS + j) >> 2] = *reinterpret_cast<const float4*>(arow + j);
                         scratchB[(size_t)ck.slot * F + i] = bi;
                     }
                     continue;
@@ -852,15 +883,15 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 auto spmv = [&](const float* sp, float self) -> float {   // four independent FMA chains, summed pairwise
                     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < C::kRegCols; j += 4) {
+                    for (int j = 0; j < REG_COLS; j += 4) {
                         const float4 pv = *reinterpret_cast<const float4*>(sp + j);
                         y0 = fmaf(a[j], pv.x, y0); y1 = fmaf(a[j + 1], pv.y, y1);
                         y2 = fmaf(a[j + 2], pv.z, y2); y3 = fmaf(a[j + 3], pv.w, y3);
                     }
 #pragma unroll
-                    for (int j = 0; j < C::kSmemCols; j += 4) {     // same chains, coefficients from this thread's smem row
+                    for (int j = 0; j < (F - REG_COLS); j += 4) {     // same chains, coefficients from this thread's smem row
                         const float4 av = *reinterpret_cast<const float4*>(arow + j);
-                        const float4 pv = *reinterpret_cast<const float4*>(sp + C::kRegCols + j);
+                        const float4 pv = *reinterpret_cast<const float4*>(sp + REG_COLS + j);
                         y0 = fmaf(av.x, pv.x, y0); y1 = fmaf(av.y, pv.y, y1);
                         y2 = fmaf(av.z, pv.z, y2); y3 = fmaf(av.w, pv.w, y3);
                     }
@@ -1066,7 +1097,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     }
     // what the MMA issuer would otherwise count: first tile of every chunk within its CTA, chunk parity within its CTA
     std::vector<int> chunk_meta(std::max(n, 1), 0);
-    const int n_wg = w->sym ? Cfg<true>::kWG : Cfg<false>::kWG;
+    const int n_wg = w->sym ? (direct ? Cfg<true, true>::kWG : Cfg<true, false>::kWG) : (direct ? Cfg<false, true>::kWG : Cfg<false, false>::kWG);
     for (int b = 0; b < grid; ++b) {
         long long tile = 0;
         for (int c = ptr[b]; c < ptr[b + 1]; ++c) {
@@ -1125,17 +1156,15 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         return CUMF_EINVAL;
     }
     if (nchunks == 0) return CUMF_OK;
-    const size_t smem = sizeof(Smem);
     static bool attr_set = false;
     if (!attr_set) {
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<true, false>::type)));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<false, false>::type)));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<true, true>::type)));
+        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<false, true>::type)));
         attr_set = true;
     }
     CUMF_REQUIRE((reinterpret_cast<uintptr_t>(d_factor) & 15u) == 0, "the factor matrix must be 16-byte aligned for TMA");
-    const int threads = w->sym ? Cfg<true>::kThreads : Cfg<false>::kThreads;
     if (w->direct) {
         // rows of the opposing factor the plan can gather = largest column id + 1 (one scan per plan and index array)
         if (w->scanned_colidx != d_colidx) {
@@ -1161,6 +1190,8 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         *launches += 1;
         const uint64_t desc_tmpl = smem_desc_template_direct(D_CHUNK_STRIDE, D_KG_STRIDE);
         auto kernel = w->sym ? als_fused_f100_kernel<true, true> : als_fused_f100_kernel<false, true>;
+        const int threads = w->sym ? Cfg<true, true>::kThreads : Cfg<false, true>::kThreads;
+        const size_t smem = w->sym ? sizeof(SmemFor<true, true>::type) : sizeof(SmemFor<false, true>::type);
         kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->split_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
                                                desc_tmpl, d_sse_terms, w->factor_rows);
@@ -1172,6 +1203,8 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
         const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
         auto kernel = w->sym ? als_fused_f100_kernel<true, false> : als_fused_f100_kernel<false, false>;
+        const int threads = w->sym ? Cfg<true, false>::kThreads : Cfg<false, false>::kThreads;
+        const size_t smem = w->sym ? sizeof(SmemFor<true, false>::type) : sizeof(SmemFor<false, false>::type);
         kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
                                                desc_tmpl, d_sse_terms, 0);
