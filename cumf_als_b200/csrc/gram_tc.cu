@@ -210,18 +210,28 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Watchdog: a protocol error (or a fault in another role's warp) must not leave the GPU spinning for ever -- after
-// 2^24 unsuccessful polls (>= 0.3 s; a healthy wait is microseconds) the CTA traps and the launch fails loudly.
+// Waiting warps must not spin: a polling loop is ready to issue most of the time and takes issue slots from the warps of
+// its scheduler that have work (the MMA issuer shares its SM sub-partition with two solver warps and two stage workers
+// that mostly wait; in the ncu source view a fifth of all issued instructions were wait-loop polls).  try_wait with a
+// suspend-time hint parks the warp in hardware until the phase completes or the hint (in ns) expires.
+// Watchdog: a protocol error (or a fault in another role's warp) must not leave the GPU waiting for ever -- after
+// ~4 s (2^33 SM cycles; a healthy wait is microseconds) the CTA traps and the launch fails loudly.
+constexpr uint32_t kWaitHintNs = 100000u;
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    uint32_t done, polls = 0;
+    uint32_t done;
+    long long t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (!done && ++polls > (1u << 24)) __trap();
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(kWaitHintNs) : "memory");
+        if (!done) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > (1ll << 33)) __trap();
+        }
     } while (!done);
 }
 // TMA tile::gather4: four rows (row coordinates r0..r3, column coordinate 0) of the 2-D tensor described
