@@ -109,7 +109,6 @@ constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated i
 // A direct stage holds 32 ratings = two 16-row MMA k-groups: one barrier round trip, one flag word and one commit of the
 // MMA-issuing warp (whose instruction stream bounds long rows) per 32 ratings instead of per 16.
 constexpr int DKT = 32;                   // ratings per direct stage
-constexpr int DS = 8;                     // direct stage ring depth: one slot per stage-worker warp
 constexpr int SPLIT_COLS = 256;           // fp16 elements per row of the pre-split table
 constexpr int SPLIT_ROW_BYTES = SPLIT_COLS * 2;
 constexpr int SPLIT_CHUNK = 64;           // elements per 128-byte swizzle line
@@ -157,6 +156,9 @@ constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST =
 //   bit 8  (direct stages) the stage holds more than 16 ratings: its second MMA k-group is fetched and issued
 constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 7;
 constexpr uint32_t FLAG_TWO_GROUPS = 256u;
+// StageDesc::info of the first stage of a tile additionally carries (bits above the flags):
+constexpr int TILE_STAGES_SHIFT = 20;             // bits 20-24: stages in the tile (1 .. 16)
+constexpr uint32_t TILE_LAST_TWO = 1u << 25;      // the tile's last stage holds more than 16 ratings
 
 // One k-step of work: 16 (or fewer) consecutive ratings of one chunk.  Precomputed per plan
 // (stage table), so every stage worker warp is autonomous.
@@ -419,7 +421,16 @@ __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const 
                                ((tile & 1u) << FLAG_BUF_SHIFT) | (wg << FLAG_WG_SHIFT) |
                                ((((tile >> 1) & 1u) ^ 1u) << FLAG_EMPTY_PARITY_SHIFT) |
                                (cnt > KT ? FLAG_TWO_GROUPS : 0u);
-        out[s] = StageDesc{pos, (uint32_t)cnt | (flags << 8)};
+        uint32_t tile_bits = 0;
+        if ((s % kSub) == 0) {
+            // first stage of a TMEM tile: what the direct-staging MMA issuer needs for the whole tile, so that it reads one
+            // word per tile instead of one per stage -- number of stages, and whether the tile's last stage has a second k-group
+            const int tile_stages = min(kSub, steps - s);
+            const int last_pos = ck.begin + (s + tile_stages - 1) * kRows;
+            const int last_cnt = max(0, min(kRows, ck.end - last_pos));
+            tile_bits = ((uint32_t)tile_stages << TILE_STAGES_SHIFT) | (last_cnt > KT ? TILE_LAST_TWO : 0u);
+        }
+        out[s] = StageDesc{pos, (uint32_t)cnt | (flags << 8) | tile_bits};
     }
 }
 
@@ -552,9 +563,47 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             auto wait_tile_free = [&](uint32_t m) {
                 if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
             };
-            if constexpr (!C::kWide) {
+            if constexpr (kDirect) {
+                // Tile by tile: one table word per TMEM tile (its first stage's info) tells how many stages it has, which
+                // buffer it accumulates in, which warpgroup drains it and the acc_empty parity to wait for; inside a tile the
+                // per-stage work is a barrier wait and the MMAs, with descriptors that depend on the ring position only.
+                const uint32_t nslot = (uint32_t)C::kSlots;
+                uint32_t slot = 0, ph = 0;
+                int S = s_begin;
+                const int s_end = s_begin + total_stages;
+                uint32_t info_next = stage_tab[S].info;
+                while (S < s_end) {
+                    const uint32_t info = info_next;
+                    const uint32_t stages = (info >> TILE_STAGES_SHIFT) & 31u;
+                    const uint32_t m = info >> 8;
+                    S += (int)stages;
+                    if (S < s_end) info_next = stage_tab[S].info;        // next tile's word: in flight during this tile
+                    const uint32_t buf = (m >> FLAG_BUF_SHIFT) & 1u;
+                    const uint32_t d_tmem = tmem_base + buf * (uint32_t)ACC_COLS;
+                    const uint32_t full_bar = acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u;      // acc_full[wg][buf]
+                    const bool last_two = (info & TILE_LAST_TWO) != 0u;
+                    mbar_wait(&sm.acc_empty[buf], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
+                    for (uint32_t st = 0; st < stages; ++st) {
+                        mbar_wait(&sm.full_op[slot], ph);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t d_hi = dbase + (uint64_t)(slot * (uint32_t)(DSTAGE_BYTES >> 4));
+                            umma_f16(d_tmem, d_hi, d_hi, idesc1, st != 0u ? 1u : 0u);
+                            if (!kSym) umma_f16(d_tmem + SCOL, d_hi + (uint64_t)LO_OFF16, d_hi, idesc2, 1u);
+                            if (st + 1u < stages || last_two) {       // ratings 16..31 of the stage: the next 8 KB k-group
+                                const uint64_t d_hi2 = d_hi + (uint64_t)(DGROUP_BYTES >> 4);
+                                umma_f16(d_tmem, d_hi2, d_hi2, idesc1, 1u);
+                                if (!kSym) umma_f16(d_tmem + SCOL, d_hi2 + (uint64_t)LO_OFF16, d_hi2, idesc2, 1u);
+                            }
+                            umma_commit_addr(empty_bar0 + slot * 8u);            // operand stage reusable once the MMAs retire
+                            if (st + 1u == stages) umma_commit_addr(full_bar);
+                        }
+                        __syncwarp();
+                        if (++slot == nslot) { slot = 0; ph ^= 1u; }
+                    }
+                }
+            } else {
                 // 8 operand slots, the loop is unrolled over them so every shared-memory descriptor is base + constant
-                static_assert(C::kWide || !kDirect || C::kSlots == S2, "the unrolled loop serves 8-slot rings");
                 for (int n0 = 0; n0 < total_stages; n0 += S2) {
                     const uint32_t ph = ((uint32_t)n0 / S2) & 1u;
                     // two stages per pass: their barrier waits and flag reads overlap, one elected region issues both
@@ -576,19 +625,6 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                             __syncwarp();
                         }
                     }
-                }
-            } else {
-                // short rows: the solver warpgroups bound the launch, not this warp -- a plain loop over a 12-slot ring
-                int slot = 0;
-                uint32_t ph = 0;
-                for (int n = 0; n < total_stages; ++n) {
-                    mbar_wait(&sm.full_op[slot], ph);
-                    const uint32_t m = sm.meta_op[slot];
-                    wait_tile_free(m);
-                    tc_fence_after();
-                    if (elect_one()) issue_step(slot, m);
-                    __syncwarp();
-                    if (++slot == C::kSlots) { slot = 0; ph ^= 1u; }
                 }
             }
         }
