@@ -15,7 +15,7 @@ tail -n 16 "$OUT/bringup.log"
 echo "working config: ${CFG:-none}" | tee "$OUT/config.txt"
 
 echo "== bench, fp32 staging (baseline of this box)"
-timeout -s KILL 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > "$OUT/bench_conv.json" 2> "$OUT/bench_conv.err"
+CUMF_TC_DIRECT=0 timeout -s KILL 400 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > "$OUT/bench_conv.json" 2> "$OUT/bench_conv.err"
 cat "$OUT/bench_conv.json"
 
 if [ -n "$CFG" ]; then
