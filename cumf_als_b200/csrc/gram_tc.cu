@@ -583,43 +583,25 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     const uint32_t full_bar = acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u;      // acc_full[wg][buf]
                     const bool last_two = (info & TILE_LAST_TWO) != 0u;
                     mbar_wait(&sm.acc_empty[buf], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
-                    // two stages per pass: their barrier waits overlap and one elected region issues both
-                    for (uint32_t st = 0; st < stages; st += 2u) {
-                        const bool two = st + 1u < stages;
-                        const bool wrap = slot + 1u == nslot;
-                        const uint32_t slot1 = wrap ? 0u : slot + 1u;
+                    // (issuing two stages per elected region was measured: no gain on long rows, 9 % slower on short rows,
+                    // where the first stage's MMAs then wait for the second stage's data)
+                    for (uint32_t st = 0; st < stages; ++st) {
                         mbar_wait(&sm.full_op[slot], ph);
-                        if (two) mbar_wait(&sm.full_op[slot1], wrap ? ph ^ 1u : ph);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t d_a = dbase + (uint64_t)(slot * (uint32_t)(DSTAGE_BYTES >> 4));
-                            umma_f16(d_tmem, d_a, d_a, idesc1, st != 0u ? 1u : 0u);
-                            if (!kSym) umma_f16(d_tmem + SCOL, d_a + (uint64_t)LO_OFF16, d_a, idesc2, 1u);
-                            if (two || last_two) {                    // ratings 16..31 of the stage: the next 8 KB k-group
-                                const uint64_t d_a2 = d_a + (uint64_t)(DGROUP_BYTES >> 4);
-                                umma_f16(d_tmem, d_a2, d_a2, idesc1, 1u);
-                                if (!kSym) umma_f16(d_tmem + SCOL, d_a2 + (uint64_t)LO_OFF16, d_a2, idesc2, 1u);
+                            const uint64_t d_hi = dbase + (uint64_t)(slot * (uint32_t)(DSTAGE_BYTES >> 4));
+                            umma_f16(d_tmem, d_hi, d_hi, idesc1, st != 0u ? 1u : 0u);
+                            if (!kSym) umma_f16(d_tmem + SCOL, d_hi + (uint64_t)LO_OFF16, d_hi, idesc2, 1u);
+                            if (st + 1u < stages || last_two) {       // ratings 16..31 of the stage: the next 8 KB k-group
+                                const uint64_t d_hi2 = d_hi + (uint64_t)(DGROUP_BYTES >> 4);
+                                umma_f16(d_tmem, d_hi2, d_hi2, idesc1, 1u);
+                                if (!kSym) umma_f16(d_tmem + SCOL, d_hi2 + (uint64_t)LO_OFF16, d_hi2, idesc2, 1u);
                             }
                             umma_commit_addr(empty_bar0 + slot * 8u);            // operand stage reusable once the MMAs retire
-                            if (two) {
-                                const uint64_t d_b = dbase + (uint64_t)(slot1 * (uint32_t)(DSTAGE_BYTES >> 4));
-                                umma_f16(d_tmem, d_b, d_b, idesc1, 1u);
-                                if (!kSym) umma_f16(d_tmem + SCOL, d_b + (uint64_t)LO_OFF16, d_b, idesc2, 1u);
-                                if (st + 2u < stages || last_two) {
-                                    const uint64_t d_b2 = d_b + (uint64_t)(DGROUP_BYTES >> 4);
-                                    umma_f16(d_tmem, d_b2, d_b2, idesc1, 1u);
-                                    if (!kSym) umma_f16(d_tmem + SCOL, d_b2 + (uint64_t)LO_OFF16, d_b2, idesc2, 1u);
-                                }
-                                umma_commit_addr(empty_bar0 + slot1 * 8u);
-                            }
-                            if (st + 2u >= stages) umma_commit_addr(full_bar);
+                            if (st + 1u == stages) umma_commit_addr(full_bar);
                         }
                         __syncwarp();
-                        // advance the ring position by one or two slots
-                        if (two) {
-                            if (wrap) { slot = 0u; ph ^= 1u; } else { slot = slot1; }
-                        }
-                        if (++slot == nslot) { slot = 0u; ph ^= 1u; }
+                        if (++slot == nslot) { slot = 0; ph ^= 1u; }
                     }
                 }
             } else {
