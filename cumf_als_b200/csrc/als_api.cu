@@ -269,6 +269,11 @@ extern "C" int cumf_plan_destroy(cumf_plan* plan) {
     return CUMF_OK;
 }
 extern "C" int cumf_plan_last_launches(const cumf_plan* plan) { return plan ? plan->last_launches : 0; }
+extern "C" int cumf_plan_set_factor_rows(cumf_plan* plan, int rows) {
+    CUMF_REQUIRE(plan && rows > 0, "cumf_plan_set_factor_rows: bad argument");
+    if (plan->tc) tc_plan_set_factor_rows(plan->tc, rows);
+    return CUMF_OK;
+}
 
 static void plan_time_begin(cumf_plan* p, cudaStream_t st, cudaEvent_t* e0, cudaEvent_t* e1) {
     *e0 = *e1 = nullptr;
@@ -641,6 +646,8 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
     if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
     s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
+    cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
+    cumf_plan_set_factor_rows(s->pt, m);
     // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
     s->can_collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
                           solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr && env_long("CUMF_SSE_DIRECT", 0) == 0);

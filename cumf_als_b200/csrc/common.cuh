@@ -109,6 +109,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
                    int rows_total, int f);
 void tc_plan_destroy(TcWork* w);
 int tc_plan_grid(const TcWork* w);
+void tc_plan_set_factor_rows(TcWork* w, int rows);
 int tc_sse_terms_per_cta();
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,
                      const int* d_colidx, const float* d_val, const float* d_factor, float* d_out,

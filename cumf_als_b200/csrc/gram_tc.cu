@@ -1010,6 +1010,7 @@ struct TcWork {
     bool direct = false;
     long long idx_span = 0;             // ratings the plan's chunks cover (largest chunk end)
     const int* scanned_colidx = nullptr;
+    int hint_rows = 0;                  // rows of the opposing factor as told by the caller (0: scan the indices)
     int factor_rows = 0;                // largest column id + 1 found in scanned_colidx[0, idx_span)
     DevBuf split_tab;                   // [factor_rows + 1][256] fp16, last row zero
     DevBuf max_idx;
@@ -1075,6 +1076,9 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
 void tc_plan_destroy(TcWork* w);
 
 int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
+// rows of the opposing factor, when the caller knows them: saves the index scan (and its stream synchronisation) of
+// the first direct-staging launch
+void tc_plan_set_factor_rows(TcWork* w, int rows) { if (w && rows > 0) w->hint_rows = rows; }
 int tc_sse_terms_per_cta() { return MAX_WG; }
 
 bool tc_path_supports(int f) {
@@ -1216,14 +1220,17 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     if (w->direct) {
         // rows of the opposing factor the plan can gather = largest column id + 1 (one scan per plan and index array)
         if (w->scanned_colidx != d_colidx) {
-            if (!w->max_idx.p) CUMF_TRY(w->max_idx.alloc(sizeof(int)));
-            CUMF_CUDA_TRY(cudaMemsetAsync(w->max_idx.p, 0, sizeof(int), st));
-            max_index_kernel<<<592, 256, 0, st>>>(d_colidx, w->idx_span, w->max_idx.as<int>());
-            int h_max = 0;
-            CUMF_CUDA_TRY(cudaMemcpyAsync(&h_max, w->max_idx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUMF_CUDA_TRY(cudaStreamSynchronize(st));
-            *launches += 1;
-            const int rows = h_max + 1;
+            int rows = w->hint_rows;
+            if (rows <= 0) {
+                if (!w->max_idx.p) CUMF_TRY(w->max_idx.alloc(sizeof(int)));
+                CUMF_CUDA_TRY(cudaMemsetAsync(w->max_idx.p, 0, sizeof(int), st));
+                max_index_kernel<<<592, 256, 0, st>>>(d_colidx, w->idx_span, w->max_idx.as<int>());
+                int h_max = 0;
+                CUMF_CUDA_TRY(cudaMemcpyAsync(&h_max, w->max_idx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+                *launches += 1;
+                rows = h_max + 1;
+            }
             if (rows != w->factor_rows || !w->split_tab.p) {
                 w->split_tab.release();
                 CUMF_TRY(w->split_tab.alloc((size_t)(rows + 1) * SPLIT_ROW_BYTES));

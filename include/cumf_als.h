@@ -123,6 +123,12 @@ int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_beg
 int cumf_plan_destroy(cumf_plan* plan);
 /* number of kernels launched by the last cumf_update_factor on this plan */
 int cumf_plan_last_launches(const cumf_plan* plan);
+/* Optional hint: the number of rows of the opposing factor (what d_factor will hold).  The
+ * fused path stages a pre-split fp16 copy of that factor; without the hint its first launch
+ * scans d_colidx for the largest id (one extra kernel + a stream synchronisation).  The
+ * reference's kernels take the same information implicitly as the extent of thetaT / XT
+ * (als.cu:805, 918-919).                                                        */
+int cumf_plan_set_factor_rows(cumf_plan* plan, int rows);
 
 /* One half-step of ALS for the plan's rows: for every row u in the plan
  *   A_u, b_u  as in cumf_gram;  d_out[u] <- solve(A_u, b_u, x0 = d_out[u])
