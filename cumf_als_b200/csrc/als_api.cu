@@ -43,6 +43,12 @@ void DevBuf::release() {
     bytes = 0;
 }
 
+static double wall_seconds() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 static long env_long(const char* name, long dflt) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
@@ -579,6 +585,10 @@ struct cumf_als_solver {
     // CG path, cooRow == CSR rows, and X untouched since that half-step
     bool theta_fresh = false, can_collect_sse = false;
     double sum_r2 = -1.0;               // sum of squared train ratings (computed on first use)
+    // one-time RMSE preparation enqueued on the upload stream right behind the data it reads (COO-vs-CSR check flag,
+    // sum of squared ratings), so that it runs while the first half-steps do: prep[0] = flag (as double), prep[1] = sum r^2
+    DevBuf prep, prep_partials;
+    bool prep_coo = false, prep_r2 = false;
     cumf_plan* px = nullptr;
     cumf_plan* pt = nullptr;
     // timers
@@ -592,6 +602,7 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     s->csr_col.release(); s->csr_val.release(); s->csc_row.release(); s->csc_val.release();
     s->coo_row.release(); s->test_row.release(); s->test_col.release(); s->test_val.release();
     s->theta.release(); s->x.release(); s->sse.release(); s->partials.release();
+    s->prep.release(); s->prep_partials.release();
     plan_free(s->px);
     plan_free(s->pt);
     if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
@@ -641,20 +652,10 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     // cscColIndex is the pointer array (n+1), cscRowIndex the row ids (nnz).
     const long long xo = csrRowIndexHostPtr[x_begin], xn = (long long)csrRowIndexHostPtr[x_end] - xo;
     const long long to = cscColIndexHostPtr[t_begin], tn = (long long)cscColIndexHostPtr[t_end] - to;
-    // Work plans first: their small synchronous copies would otherwise queue behind the rating uploads on the
-    // copy engine.  Factors and scratch next, then the ratings in the order the iteration needs them.
-    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
-    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
-    s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
-    cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
-    cumf_plan_set_factor_rows(s->pt, m);
-    // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
-    s->can_collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
-                          solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr && env_long("CUMF_SSE_DIRECT", 0) == 0);
-    if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
-    if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
-    if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
-    if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
+    // Order: what the first X half-step needs goes to the copy engine first (factors, CSR), the work plans are built on
+    // the host while those 1 GB are in flight, then the CSC / COO / test uploads follow; each group has its event.
+    const bool debug = env_long("CUMF_DEBUG", 0) != 0;
+    const double t_begin_wall = wall_seconds();
     if (cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_csr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_csc, cudaEventDisableTiming) != cudaSuccess ||
@@ -663,6 +664,8 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         return fail(CUMF_ECUDA);
     }
     cudaStream_t up = s->up_stream;
+    if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
     // initial factors (optional here; cumf_als_set_factors otherwise) go first: the X half-step needs them
     if ((thetaTHost && cudaMemcpyAsync(s->theta.p, thetaTHost, sizeof(float) * (size_t)n * f, cudaMemcpyHostToDevice, up) != cudaSuccess) ||
         (XTHost && cudaMemcpyAsync(s->x.p, XTHost, sizeof(float) * (size_t)m * f, cudaMemcpyHostToDevice, up) != cudaSuccess)) {
@@ -672,12 +675,39 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     if ((rc = upload(s->csr_col, csrColIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csr, up);
+    const double t_plans = wall_seconds();
+    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csc, up);
+    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
+    const double t_plans_end = wall_seconds();
+    s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
+    cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
+    cumf_plan_set_factor_rows(s->pt, m);
+    // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
+    s->can_collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
+                          solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr && env_long("CUMF_SSE_DIRECT", 0) == 0);
+    if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
+    if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
+    if ((rc = s->prep.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
+    if ((rc = s->prep_partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
+    cudaMemsetAsync(s->prep.p, 0, sizeof(double) * 2, up);
+    if (s->can_collect_sse && tn > 0) {
+        // sum of squared ratings (the constant of the by-product train RMSE), behind the CSC upload
+        if ((rc = launch_sumsq(s->csc_val.as<float>(), (long)tn, s->prep.as<double>() + 1, s->prep_partials.as<double>(),
+                               sse_partial_capacity(), up)) != CUMF_OK) return fail(rc);
+        s->prep_r2 = true;
+    }
     if (cooRowIndexHostPtr) {
         if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
         s->train_cnt = (long)xn;
+        if (env_long("CUMF_SSE_LITERAL", 0) == 0 && xn > 0) {
+            // is cooRowIndex the CSR row expansion?  (decides the train-RMSE walk, see cumf_als_sse)
+            if ((rc = launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(),
+                                       reinterpret_cast<int*>(s->prep.p), up)) != CUMF_OK) return fail(rc);
+            s->prep_coo = true;
+        }
     }
     if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
         // samples the reference's launch covers: 256*((nnz_test-1)/256) (als.cu:1006); this
@@ -689,6 +719,9 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         if ((rc = upload(s->test_val, cooValHostTestPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
         s->test_cnt = (long)(t1 - t0);
     }
+    if (debug)
+        printf("\tsetup: allocations + first uploads enqueued %.4f s, work plans %.4f s, rest %.4f s\n", t_plans - t_begin_wall,
+               t_plans_end - t_plans, wall_seconds() - t_plans_end);
     cudaEventRecord(s->ev_rmse, up);
     if (wait_uploads && cudaStreamSynchronize(s->up_stream) != cudaSuccess) {
         set_last_error(std::string("cumf_als_create: upload failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -773,19 +806,25 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
         // are the matrix entries and can be walked row by row or column by column; otherwise keep the literal pairs.
         s->train_mode = 0;
         if (env_long("CUMF_SSE_LITERAL", 0) == 0) {
-            int* flag = reinterpret_cast<int*>(d);      // scratch: re-zeroed below
-            CUMF_TRY(launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(), flag, st));
             int h_flag = 1;
-            CUMF_CUDA_TRY(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-            CUMF_CUDA_TRY(cudaStreamSynchronize(st));
-            CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
-            s->launches += 1;
+            if (s->prep_coo) {
+                // checked on the upload stream while the first half-steps ran (ev_rmse is behind it)
+                CUMF_CUDA_TRY(cudaMemcpyAsync(&h_flag, s->prep.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+            } else {
+                int* flag = reinterpret_cast<int*>(d);      // scratch: re-zeroed below
+                CUMF_TRY(launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(), flag, st));
+                CUMF_CUDA_TRY(cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+                CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
+                s->launches += 1;
+            }
             if (h_flag == 0) {
                 // gather from the smaller factor.  A row shard keeps the CSR walk: its sample set (the owned CSR rows)
                 // is then the same whatever the other ranks decide.
                 const bool whole = (s->xb == 0 && s->xe == s->m && s->tb == 0 && s->te == s->n);
                 s->train_mode = (whole && s->m <= s->n) ? 1 : 2;
-                s->coo_row.release();
+                // (cooRowIndex is not read again; its buffer goes with the solver -- cudaFree would synchronise the device here)
             }
         }
     }
@@ -795,6 +834,12 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
         // since, so  train SSE = sum r^2 - T  (gram_tc.cu) with no further pass over the ratings.  The subtraction
         // loses log10(sum r^2 / SSE) digits of the fp32 row terms (about 1.6 on rating data); the streaming kernel
         // takes over when the fit is so tight that less than three digits would be left, or on any non-finite term.
+        if (s->sum_r2 < 0.0 && s->prep_r2) {
+            double h_r2 = 0.0;
+            CUMF_CUDA_TRY(cudaMemcpyAsync(&h_r2, s->prep.as<double>() + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+            CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+            s->sum_r2 = h_r2;
+        }
         if (s->sum_r2 < 0.0) {
             CUMF_TRY(launch_sumsq(s->csc_val.as<float>(), (long)s->train_cnt, d, s->partials.as<double>(), sse_partial_capacity(), st));
             double h_r2 = 0.0;
@@ -912,12 +957,6 @@ extern "C" int cumf_als_timers(cumf_als_solver* s, double* out6, int reset) {
     exit(EXIT_FAILURE);
 }
 
-static double wall_seconds() {
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec + 1e-9 * ts.tv_nsec;
-}
-
 float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
             const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
             const int* cooRowIndexHostPtr, float* thetaTHost, float* XTHost, const int* cooRowIndexTestHostPtr,
@@ -976,8 +1015,11 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
             printf("--------- Test RMSE in iter %d: %f\n", iter, final_rmse);
         }
     }
+    const double t_down = wall_seconds();
     if (cumf_als_get_factors(s, thetaTHost, XTHost) != CUMF_OK) die("cumf_als_get_factors");   // als.cu:1024-1025
+    const double t_free = wall_seconds();
     cumf_als_destroy(s);
+    if (debug) printf("\tfactor download run %f seconds, release of the device buffers %f seconds.\n", t_free - t_down, wall_seconds() - t_free);
     // like the reference, do NOT cudaDeviceReset here: the caller owns the context (als.cu:1031-1033)
     return final_rmse;
 }
