@@ -25,10 +25,44 @@ namespace cumf {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
+// Device buffers of a destroyed solver are kept for the next one (doALS is typically called again on inputs of the
+// same shape; cudaFree synchronises the device and cudaMalloc of gigabytes costs milliseconds).  Only buffers that
+// went through release_to_cache() -- i.e. whose work is known to be complete -- are reused; CUMF_CACHE_MB caps what is
+// retained (default 16384, 0 disables), cumf_release_cached_memory() returns it to the driver.
+namespace {
+struct CachedBuf { void* p; size_t bytes; int device; };
+std::vector<CachedBuf> g_buf_cache;
+size_t g_buf_cache_bytes = 0;
+std::mutex g_buf_cache_mutex;
+constexpr size_t kCacheMinBytes = 1u << 20;
+}  // namespace
+
 int DevBuf::alloc(size_t n) {
     release();
     if (n == 0) n = 16;
+    if (n >= kCacheMinBytes) {
+        std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        size_t best = g_buf_cache.size();
+        for (size_t i = 0; i < g_buf_cache.size(); ++i) {
+            const CachedBuf& c = g_buf_cache[i];
+            if (c.device == dev && c.bytes >= n && c.bytes <= n + n / 4 && (best == g_buf_cache.size() || c.bytes < g_buf_cache[best].bytes)) best = i;
+        }
+        if (best < g_buf_cache.size()) {
+            p = g_buf_cache[best].p;
+            bytes = g_buf_cache[best].bytes;
+            g_buf_cache_bytes -= bytes;
+            g_buf_cache.erase(g_buf_cache.begin() + (long)best);
+            return CUMF_OK;
+        }
+    }
     cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess && g_buf_cache_bytes > 0) {    // make room: drop what is cached and retry once
+        cudaGetLastError();
+        cumf_release_cached_memory();
+        e = cudaMalloc(&p, n);
+    }
     if (e != cudaSuccess) {
         p = nullptr;
         set_last_error(std::string("cudaMalloc(") + std::to_string(n) + "): " + cudaGetErrorString(e));
@@ -41,6 +75,36 @@ void DevBuf::release() {
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
+}
+// the caller guarantees that no work touching the buffer is in flight
+void DevBuf::release_to_cache() {
+    const char* v = getenv("CUMF_CACHE_MB");
+    const size_t cap = (size_t)((v && *v) ? atol(v) : 16384) << 20;
+    std::unique_lock<std::mutex> lock(g_buf_cache_mutex);
+    if (p && bytes >= kCacheMinBytes && g_buf_cache_bytes + bytes <= cap) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        g_buf_cache.push_back(CachedBuf{p, bytes, dev});
+        g_buf_cache_bytes += bytes;
+        p = nullptr;
+        bytes = 0;
+        return;
+    }
+    lock.unlock();
+    release();
+}
+extern "C" int cumf_release_cached_memory(void) {
+    std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
+    for (auto& c : g_buf_cache) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev != c.device) cudaSetDevice(c.device);
+        cudaFree(c.p);
+        if (dev != c.device) cudaSetDevice(dev);
+    }
+    g_buf_cache.clear();
+    g_buf_cache_bytes = 0;
+    return CUMF_OK;
 }
 
 static double wall_seconds() {
@@ -166,11 +230,13 @@ struct cumf_plan {
     double kernel_ms_total = 0.0;
 };
 
-static void plan_free(cumf_plan* p) {
+// cache = true only when the device is known to be idle (cumf_als_destroy): the buffers are kept for the next plan
+static void plan_free(cumf_plan* p, bool cache = false) {
     if (!p) return;
-    p->d_chunks.release(); p->d_splits.release();
-    p->scratchA.release(); p->scratchB.release(); p->tt.release(); p->rhs.release(); p->sse_terms.release();
-    if (p->tc) tc_plan_destroy(p->tc);
+    auto rel = [cache](DevBuf& b) { if (cache) b.release_to_cache(); else b.release(); };
+    rel(p->d_chunks); rel(p->d_splits);
+    rel(p->scratchA); rel(p->scratchB); rel(p->tt); rel(p->rhs); rel(p->sse_terms);
+    if (p->tc) tc_plan_destroy(p->tc, cache);
     for (auto& e : p->kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete p;
 }
@@ -599,12 +665,14 @@ struct cumf_als_solver {
 extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     if (!s) return CUMF_OK;
     cudaSetDevice(s->device);
-    s->csr_col.release(); s->csr_val.release(); s->csc_row.release(); s->csc_val.release();
-    s->coo_row.release(); s->test_row.release(); s->test_col.release(); s->test_val.release();
-    s->theta.release(); s->x.release(); s->sse.release(); s->partials.release();
+    if (s->up_stream) cudaStreamSynchronize(s->up_stream);
+    cudaDeviceSynchronize();            // what cudaFree would do implicitly: nothing may still use the buffers kept for reuse
+    s->csr_col.release_to_cache(); s->csr_val.release_to_cache(); s->csc_row.release_to_cache(); s->csc_val.release_to_cache();
+    s->coo_row.release_to_cache(); s->test_row.release_to_cache(); s->test_col.release_to_cache(); s->test_val.release_to_cache();
+    s->theta.release_to_cache(); s->x.release_to_cache(); s->sse.release(); s->partials.release();
     s->prep.release(); s->prep_partials.release();
-    plan_free(s->px);
-    plan_free(s->pt);
+    plan_free(s->px, true);
+    plan_free(s->pt, true);
     if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
     if (s->ev_csr) cudaEventDestroy(s->ev_csr);
     if (s->ev_csc) cudaEventDestroy(s->ev_csc);
@@ -664,6 +732,9 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         return fail(CUMF_ECUDA);
     }
     cudaStream_t up = s->up_stream;
+    // the plan of the first half-step before anything is on the copy engine (its small synchronous copies would queue
+    // behind the uploads); the theta-side plan is built while factors + CSR are in flight
+    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
     if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
     if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
     // initial factors (optional here; cumf_als_set_factors otherwise) go first: the X half-step needs them
@@ -676,11 +747,10 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csr, up);
     const double t_plans = wall_seconds();
-    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
+    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csc, up);
-    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
     const double t_plans_end = wall_seconds();
     s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
     cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
@@ -720,7 +790,7 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         s->test_cnt = (long)(t1 - t0);
     }
     if (debug)
-        printf("\tsetup: allocations + first uploads enqueued %.4f s, work plans %.4f s, rest %.4f s\n", t_plans - t_begin_wall,
+        printf("\tsetup: X plan + first uploads enqueued %.4f s, theta plan + CSC enqueued %.4f s, rest %.4f s\n", t_plans - t_begin_wall,
                t_plans_end - t_plans, wall_seconds() - t_plans_end);
     cudaEventRecord(s->ev_rmse, up);
     if (wait_uploads && cudaStreamSynchronize(s->up_stream) != cudaSuccess) {

@@ -68,6 +68,7 @@ struct DevBuf {
     size_t bytes = 0;
     int alloc(size_t n);
     void release();
+    void release_to_cache();   // keep the allocation for the next DevBuf::alloc of a similar size (als_api.cu)
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -107,7 +108,7 @@ bool tc_path_supports(int f);
 struct TcWork;  // opaque per-plan state of the fused kernel
 int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* d_chunks, const std::vector<SplitRow>& splits,
                    int rows_total, int f);
-void tc_plan_destroy(TcWork* w);
+void tc_plan_destroy(TcWork* w, bool cache = false);
 int tc_plan_grid(const TcWork* w);
 void tc_plan_set_factor_rows(TcWork* w, int rows);
 int tc_sse_terms_per_cta();

@@ -1073,7 +1073,7 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
     return CUMF_OK;
 }
 
-void tc_plan_destroy(TcWork* w);
+void tc_plan_destroy(TcWork* w, bool cache);
 
 int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
 // rows of the opposing factor, when the caller knows them: saves the index scan (and its stream synchronisation) of
@@ -1183,20 +1183,21 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
             rc = CUMF_ECUDA;
         }
     }
-    if (rc != CUMF_OK) { tc_plan_destroy(w); return rc; }
+    if (rc != CUMF_OK) { tc_plan_destroy(w, false); return rc; }
     *out = w;
     return CUMF_OK;
 }
 
-void tc_plan_destroy(TcWork* w) {
+void tc_plan_destroy(TcWork* w, bool cache) {
     if (!w) return;
-    w->cta_ptr.release();
-    w->cta_stage_ptr.release();
-    w->stage_tab.release();
-    w->chunk_stage_base.release();
-    w->chunk_meta.release();
-    w->split_tab.release();
-    w->max_idx.release();
+    auto rel = [cache](DevBuf& b) { if (cache) b.release_to_cache(); else b.release(); };
+    rel(w->cta_ptr);
+    rel(w->cta_stage_ptr);
+    rel(w->stage_tab);
+    rel(w->chunk_stage_base);
+    rel(w->chunk_meta);
+    rel(w->split_tab);
+    rel(w->max_idx);
     delete w;
 }
 

@@ -176,6 +176,10 @@ int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const 
                     long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
                     int device, int solver, int path);
 int cumf_als_destroy(cumf_als_solver* s);
+/* cumf_als_destroy (and so cumf_doALS) keeps the large device buffers of the solver for the next
+ * one instead of cudaFree-ing them (at most CUMF_CACHE_MB megabytes, default 16384; 0 disables);
+ * this call returns them to the driver.  The reference frees everything (als.cu:1026-1033).   */
+int cumf_release_cached_memory(void);
 /* Train RMSE as a by-product of the theta half-step: when on (returns 1 if the solver can do it: whole matrix on this
  * GPU, fused CG path, cooRowIndex == CSR rows), cumf_als_update_theta also accumulates, per row, x^T b + x^T r + reg x^T x
  * from the CG state, and cumf_als_sse returns  sum r^2 - that  for the train set instead of streaming over the ratings
