@@ -107,6 +107,50 @@ extern "C" int cumf_release_cached_memory(void) {
     return CUMF_OK;
 }
 
+// ---- pinned staging arena + copy kernel (see common.cuh) ---------------------------------------------
+namespace {
+unsigned char* g_stage = nullptr;
+size_t g_stage_bytes = 0, g_stage_used = 0;
+std::vector<unsigned char*> g_stage_retired;     // arenas outgrown while copies from them may still be queued
+__global__ void copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace
+
+void staging_reset() {
+    g_stage_used = 0;
+    for (unsigned char* p : g_stage_retired) cudaFreeHost(p);
+    g_stage_retired.clear();
+}
+
+int upload_via_kernel(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return CUMF_OK;
+    CUMF_REQUIRE((bytes & 3u) == 0, "upload_via_kernel: size must be a multiple of 4");
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (g_stage_used + need > g_stage_bytes) {
+        const size_t grow = std::max<size_t>(std::max<size_t>(g_stage_bytes * 2, (size_t)16 << 20), g_stage_used + need);
+        unsigned char* fresh = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), grow, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            // no pinned memory to be had: fall back to the (blocking) copy engine path
+            CUMF_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+            return CUMF_OK;
+        }
+        if (g_stage) g_stage_retired.push_back(g_stage);     // queued copies may still read it: freed at the next reset
+        g_stage = fresh;
+        g_stage_bytes = grow;
+        g_stage_used = 0;
+    }
+    unsigned char* slot = g_stage + g_stage_used;
+    g_stage_used += need;
+    memcpy(slot, h_src, bytes);
+    const size_t words = bytes / 4;
+    const int blocks = (int)std::min<size_t>((words + 255) / 256, 592);
+    copy_words_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint32_t*>(d_dst), reinterpret_cast<const uint32_t*>(slot), words);
+    CUMF_CUDA_TRY(cudaGetLastError());
+    return CUMF_OK;
+}
+
 static double wall_seconds() {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -251,6 +295,10 @@ static int plan_create_core(cumf_plan** out, const long long* h_begin, const lon
     CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
     CUMF_TRY(check_f(f));
     CUMF_TRY(check_device());
+    // plan metadata goes to the device through the pinned staging arena (one plan at a time)
+    static std::mutex plan_mutex;
+    std::lock_guard<std::mutex> plan_lock(plan_mutex);
+    staging_reset();
     cumf_plan* p = new cumf_plan();
     p->rows = rows; p->row_begin = row_begin; p->row_end = row_end; p->f = f;
     if (path == CUMF_PATH_AUTO) path = tc_path_supports(f) ? CUMF_PATH_TC : CUMF_PATH_SIMT;
@@ -300,10 +348,10 @@ static int plan_create_core(cumf_plan** out, const long long* h_begin, const lon
 
     int rc = p->d_chunks.alloc(sizeof(Chunk) * std::max<size_t>(1, p->chunks.size()));
     if (rc == CUMF_OK && !p->chunks.empty())
-        if (cudaMemcpy(p->d_chunks.p, p->chunks.data(), sizeof(Chunk) * p->chunks.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = CUMF_ECUDA;
+        rc = upload_via_kernel(p->d_chunks.p, p->chunks.data(), sizeof(Chunk) * p->chunks.size(), 0);
     if (rc == CUMF_OK) rc = p->d_splits.alloc(sizeof(SplitRow) * std::max<size_t>(1, p->splits.size()));
     if (rc == CUMF_OK && !p->splits.empty())
-        if (cudaMemcpy(p->d_splits.p, p->splits.data(), sizeof(SplitRow) * p->splits.size(), cudaMemcpyHostToDevice) != cudaSuccess) rc = CUMF_ECUDA;
+        rc = upload_via_kernel(p->d_splits.p, p->splits.data(), sizeof(SplitRow) * p->splits.size(), 0);
     const size_t ff = (size_t)f * f;
     if (rc == CUMF_OK && slot > 0) {
         rc = p->scratchA.alloc(sizeof(float) * ff * slot);
@@ -325,6 +373,11 @@ static int plan_create_core(cumf_plan** out, const long long* h_begin, const lon
             rc = p->tt.alloc(sizeof(float) * ff * p->batch_rows);
             if (rc == CUMF_OK) rc = p->rhs.alloc(sizeof(float) * (size_t)f * p->batch_rows);
         }
+    }
+    // the staged copies (legacy default stream) must have read the arena before the next plan recycles it
+    if (rc == CUMF_OK && cudaStreamSynchronize(0) != cudaSuccess) {
+        set_last_error(std::string("plan upload: ") + cudaGetErrorString(cudaGetLastError()));
+        rc = CUMF_ECUDA;
     }
     if (rc != CUMF_OK) {
         if (rc == CUMF_ECUDA && g_last_error.empty()) set_last_error("plan upload failed");
@@ -746,11 +799,11 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     if ((rc = upload(s->csr_col, csrColIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csr, up);
-    const double t_plans = wall_seconds();
-    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
     if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csc, up);
+    const double t_plans = wall_seconds();
+    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
     const double t_plans_end = wall_seconds();
     s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
     cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
@@ -763,21 +816,9 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     if ((rc = s->prep.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
     if ((rc = s->prep_partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
     cudaMemsetAsync(s->prep.p, 0, sizeof(double) * 2, up);
-    if (s->can_collect_sse && tn > 0) {
-        // sum of squared ratings (the constant of the by-product train RMSE), behind the CSC upload
-        if ((rc = launch_sumsq(s->csc_val.as<float>(), (long)tn, s->prep.as<double>() + 1, s->prep_partials.as<double>(),
-                               sse_partial_capacity(), up)) != CUMF_OK) return fail(rc);
-        s->prep_r2 = true;
-    }
     if (cooRowIndexHostPtr) {
         if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
         s->train_cnt = (long)xn;
-        if (env_long("CUMF_SSE_LITERAL", 0) == 0 && xn > 0) {
-            // is cooRowIndex the CSR row expansion?  (decides the train-RMSE walk, see cumf_als_sse)
-            if ((rc = launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(),
-                                       reinterpret_cast<int*>(s->prep.p), up)) != CUMF_OK) return fail(rc);
-            s->prep_coo = true;
-        }
     }
     if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
         // samples the reference's launch covers: 256*((nnz_test-1)/256) (als.cu:1006); this
@@ -789,8 +830,22 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         if ((rc = upload(s->test_val, cooValHostTestPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
         s->test_cnt = (long)(t1 - t0);
     }
+    // One-time RMSE preparation behind the last upload (kernels on this stream queue behind the persistent half-step
+    // kernel that owns every SM, so anything placed before an upload would hold that upload back):
+    if (s->can_collect_sse && tn > 0) {
+        // sum of squared ratings, the constant of the by-product train RMSE
+        if ((rc = launch_sumsq(s->csc_val.as<float>(), (long)tn, s->prep.as<double>() + 1, s->prep_partials.as<double>(),
+                               sse_partial_capacity(), up)) != CUMF_OK) return fail(rc);
+        s->prep_r2 = true;
+    }
+    if (cooRowIndexHostPtr && env_long("CUMF_SSE_LITERAL", 0) == 0 && xn > 0) {
+        // is cooRowIndex the CSR row expansion?  (decides the train-RMSE walk, see cumf_als_sse)
+        if ((rc = launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(),
+                                   reinterpret_cast<int*>(s->prep.p), up)) != CUMF_OK) return fail(rc);
+        s->prep_coo = true;
+    }
     if (debug)
-        printf("\tsetup: X plan + first uploads enqueued %.4f s, theta plan + CSC enqueued %.4f s, rest %.4f s\n", t_plans - t_begin_wall,
+        printf("\tsetup: X plan + factor/CSR/CSC uploads enqueued %.4f s, theta plan %.4f s, rest %.4f s\n", t_plans - t_begin_wall,
                t_plans_end - t_plans, wall_seconds() - t_plans_end);
     cudaEventRecord(s->ev_rmse, up);
     if (wait_uploads && cudaStreamSynchronize(s->up_stream) != cudaSuccess) {

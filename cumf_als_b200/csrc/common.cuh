@@ -72,6 +72,13 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Small host -> device uploads of plan metadata that must not queue on the copy engine behind gigabytes of rating
+// uploads: the bytes go through a pinned staging arena (process-wide, grown on demand, kept) and are copied by a kernel
+// reading the arena over PCIe.  Asynchronous on `st`; the arena is recycled by staging_reset(), which the caller may
+// only invoke after `st` has been synchronised.  `bytes` must be a multiple of 4.   (als_api.cu)
+int upload_via_kernel(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
+void staging_reset();
+
 // Launch helpers implemented in the .cu files -------------------------------------
 // SIMT Gram (+RHS) over chunk range [c0,c1): direct rows go to tt/rhs at
 // (row - out_row_base), split chunks to scratchA/scratchB[slot].

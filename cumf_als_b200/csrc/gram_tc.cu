@@ -1164,10 +1164,10 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     if (rc == CUMF_OK) rc = d_base.alloc(sizeof(int) * (n + 1));
     if (rc == CUMF_OK) rc = w->chunk_meta.alloc(sizeof(int) * std::max(n, 1));
     if (rc == CUMF_OK &&
-        (cudaMemcpy(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
-         cudaMemcpy(w->chunk_meta.p, chunk_meta.data(), sizeof(int) * std::max(n, 1), cudaMemcpyHostToDevice) != cudaSuccess ||
-         cudaMemcpy(w->cta_stage_ptr.p, sptr.data(), sizeof(int) * (grid + 1), cudaMemcpyHostToDevice) != cudaSuccess ||
-         cudaMemcpy(d_base.p, stage_base.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice) != cudaSuccess)) {
+        (upload_via_kernel(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), 0) != CUMF_OK ||
+         upload_via_kernel(w->chunk_meta.p, chunk_meta.data(), sizeof(int) * std::max(n, 1), 0) != CUMF_OK ||
+         upload_via_kernel(w->cta_stage_ptr.p, sptr.data(), sizeof(int) * (grid + 1), 0) != CUMF_OK ||
+         upload_via_kernel(d_base.p, stage_base.data(), sizeof(int) * (n + 1), 0) != CUMF_OK)) {
         set_last_error("tc_plan_create: upload failed");
         rc = CUMF_ECUDA;
     }
