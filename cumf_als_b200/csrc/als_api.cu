@@ -34,7 +34,7 @@ struct CachedBuf { void* p; size_t bytes; int device; };
 std::vector<CachedBuf> g_buf_cache;
 size_t g_buf_cache_bytes = 0;
 std::mutex g_buf_cache_mutex;
-constexpr size_t kCacheMinBytes = 1u << 20;
+constexpr size_t kCacheMinBytes = 256;     // (the 16-byte scalars are not worth a list entry)
 }  // namespace
 
 int DevBuf::alloc(size_t n) {
