@@ -80,13 +80,19 @@ constexpr int REG_COLS = F;               // columns of row i of [A] a solver th
 //     512 threads x 128 registers = 65536 = 128 (56 + 3 x 152).
 // (An earlier 3-warpgroup shape that kept columns [64,100) of every row in shared memory to fit the register file was
 // slower -- the CG shares the shared-memory pipe with staging and operand reads; here every row stays in registers.)
-template <bool kSym, bool kDirect> struct Cfg {
+// kRows: ratings per stage -- 16 (fp32 staging: one MMA k-group per stage), 32 or 64 (direct staging: 2 / 4 k-groups per
+// barrier round trip, flag word and commit of the MMA-issuing warp).
+template <bool kSym, bool kDirect, int kRows> struct Cfg {
+    static_assert(kDirect ? (kRows == 32 || kRows == 64) : kRows == 16, "stage size");
     static constexpr bool kWide = kDirect && !kSym;
+    static constexpr int kGroups = kRows / 16;                     // MMA k-groups per stage
+    static constexpr int kSubSteps = 256 / kRows;                  // stages per TMEM tile: 256 ratings in every variant
+    static constexpr int kStageBytes = kDirect ? kRows * 512 : 8192;   // operand bytes of one stage (SPLIT_ROW_BYTES / OP_STAGE_BYTES)
     static constexpr int kWG = kWide ? 3 : 2;                      // solver warpgroups
     static constexpr int kFirstWorker = kWide ? 0 : 4;
-    static constexpr int kWorkers = kWide ? 3 : 8;                 // stage worker warps
-    static constexpr int kSlotsPerWorker = kWide ? 4 : 1;          // direct ring: slots owned by one worker
-    static constexpr int kSlots = kWorkers * kSlotsPerWorker;      // direct ring depth (stages of 32 ratings)
+    static constexpr int kWorkers = kWide ? 3 : (kRows == 64 ? 5 : 8);       // stage worker warps (the other warps of 4..11 idle)
+    static constexpr int kSlotsPerWorker = kWide ? (kRows == 64 ? 2 : 4) : 1;   // direct ring: slots owned by one worker
+    static constexpr int kSlots = kWorkers * kSlotsPerWorker;      // direct ring depth
     static constexpr int kFirstEpiWarp = kWide ? 4 : 12;
     static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;          // 640 / 512
     static constexpr int kRegsLaunch = kWide ? 128 : 96;
@@ -96,6 +102,7 @@ template <bool kSym, bool kDirect> struct Cfg {
     static_assert(128 * (kRegsProd + (kWide ? 0 : 2 * kRegsStage) + kWG * kRegsEpi) <= kThreads * kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
     static_assert(kThreads * kRegsLaunch <= 65536, "launch registers");
     static_assert(!kDirect || kSlots <= 16, "ring barriers");
+    static_assert(kGroups >= 1 && kGroups <= 4, "k-groups per stage (2-bit fields in the stage flags)");
 };
 constexpr int MAX_WG = 3;
 constexpr int SM_ROW_STRIDE = 36;         // floats per row of the shared-memory part: 36 = 4 (mod 32) keeps LDS.128 conflict-free
@@ -106,20 +113,18 @@ constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated i
 // rows of a k-step straight into the UMMA **MN-major** SWIZZLE_128B canonical layout: four 64-element chunks per
 // row, 8 rows x 128 B per swizzle atom.  No fp32 staging ring, no conversion pass: per k-step the shared-memory pipe
 // carries 8 KB of TMA writes + the UMMA operand reads instead of 6.4 + 6.4 + 6.5 KB of staging traffic on top of them.
-// A direct stage holds 32 ratings = two 16-row MMA k-groups: one barrier round trip, one flag word and one commit of the
-// MMA-issuing warp (whose instruction stream bounds long rows) per 32 ratings instead of per 16.
-constexpr int DKT = 32;                   // ratings per direct stage
+// A direct stage holds 32 or 64 ratings = two / four 16-row MMA k-groups: one barrier round trip, one flag word and one
+// commit of the MMA-issuing warp (whose instruction stream bounds long rows) per stage instead of per 16 ratings.
+constexpr int DKT_MAX = 64;               // largest direct stage
 constexpr int SPLIT_COLS = 256;           // fp16 elements per row of the pre-split table
 constexpr int SPLIT_ROW_BYTES = SPLIT_COLS * 2;
 constexpr int SPLIT_CHUNK = 64;           // elements per 128-byte swizzle line
 constexpr int DGROUP_BYTES = KT * SPLIT_ROW_BYTES;    // 8192: one MMA k-group (16 rows)
-constexpr int DSTAGE_BYTES = DKT * SPLIT_ROW_BYTES;   // 16384
-constexpr int DSUB_STEPS = 8;             // direct stages per TMEM tile: the same 256 ratings as SUB_STEPS x KT
 // inside a k-group: 8-row swizzle atoms of one 64-element chunk are 1 KB, the four chunks of 8 rows 4 KB
 // (the CUTLASS tile_to_shape order of Layout_MN_SW128_Atom; tools/mn_major_probe.cu checks it against the hardware)
 constexpr int D_CHUNK_STRIDE = 1024;      // -> descriptor leading byte offset
 constexpr int D_KG_STRIDE = 4096;         // -> descriptor stride byte offset
-static_assert(DSUB_STEPS * DKT == SUB_STEPS * KT, "both stagings cut the accumulation chains at the same ratings");
+static_assert(SUB_STEPS * KT == 256, "every staging cuts the accumulation chains at the same ratings");
 constexpr int TMEM_COLS = 512;
 // accumulator tile, one MMA per k-step:  D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']
 //   lanes 0..99 (features i):  [0,112) P[i][:] = hi_i . hi_j | 112 hi_i . r_hi | 113 hi_i . r_lo' | [128,240) S[i][:] = hi_i . lo'_j
@@ -153,12 +158,11 @@ constexpr uint32_t FLAG_CHUNK_FIRST = 1u, FLAG_CHUNK_LAST = 2u, FLAG_SUB_FIRST =
 //   bit 4  TMEM buffer of the stage's tile (tile index within the CTA & 1)
 //   bits 5-6  solver warpgroup that drains it (chunk index within the CTA mod #warpgroups) -> acc_full[wg][bit4]
 //   bit 7  parity to wait for on acc_empty[bit4] before the tile's first MMA
-//   bit 8  (direct stages) the stage holds more than 16 ratings: its second MMA k-group is fetched and issued
-constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 7;
-constexpr uint32_t FLAG_TWO_GROUPS = 256u;
+//   bits 8-9  (direct stages) number of 16-rating MMA k-groups the stage fetches and issues, minus one
+constexpr int FLAG_BUF_SHIFT = 4, FLAG_WG_SHIFT = 5, FLAG_EMPTY_PARITY_SHIFT = 7, FLAG_GROUPS_SHIFT = 8;
 // StageDesc::info of the first stage of a tile additionally carries (bits above the flags):
 constexpr int TILE_STAGES_SHIFT = 20;             // bits 20-24: stages in the tile (1 .. 16)
-constexpr uint32_t TILE_LAST_TWO = 1u << 25;      // the tile's last stage holds more than 16 ratings
+constexpr int TILE_LAST_GROUPS_SHIFT = 25;        // bits 25-26: k-groups of the tile's last stage, minus one (earlier stages are full)
 
 // One k-step of work: 16 (or fewer) consecutive ratings of one chunk.  Precomputed per plan
 // (stage table), so every stage worker warp is autonomous.
@@ -173,11 +177,11 @@ constexpr int CONV_RING_BYTES = S1 * STAGE_F32_BYTES + S2 * OP_STAGE_BYTES;     
 constexpr int NBAR = 16;                  // stage barriers / metadata slots (the largest ring)
 static_assert(NBAR >= S1 && NBAR >= S2, "barrier / metadata arrays cover every ring");
 // dynamic shared memory, used in place (SWIZZLE_128B atoms need 1024-byte alignment)
-template <int kRingBytes, int kScratchFloats> struct __align__(1024) SmemT {
-    unsigned char ring[kRingBytes];   // kDirect: kSlots x 16 KB, TMA destination == UMMA operand; else the two rings above
-    float stage_vals[NBAR][DKT]; // the ratings of the stage in flight in each gather slot (zero beyond cnt)
+template <int kRingBytes, int kScratchFloats, int kStageBytes> struct __align__(1024) SmemT {
+    unsigned char ring[kRingBytes];   // kDirect: kSlots stages, TMA destination == UMMA operand; else the two rings above
+    float stage_vals[NBAR][DKT_MAX]; // the ratings of the stage in flight in each gather slot (zero beyond cnt)
     uint32_t meta_op[NBAR];      // stage flags forwarded to the MMA warp
-    __align__(16) int stage_idx[NBAR][DKT];   // direct staging: the column ids of the stage being fetched into each slot
+    __align__(16) int stage_idx[NBAR][DKT_MAX];   // direct staging: the column ids of the stage being fetched into each slot
     // per solver warpgroup, kSym only: TR_ROWS rows of G (+ the rating row) for the transpose (2 x 5100 floats)
     float solver_scratch[kScratchFloats];
     float sp[MAX_WG][2][128];    // CG direction vector per solver warpgroup, double buffered
@@ -190,13 +194,13 @@ template <int kRingBytes, int kScratchFloats> struct __align__(1024) SmemT {
     uint32_t tmem_base;
     __device__ __forceinline__ unsigned char* f32_stage(int slot) { return ring + slot * STAGE_F32_BYTES; }
     __device__ __forceinline__ unsigned char* op_stage(int slot) { return ring + S1 * STAGE_F32_BYTES + slot * OP_STAGE_BYTES; }
-    __device__ __forceinline__ unsigned char* dstage(int slot) { return ring + slot * DSTAGE_BYTES; }
+    __device__ __forceinline__ unsigned char* dstage(int slot) { return ring + slot * kStageBytes; }
 };
-template <bool kSym, bool kDirect> struct SmemFor {
-    using C = Cfg<kSym, kDirect>;
-    static constexpr int kRing = kDirect ? C::kSlots * DSTAGE_BYTES : CONV_RING_BYTES;
+template <bool kSym, bool kDirect, int kRows> struct SmemFor {
+    using C = Cfg<kSym, kDirect, kRows>;
+    static constexpr int kRing = kDirect ? C::kSlots * C::kStageBytes : CONV_RING_BYTES;
     static constexpr int kScratch = kSym ? 2 * (TR_ROWS + 1) * F : 4;
-    using type = SmemT<kRing, kScratch>;
+    using type = SmemT<kRing, kScratch, C::kStageBytes>;
     static_assert(sizeof(type) <= 232448, "Smem exceeds the 227 KB a CTA can opt into");
 };
 
@@ -420,7 +424,7 @@ __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const 
                                ((last || (s % kSub) == kSub - 1) ? FLAG_SUB_LAST : 0u) |
                                ((tile & 1u) << FLAG_BUF_SHIFT) | (wg << FLAG_WG_SHIFT) |
                                ((((tile >> 1) & 1u) ^ 1u) << FLAG_EMPTY_PARITY_SHIFT) |
-                               (cnt > KT ? FLAG_TWO_GROUPS : 0u);
+                               ((uint32_t)(max(1, (cnt + KT - 1) / KT) - 1) << FLAG_GROUPS_SHIFT);
         uint32_t tile_bits = 0;
         if ((s % kSub) == 0) {
             // first stage of a TMEM tile: what the direct-staging MMA issuer needs for the whole tile, so that it reads one
@@ -428,7 +432,8 @@ __global__ void fill_stage_table_kernel(const Chunk* __restrict__ chunks, const 
             const int tile_stages = min(kSub, steps - s);
             const int last_pos = ck.begin + (s + tile_stages - 1) * kRows;
             const int last_cnt = max(0, min(kRows, ck.end - last_pos));
-            tile_bits = ((uint32_t)tile_stages << TILE_STAGES_SHIFT) | (last_cnt > KT ? TILE_LAST_TWO : 0u);
+            tile_bits = ((uint32_t)tile_stages << TILE_STAGES_SHIFT) |
+                        ((uint32_t)(max(1, (last_cnt + KT - 1) / KT) - 1) << TILE_LAST_GROUPS_SHIFT);
         }
         out[s] = StageDesc{pos, (uint32_t)cnt | (flags << 8) | tile_bits};
     }
@@ -475,8 +480,8 @@ __global__ void max_index_kernel(const int* __restrict__ idx, long long n, int* 
 
 // kDirect: `factor_map` describes the pre-split fp16 table (box {64, 1}, SWIZZLE_128B), `zero_row` is the index of its
 // all-zero row (the padding of ragged k-groups).
-template <bool kSym, bool kDirect>
-__global__ void __launch_bounds__(Cfg<kSym, kDirect>::kThreads, 1)
+template <bool kSym, bool kDirect, int kRows>
+__global__ void __launch_bounds__(Cfg<kSym, kDirect, kRows>::kThreads, 1)
 als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ cta_chunk_ptr,
                       const StageDesc* __restrict__ stage_tab, const int* __restrict__ cta_stage_ptr,
                       const int* __restrict__ colidx, const float* __restrict__ val,
@@ -486,8 +491,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    using C = Cfg<kSym, kDirect>;
-    using Smem = typename SmemFor<kSym, kDirect>::type;
+    using C = Cfg<kSym, kDirect, kRows>;
+    using Smem = typename SmemFor<kSym, kDirect, kRows>::type;
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
 
     constexpr int NUM_THREADS = C::kThreads;
@@ -532,7 +537,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             // the 8 operand slots so every shared-memory descriptor is base + compile-time constant.
             constexpr uint32_t idesc1 = make_idesc(128, kSym ? N1_SYM : N1, kDirect);
             constexpr uint32_t idesc2 = make_idesc(128, N2, kDirect);
-            constexpr int STAGE_BYTES = kDirect ? DSTAGE_BYTES : OP_STAGE_BYTES;
+            constexpr int STAGE_BYTES = C::kStageBytes;
             // operand rows 128.. (lo' | 0): 16 eight-row groups further (K-major), or two 64-element chunks further (direct)
             constexpr uint32_t LO_OFF16 = (uint32_t)((kDirect ? 2 * D_CHUNK_STRIDE : (LO_ROW / 8) * OP_GROUP_BYTES) >> 4);
             const uint32_t op_base0 = kDirect ? smem_u32(sm.dstage(0)) : smem_u32(sm.op_stage(0));
@@ -545,22 +550,17 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             // one k-group: D[0:128, 0:240] (+)= [hi | r]^T [hi | r | 0 | lo']   (+ D[:, 128:256] += lo'^T [hi | r] if !kSym)
             // Everything the step needs beyond the slot number comes from the stage's flag word (see FLAG_*): no
             // run-time tile / chunk counters in this warp, whose instruction stream bounds the k-step rate on long rows.
-            auto issue_step = [&](int slot, uint32_t m) {
+            [[maybe_unused]] auto issue_step = [&](int slot, uint32_t m) {      // fp32 staging: one k-group per stage
                 // start-address field is (byte address >> 4); slots and row groups are 16-byte multiples and the
                 // whole ring lies below the field's 256 KB wrap, so plain addition is exact
                 const uint64_t d_hi = dbase + (uint64_t)((slot * STAGE_BYTES) >> 4);       // rows 0.. : hi | r | 0 | lo'
                 const uint32_t d_tmem = tmem_base + ((m >> FLAG_BUF_SHIFT) & 1u) * (uint32_t)ACC_COLS;
                 umma_f16(d_tmem, d_hi, d_hi, idesc1, (m & FLAG_SUB_FIRST) ? 0u : 1u);
                 if (!kSym) umma_f16(d_tmem + SCOL, d_hi + (uint64_t)LO_OFF16, d_hi, idesc2, 1u);      // rows 128.. : lo' | 0
-                if (kDirect && (m & FLAG_TWO_GROUPS)) {       // ratings 16..31 of the stage: the next 8 KB k-group
-                    const uint64_t d_hi2 = d_hi + (uint64_t)(DGROUP_BYTES >> 4);
-                    umma_f16(d_tmem, d_hi2, d_hi2, idesc1, 1u);
-                    if (!kSym) umma_f16(d_tmem + SCOL, d_hi2 + (uint64_t)LO_OFF16, d_hi2, idesc2, 1u);
-                }
                 umma_commit_addr(empty_bar0 + (uint32_t)slot * 8u);          // operand stage reusable once the MMAs retire
                 if (m & FLAG_SUB_LAST) umma_commit_addr(acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u);   // acc_full[wg][buf]: index 2 wg + buf
             };
-            auto wait_tile_free = [&](uint32_t m) {
+            [[maybe_unused]] auto wait_tile_free = [&](uint32_t m) {
                 if (m & FLAG_SUB_FIRST) mbar_wait(&sm.acc_empty[(m >> FLAG_BUF_SHIFT) & 1u], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
             };
             if constexpr (kDirect) {
@@ -581,7 +581,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     const uint32_t buf = (m >> FLAG_BUF_SHIFT) & 1u;
                     const uint32_t d_tmem = tmem_base + buf * (uint32_t)ACC_COLS;
                     const uint32_t full_bar = acc_full_bar0 + ((m >> FLAG_BUF_SHIFT) & 7u) * 8u;      // acc_full[wg][buf]
-                    const bool last_two = (info & TILE_LAST_TWO) != 0u;
+                    const uint32_t last_groups = ((info >> TILE_LAST_GROUPS_SHIFT) & 3u) + 1u;
                     mbar_wait(&sm.acc_empty[buf], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
                     // (issuing two stages per elected region was measured: no gain on long rows, 9 % slower on short rows,
                     // where the first stage's MMAs then wait for the second stage's data)
@@ -589,13 +589,16 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                         mbar_wait(&sm.full_op[slot], ph);
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t d_hi = dbase + (uint64_t)(slot * (uint32_t)(DSTAGE_BYTES >> 4));
-                            umma_f16(d_tmem, d_hi, d_hi, idesc1, st != 0u ? 1u : 0u);
-                            if (!kSym) umma_f16(d_tmem + SCOL, d_hi + (uint64_t)LO_OFF16, d_hi, idesc2, 1u);
-                            if (st + 1u < stages || last_two) {       // ratings 16..31 of the stage: the next 8 KB k-group
-                                const uint64_t d_hi2 = d_hi + (uint64_t)(DGROUP_BYTES >> 4);
-                                umma_f16(d_tmem, d_hi2, d_hi2, idesc1, 1u);
-                                if (!kSym) umma_f16(d_tmem + SCOL, d_hi2 + (uint64_t)LO_OFF16, d_hi2, idesc2, 1u);
+                            const uint64_t d_hi = dbase + (uint64_t)(slot * (uint32_t)(STAGE_BYTES >> 4));
+                            // every stage of a tile but the last is full; k-group g = ratings 16 g .. 16 g + 15, 8 KB apart
+                            const uint32_t groups = (st + 1u < stages) ? (uint32_t)C::kGroups : last_groups;
+#pragma unroll
+                            for (int g = 0; g < C::kGroups; ++g) {
+                                if ((uint32_t)g < groups) {
+                                    const uint64_t d_g = d_hi + (uint64_t)((g * DGROUP_BYTES) >> 4);
+                                    umma_f16(d_tmem, d_g, d_g, idesc1, (g == 0 && st == 0u) ? 0u : 1u);
+                                    if (!kSym) umma_f16(d_tmem + SCOL, d_g + (uint64_t)LO_OFF16, d_g, idesc2, 1u);
+                                }
                             }
                             umma_commit_addr(empty_bar0 + slot * 8u);            // operand stage reusable once the MMAs retire
                             if (st + 1u == stages) umma_commit_addr(full_bar);
@@ -643,10 +646,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 return (t < own) ? stage_tab[s_begin + sw + STAGE_WARPS * t] : StageDesc{0, 0u};
             };
             // lane k < 16 fetches column index and rating k of a stage (coalesced 64-byte reads)
-            auto load_idx = [&](const StageDesc& d) -> int {
-                return (lane < (int)(d.info & 0xffu)) ? __ldg(colidx + d.pos + lane) : (kDirect ? zero_row : 0);
+            [[maybe_unused]] auto load_idx = [&](const StageDesc& d) -> int {
+                return (lane < (int)(d.info & 0xffu)) ? __ldg(colidx + d.pos + lane) : 0;
             };
-            auto load_val = [&](const StageDesc& d) -> float {
+            [[maybe_unused]] auto load_val = [&](const StageDesc& d) -> float {
                 return (lane < (int)(d.info & 0xffu)) ? __ldg(val + d.pos + lane) : 0.f;
             };
             if constexpr (kDirect) {
@@ -655,12 +658,28 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 constexpr int R = C::kSlotsPerWorker;
                 // arm the slot's mbarrier and launch the gathers of one stage (warp-collective).  Rows past cnt inside a
                 // fetched k-group carry the index of the table's all-zero row; a stage of <= 16 ratings fetches one k-group.
-                auto issue_direct = [&](int slot, uint32_t flags, int my_idx, float my_val) {
-                    const uint32_t groups = (flags & FLAG_TWO_GROUPS) ? 2u : 1u;
+                constexpr int LPR = kRows / 32;       // ratings per lane of a stage: lane handles ratings lane, lane + 32
+                struct Rat { int idx[LPR]; float val[LPR]; };
+                auto load_rat = [&](const StageDesc& d) -> Rat {
+                    Rat r;
+                    const int cnt = (int)(d.info & 0xffu);
+#pragma unroll
+                    for (int e = 0; e < LPR; ++e) {
+                        const int k = lane + 32 * e;
+                        r.idx[e] = (k < cnt) ? __ldg(colidx + d.pos + k) : zero_row;
+                        r.val[e] = (k < cnt) ? __ldg(val + d.pos + k) : 0.f;
+                    }
+                    return r;
+                };
+                auto issue_direct = [&](int slot, uint32_t flags, const Rat& rat) {
+                    const uint32_t groups = ((flags >> FLAG_GROUPS_SHIFT) & 3u) + 1u;
                     unsigned char* sbase = sm.dstage(slot);
-                    sm.stage_vals[slot][lane] = my_val;
-                    sm.stage_idx[slot][lane] = my_idx;
-                    if (lane == 0) sm.meta_op[slot] = flags;      // the issuer reads it after this stage's full_op arrive
+#pragma unroll
+                    for (int e = 0; e < LPR; ++e) {
+                        sm.stage_vals[slot][lane + 32 * e] = rat.val[e];
+                        sm.stage_idx[slot][lane + 32 * e] = rat.idx[e];
+                    }
+                    if (lane == 0) sm.meta_op[slot] = flags;      // read back by this warp when the stage has landed
                     __syncwarp();
                     // One lane issues all gathers from an unrolled loop: the four row coordinates of a quad are loaded once
                     // (LDS.128) and reused by its four 64-element chunks, so successive UTMALDG differ only in destination and
@@ -670,7 +689,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&sm.full_f32[slot], groups * (uint32_t)DGROUP_BYTES);
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
+                        for (int g = 0; g < C::kGroups; ++g) {
                             if ((uint32_t)g < groups) {
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
@@ -690,9 +709,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 for (int j = 0; j < R; ++j) {
                     if (j < own) {
                         const StageDesc d = load_desc(j);
-                        const int ia = load_idx(d);
-                        const float va = load_val(d);
-                        issue_direct(sw + STAGE_WARPS * j, d.info >> 8, ia, va);
+                        const Rat rat = load_rat(d);
+                        issue_direct(sw + STAGE_WARPS * j, d.info >> 8, rat);
                     }
                 }
                 StageDesc dn = load_desc(R);              // descriptor of the stage the next refill fetches
@@ -702,21 +720,24 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     // software prefetch: descriptor of own-stage t+R+1, indices/ratings of t+R (consumed after the waits below)
                     const StageDesc dcur = dn;
                     dn = load_desc(t + R + 1);
-                    const int nidx = load_idx(dcur);
-                    const float nval = load_val(dcur);
+                    const Rat nrat = load_rat(dcur);
                     const int slot = sw + STAGE_WARPS * slot_j;
                     unsigned char* sbase = sm.dstage(slot);
                     mbar_wait(&sm.full_f32[slot], par);               // the rows have landed
-                    const uint32_t flags = sm.meta_op[slot];          // this warp's own write at issue time
-                    if (lane < KT || (flags & FLAG_TWO_GROUPS)) {
-                        // the ratings ride along as operand columns 112 (r_hi) and 113 (r_lo') of gathered row k = lane:
-                        // chunk 1, element 48 -> 16-byte piece 6 of the row's 128-byte line, XOR-swizzled with the line number
-                        const float r0 = sm.stage_vals[slot][lane];
-                        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
-                        const uint32_t k = (uint32_t)lane & 15u;
-                        unsigned char* ob = sbase + ((uint32_t)lane >> 4) * DGROUP_BYTES + (k >> 3) * D_KG_STRIDE + D_CHUNK_STRIDE +
-                                            (k & 7u) * 128u + ((6u ^ (k & 7u)) << 4);
-                        *reinterpret_cast<__half2*>(ob) = __floats2half2_rn(h0, (r0 - h0) * kLoScale);
+                    const uint32_t groups = ((sm.meta_op[slot] >> FLAG_GROUPS_SHIFT) & 3u) + 1u;      // this warp's own write at issue time
+#pragma unroll
+                    for (int e = 0; e < LPR; ++e) {
+                        const uint32_t kk = (uint32_t)lane + 32u * e;       // rating (= gathered row) of the stage
+                        if ((kk >> 4) < groups) {
+                            // the ratings ride along as operand columns 112 (r_hi) and 113 (r_lo') of gathered row kk: chunk 1,
+                            // element 48 -> 16-byte piece 6 of the row's 128-byte line, XOR-swizzled with the line number
+                            const float r0 = sm.stage_vals[slot][kk];
+                            const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
+                            const uint32_t k = kk & 15u;
+                            unsigned char* ob = sbase + (kk >> 4) * DGROUP_BYTES + (k >> 3) * D_KG_STRIDE + D_CHUNK_STRIDE +
+                                                (k & 7u) * 128u + ((6u ^ (k & 7u)) << 4);
+                            *reinterpret_cast<__half2*>(ob) = __floats2half2_rn(h0, (r0 - h0) * kLoScale);
+                        }
                     }
                     fence_proxy_async();                  // the generic-proxy rating writes ordered before the tensor core's reads
                     __syncwarp();
@@ -724,7 +745,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     if (t + R < own) {
                         // own-stage t+R reuses the slot: the MMAs of stage t must have retired (tcgen05.commit -> empty_op)
                         mbar_wait(&sm.empty_op[slot], par);
-                        issue_direct(slot, dcur.info >> 8, nidx, nval);
+                        issue_direct(slot, dcur.info >> 8, nrat);
                     }
                     if (++slot_j == R) { slot_j = 0; par ^= 1u; }
                 }
@@ -855,8 +876,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             for (int c = c_begin; c < c_end; ++c) {
                 const Chunk ck = ck_next;
                 if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
-                const int tiles = kDirect ? (chunk_steps<DKT>(ck) + DSUB_STEPS - 1) / DSUB_STEPS
-                                          : (chunk_steps<KT>(ck) + SUB_STEPS - 1) / SUB_STEPS;
+                const int tiles = (chunk_steps<kRows>(ck) + C::kSubSteps - 1) / C::kSubSteps;
                 if (((c - c_begin) % C::kWG) != wg) { q += tiles; continue; }
                 float a[REG_COLS];
                 float bi = 0.f;
@@ -1008,6 +1028,7 @@ struct TcWork {
     const float* mapped_factor = nullptr;
     // direct staging (CUMF_TC_DIRECT=1): fp16 pre-split copy of the opposing factor, refreshed before every launch
     bool direct = false;
+    int stage_rows = KT;                // ratings per stage: 16 (fp32 staging), 32 or 64 (direct)
     long long idx_span = 0;             // ratings the plan's chunks cover (largest chunk end)
     const int* scanned_colidx = nullptr;
     int hint_rows = 0;                  // rows of the opposing factor as told by the caller (0: scan the indices)
@@ -1104,7 +1125,8 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     // fp32 ring + in-kernel conversion (16-rating stages)
     const char* denv = getenv("CUMF_TC_DIRECT");
     const bool direct = !(denv && *denv == '0');        // default; CUMF_TC_DIRECT=0 selects the fp32 staging ring
-    const int kt = direct ? DKT : KT, sub = direct ? DSUB_STEPS : SUB_STEPS;
+    const char* renv = getenv("CUMF_TC_STAGE_ROWS");
+    const int kt = direct ? ((renv && atoi(renv) == 64) ? 64 : 32) : KT, sub = 256 / kt;
     // contiguous, cost-balanced partition of the (row-ordered) chunk list: cost = MMA k-steps
     // plus a per-chunk epilogue/solve term, so every CTA streams one contiguous rating range.
     const char* rc_env = getenv("CUMF_TC_ROW_COST");
@@ -1140,16 +1162,19 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     w->grid = grid;
     w->nchunks = n;
     w->direct = direct;
+    w->stage_rows = kt;
     for (int c = 0; c < n; ++c) w->idx_span = std::max<long long>(w->idx_span, chunks[c].end);
     {   // per-chunk epilogue cost (transpose) vs per-k-step MMA saving: the symmetric mode pays from ~32 k-steps per chunk;
         // measured on Netflix: X side (348 k-steps/chunk) 9.6 -> 8.6 ms, theta side (13 k-steps/chunk) 14.8 -> 16.2 ms
         const char* m = getenv("CUMF_TC_SYM");
-        const long long sym_min_steps = 64;
-        w->sym = (m && *m) ? (*m == '1') : (n > 0 && (long long)stage_base[n] >= sym_min_steps * n);
+        const long long sym_min_ratings = 1024;      // per chunk on average (staged ratings: 64 k-steps of 16)
+        w->sym = (m && *m) ? (*m == '1') : (n > 0 && (long long)stage_base[n] * kt >= sym_min_ratings * n);
     }
     // what the MMA issuer would otherwise count: first tile of every chunk within its CTA, chunk parity within its CTA
     std::vector<int> chunk_meta(std::max(n, 1), 0);
-    const int n_wg = w->sym ? (direct ? Cfg<true, true>::kWG : Cfg<true, false>::kWG) : (direct ? Cfg<false, true>::kWG : Cfg<false, false>::kWG);
+    const int n_wg = (direct && !w->sym) ? 3 : 2;       // Cfg<>::kWG of the variant that will run
+    static_assert(Cfg<false, true, 32>::kWG == 3 && Cfg<false, true, 64>::kWG == 3 && Cfg<true, true, 32>::kWG == 2 &&
+                  Cfg<true, true, 64>::kWG == 2 && Cfg<true, false, 16>::kWG == 2 && Cfg<false, false, 16>::kWG == 2, "solver warpgroups");
     for (int b = 0; b < grid; ++b) {
         long long tile = 0;
         for (int c = ptr[b]; c < ptr[b + 1]; ++c) {
@@ -1172,12 +1197,8 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
         rc = CUMF_ECUDA;
     }
     if (rc == CUMF_OK && n > 0) {
-        if (direct)
-            fill_stage_table_kernel<DKT, DSUB_STEPS><<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n,
-                                                                               w->stage_tab.as<StageDesc>());
-        else
-            fill_stage_table_kernel<KT, SUB_STEPS><<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n,
-                                                                             w->stage_tab.as<StageDesc>());
+        auto fill = kt == 64 ? fill_stage_table_kernel<64, 4> : (kt == 32 ? fill_stage_table_kernel<32, 8> : fill_stage_table_kernel<KT, SUB_STEPS>);
+        fill<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n, w->stage_tab.as<StageDesc>());
         if (cudaStreamSynchronize(0) != cudaSuccess) {      // not the device: uploads may be running on another stream
             set_last_error(std::string("tc_plan_create: stage table: ") + cudaGetErrorString(cudaGetLastError()));
             rc = CUMF_ECUDA;
@@ -1209,14 +1230,20 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         return CUMF_EINVAL;
     }
     if (nchunks == 0) return CUMF_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<true, false>::type)));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<false, false>::type)));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<true, true>::type)));
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(als_fused_f100_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemFor<false, true>::type)));
-        attr_set = true;
-    }
+    // kernel variant: (long rows -> symmetric single-MMA mode) x (staging, stage size)
+    using KernelFn = void (*)(const Chunk*, const int*, const StageDesc*, const int*, const int*, const float*, const CUtensorMap, float*,
+                              float, float, float*, float*, uint64_t, double*, int);
+    struct Variant { KernelFn fn; int threads; size_t smem; };
+    auto variant = [&]() -> Variant {
+#define CUMF_VARIANT(SYM, DIRECT, ROWS) \
+        Variant{als_fused_f100_kernel<SYM, DIRECT, ROWS>, Cfg<SYM, DIRECT, ROWS>::kThreads, sizeof(typename SmemFor<SYM, DIRECT, ROWS>::type)}
+        if (!w->direct) return w->sym ? CUMF_VARIANT(true, false, 16) : CUMF_VARIANT(false, false, 16);
+        if (w->stage_rows == 64) return w->sym ? CUMF_VARIANT(true, true, 64) : CUMF_VARIANT(false, true, 64);
+        return w->sym ? CUMF_VARIANT(true, true, 32) : CUMF_VARIANT(false, true, 32);
+#undef CUMF_VARIANT
+    };
+    const Variant v = variant();
+    CUMF_CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     CUMF_REQUIRE((reinterpret_cast<uintptr_t>(d_factor) & 15u) == 0, "the factor matrix must be 16-byte aligned for TMA");
     if (w->direct) {
         // rows of the opposing factor the plan can gather = largest column id + 1 (one scan per plan and index array)
@@ -1245,10 +1272,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         CUMF_CUDA_TRY(cudaGetLastError());
         *launches += 1;
         const uint64_t desc_tmpl = smem_desc_template_direct(D_CHUNK_STRIDE, D_KG_STRIDE);
-        auto kernel = w->sym ? als_fused_f100_kernel<true, true> : als_fused_f100_kernel<false, true>;
-        const int threads = w->sym ? Cfg<true, true>::kThreads : Cfg<false, true>::kThreads;
-        const size_t smem = w->sym ? sizeof(SmemFor<true, true>::type) : sizeof(SmemFor<false, true>::type);
-        kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
+        v.fn<<<w->grid, v.threads, v.smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->split_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
                                                desc_tmpl, d_sse_terms, w->factor_rows);
     } else {
@@ -1258,10 +1282,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         }
         const char* swap = getenv("CUMF_TC_SWAP_LBO_SBO");   // bring-up knob: swap the two descriptor strides
         const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
-        auto kernel = w->sym ? als_fused_f100_kernel<true, false> : als_fused_f100_kernel<false, false>;
-        const int threads = w->sym ? Cfg<true, false>::kThreads : Cfg<false, false>::kThreads;
-        const size_t smem = w->sym ? sizeof(SmemFor<true, false>::type) : sizeof(SmemFor<false, false>::type);
-        kernel<<<w->grid, threads, smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
+        v.fn<<<w->grid, v.threads, v.smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
                                                desc_tmpl, d_sse_terms, 0);
     }

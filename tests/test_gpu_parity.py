@@ -518,3 +518,87 @@ def test_train_sse_keeps_literal_pairs_when_coo_disagrees_with_csr(cuda):
     assert tr == pytest.approx(_direct_sse(r, th, X, row=coo), rel=2e-6)
     assert abs(tr - _direct_sse(r, th, X)) > 1e-3 * tr          # and it is not the matrix walk
     s.close()
+
+
+# ---- direct staging (pre-split fp16 table, swizzled MN-major gather) vs the fp32 staging ring ---------------
+def test_tc_direct_staging_bit_identical_to_fp32_staging(cuda, monkeypatch):
+    """Both stagings hand the tensor core the same operands in the same order (16-rating k-groups, accumulation
+    chains cut every 256 ratings), so the materialised [A|b] must agree bit for bit -- including ragged stages,
+    empty rows and multi-tile rows."""
+    rng = np.random.default_rng(11)
+    n, f, lam = 6000, 100, 0.05
+    lengths = TC_LENGTHS + [64, 65, 255, 256, 257, 511, 513]
+    rowptr, colidx, val = random_csr(rng, lengths, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CUMF_TC_DIRECT", mode)
+        out[mode] = run_gram(cuda, rowptr, colidx, val, factor, f, lam, path=c.PATH_TC)
+    assert np.array_equal(out["0"][0], out["1"][0]) and np.array_equal(out["0"][1], out["1"][1])
+
+
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_tc_half_step_both_stagings_vs_simt(cuda, monkeypatch, direct):
+    """Fused half-step (long-row and short-row kernel variants of either staging) against the exact-fp32 unfused path."""
+    monkeypatch.setenv("CUMF_TC_DIRECT", direct)
+    rng = np.random.default_rng(12)
+    n, f, lam = 9000, 100, 0.048
+    for lengths in ([int(x) for x in rng.integers(1, 120, 600)],            # short rows: two-MMA variant (three solver warpgroups)
+                    [int(x) for x in rng.integers(1500, 4000, 40)] + [0]):  # long rows: symmetric single-MMA variant
+        rowptr, colidx, val = random_csr(rng, lengths, n)
+        factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+        x0 = (0.1 * rng.standard_normal((len(lengths), f))).astype(np.float32)
+        outs = {}
+        for name, path in (("simt", c.PATH_SIMT), ("tc", c.PATH_TC)):
+            plan = c.Plan(rowptr, 0, len(lengths), f, path)
+            x = dev(cuda, x0)
+            c.update_factor(plan, dev(cuda, colidx), dev(cuda, val), dev(cuda, factor), x, lam)
+            cuda.cuda.synchronize()
+            outs[name] = x.cpu().numpy()
+            plan.close()
+        ok = np.isfinite(outs["simt"]).all(axis=1)
+        assert ok.sum() >= len(lengths) - 1
+        assert rel_fro(outs["tc"][ok], outs["simt"][ok]) < TOL
+
+
+def test_plan_factor_rows_hint_saves_the_index_scan(cuda, monkeypatch):
+    """cumf_plan_set_factor_rows: same result, one kernel launch less on the first call (no scan of the column ids)."""
+    monkeypatch.setenv("CUMF_TC_DIRECT", "1")
+    rng = np.random.default_rng(13)
+    n, f, lam = 3000, 100, 0.05
+    lengths = [int(x) for x in rng.integers(1, 300, 200)]
+    rowptr, colidx, val = random_csr(rng, lengths, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    x0 = (0.1 * rng.standard_normal((len(lengths), f))).astype(np.float32)
+    res, launches = [], []
+    for hint in (False, True):
+        plan = c.Plan(rowptr, 0, len(lengths), f, c.PATH_TC)
+        if hint:
+            plan.set_factor_rows(n)
+        x = dev(cuda, x0)
+        c.update_factor(plan, dev(cuda, colidx), dev(cuda, val), dev(cuda, factor), x, lam)
+        cuda.cuda.synchronize()
+        res.append(x.cpu().numpy())
+        launches.append(plan.last_launches)
+        plan.close()
+    assert np.array_equal(res[0], res[1])
+    assert launches[1] == launches[0] - 1
+
+
+def test_doals_twice_reuses_cached_buffers_and_matches(cuda):
+    """cumf_als_destroy keeps the device buffers for the next solver; a second doALS on the same inputs must give the
+    same factors and RMSE, and cumf_release_cached_memory must hand the memory back."""
+    f, lam, iters = 100, 0.048, 2
+    r = synth_ratings(300, 500, 20000, 2000, seed=5)
+    theta0, X0 = init_factors(r.m, r.n, f, seed=2)
+    os.environ["CUMF_QUIET"] = "1"
+    runs = []
+    for _ in range(2):
+        th, X = theta0.copy(), X0.copy()
+        fin = c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz, r.nnz_test, lam, iters, 1, 1, 0)
+        runs.append((fin, th, X))
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    free0 = cuda.cuda.mem_get_info()[0]
+    assert c.load_library().cumf_release_cached_memory() == 0
+    assert cuda.cuda.mem_get_info()[0] >= free0

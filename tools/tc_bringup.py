@@ -56,33 +56,34 @@ def main():
             print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", tt[u][0, :6])
             print("  row 9 ref[1,:6]", ref[u][1, :6], "\n  row 9 got[1,:6]", tt[u][1, :6])
     elif which == "direct":
-        # direct staging (pre-split fp16 table, swizzled MN-major gather) against the fp32-staging kernel: both feed the
-        # tensor core identical operands in the same order, so materialised [A|b] must agree bit for bit
+        # direct staging (pre-split fp16 table, swizzled MN-major gather; 32- or 64-rating stages) against the fp32-staging
+        # kernel: all feed the tensor core identical operands in the same order, so materialised [A|b] must agree bit for bit
+        lengths += [64, 65, 127, 128, 129, 255, 256, 257, 511, 513]
+        rowptr, colidx, val = csr(rng, lengths, n)
+        m = len(lengths)
+        ref = O.gram(rowptr, colidx, factor, f, lam)
+        rhs_ref = O.rhs(rowptr, colidx, val, factor, f)
+        modes = {"fp32": {"CUMF_TC_DIRECT": "0"}, "direct32": {"CUMF_TC_DIRECT": "1", "CUMF_TC_STAGE_ROWS": "32"},
+                 "direct64": {"CUMF_TC_DIRECT": "1", "CUMF_TC_STAGE_ROWS": "64"}}
         outs = {}
-        for mode in ("0", "1"):
-            os.environ["CUMF_TC_DIRECT"] = mode
+        for name, env in modes.items():
+            os.environ.update(env)
             tt = torch.full((m, f, f), float("nan"), device="cuda")
             rhs = torch.full((m, f), float("nan"), device="cuda")
             c.gram(0, m, tt, dev(rowptr), dev(colidx), lam, m, f, dev(factor), rhs=rhs, val=dev(val), path=c.PATH_TC)
             torch.cuda.synchronize()
-            outs[mode] = (tt.cpu().numpy(), rhs.cpu().numpy())
-        print("direct arr =", os.environ.get("CUMF_TC_DIRECT_ARR", "0"), "lbo/sbo =", os.environ.get("CUMF_TC_DIRECT_LBO"),
-              os.environ.get("CUMF_TC_DIRECT_SBO"))
-        worst = 0.0
+            outs[name] = (tt.cpu().numpy(), rhs.cpu().numpy())
+        worst, all_same = 0.0, True
         for u in range(m):
             scale = max(np.abs(ref[u]).max(), 1e-30)
-            e_conv = np.abs(outs["0"][0][u] - ref[u]).max() / scale
-            e_dir = np.abs(outs["1"][0][u] - ref[u]).max() / scale
-            same = np.array_equal(outs["0"][0][u], outs["1"][0][u]) and np.array_equal(outs["0"][1][u], outs["1"][1][u])
-            rb = np.abs(outs["1"][1][u] - rhs_ref[u]).max() / max(np.abs(rhs_ref[u]).max(), 1e-30)
-            worst = max(worst, e_dir if np.isfinite(e_dir) else 1e9, rb if np.isfinite(rb) else 1e9)
-            print(f"  row {u:2d} len {lengths[u]:5d}: err vs oracle  fp32-staging {e_conv:.3e}  direct {e_dir:.3e}  rhs {rb:.1e}  bit-identical {same}")
-        print("DIRECT GRAM", "OK" if worst < 1e-5 else "WRONG", f"(worst {worst:.3e})")
-        if worst >= 1e-5:
-            u = 9
-            print("  row 9 ref[0,:6]", ref[u][0, :6], "\n  row 9 got[0,:6]", outs["1"][0][u][0, :6])
-            print("  row 9 ref[1,:6]", ref[u][1, :6], "\n  row 9 got[1,:6]", outs["1"][0][u][1, :6])
-            print("  row 9 rhs ref[:6]", rhs_ref[u][:6], "\n  row 9 rhs got[:6]", outs["1"][1][u][:6])
+            errs = {k: np.abs(v[0][u] - ref[u]).max() / scale for k, v in outs.items()}
+            same = all(np.array_equal(outs["fp32"][0][u], v[0][u]) and np.array_equal(outs["fp32"][1][u], v[1][u]) for v in outs.values())
+            all_same &= same
+            rb = max(np.abs(v[1][u] - rhs_ref[u]).max() / max(np.abs(rhs_ref[u]).max(), 1e-30) for v in outs.values())
+            worst = max([worst, rb if np.isfinite(rb) else 1e9] + [e if np.isfinite(e) else 1e9 for e in errs.values()])
+            print(f"  row {u:2d} len {lengths[u]:5d}: err vs oracle " + "  ".join(f"{k} {e:.3e}" for k, e in errs.items()) + f"  rhs {rb:.1e}  bit-identical {same}")
+        print("DIRECT GRAM", "OK" if worst < 1e-5 and all_same else "WRONG", f"(worst {worst:.3e}, bit-identical {all_same})")
+        if not (worst < 1e-5 and all_same):
             sys.exit(3)
     elif which == "stress":
         # many chunks per CTA (CUMF_TC_CTAS small), multi-tile rows, split rows: fused vs SIMT
