@@ -1,8 +1,8 @@
 // gram_tc.cu -- the fused B200 half-step kernel:
-//   TMA tile::gather4 row gather -> split-fp16 operand staging -> tcgen05.mma (accumulators in
-//   TMEM) -> epilogue straight into an in-register conjugate-gradient solve.
-// A_u is never written to HBM; per rating the kernel moves one f-wide fp32 factor row,
-// one int32 column index and one fp32 value (B_gram_fused).
+//   TMA tile::gather4 row gather -> split-fp16 operands -> tcgen05.mma (accumulators in TMEM) ->
+//   epilogue straight into an in-register conjugate-gradient solve.
+// A_u is never written to HBM; per rating the kernel moves one f-wide factor row, one int32 column
+// index and one fp32 value (B_gram_fused).
 //
 // What it replaces in the reference: get_hermitian100 (als.cu:443-569) + the cuSPARSE RHS
 // pass (als.cu:750-757) + updateXWithCGKernel (cg.cu:36-231) for f = 100, i.e. the body of
@@ -18,26 +18,32 @@
 // kind::f16 MMAs (the dropped lo^T lo term is < 2^-20 relative).  The ratings get the same
 // split and ride along as two extra operand rows, so  b = sum r_uj theta_j  comes out of the
 // same MMAs.  The tensor core truncates when it accumulates (measured ~6e-8 relative bias per
-// k-step): accumulation chains are cut every 16 k-steps and the tiles summed with
+// 16 ratings): accumulation chains are cut every 256 ratings and the tiles summed with
 // round-to-nearest in registers.  The CG is the fp32 register-resident solve of cg.cu with
 // identical semantics (cg.cu:47-230).
 //
-// CTA = 20 warps (5 warpgroups, setmaxnreg budgets 48/64/64/152/152), persistent, one per SM, each
-// owning a contiguous, cost-balanced range of row chunks (so its ratings are one stream):
-//   warps 0-2     idle (they only return their registers to the pool)
-//   warp 3        MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128, N=256 and N=128, K=16,
-//                 smem descriptors (K-major, no swizzle); tcgen05.commit frees operand stages /
-//                 publishes accumulator tiles; owns the TMEM allocation
-//   warps 4-11    autonomous stage workers, one warp per stage, 16 stages of gathered rows in flight:
-//                 each warp reads its stages' descriptors from a precomputed stage table, prefetches
-//                 the 16 column indices / ratings, arms the stage mbarrier and issues four TMA
-//                 tile::gather4 (SASS UTMALDG.2D.GATHER4, 4 factor rows each) into its own ring slot,
-//                 later converts the landed fp32 rows -> (hi | lo' | r) fp16 in the UMMA K-major
-//                 core-matrix layout (fence.proxy.async) and re-arms the slot two stages ahead
-//   warps 12-19   two epilogue + solver warpgroups (alternate chunks): tcgen05.ld of row i of
-//                 [A | b] into registers, + lambda*n_u, 6-step CG with named-barrier reductions,
-//                 x written back; chunks of split rows store their partial [A|b] instead
-//                 (reduced + solved by the unfused kernels).
+// Staging, two variants that feed the tensor core bit-identical operands in the same order:
+//   direct (default): split_factor_kernel rewrites the opposing factor once per half-step as an fp16 table
+//     [hi | r slots | lo'] (512 B per row); tile::gather4 with CU_TENSOR_MAP_SWIZZLE_128B drops the gathered rows
+//     straight into the UMMA MN-major SWIZZLE_128B operand layout (tools/mn_major_probe.cu pins the layout against
+//     the hardware).  No staging ring, no conversion pass: per 16 ratings the shared-memory pipe carries 8 KB of TMA
+//     writes + the operand reads.  Stages hold 64 (or 32) ratings = 4 (2) MMA k-groups per barrier round trip.
+//   fp32 ring (CUMF_TC_DIRECT=0): gather the fp32 rows, convert them to (hi | lo' | r) fp16 in the UMMA K-major
+//     no-swizzle layout with the stage-worker warps (the round-1 kernel; 16 ratings per stage).
+//
+// Persistent CTAs, one per SM, each owning a contiguous, cost-balanced range of row chunks (so its ratings are one
+// stream); warp roles (Cfg<> below has the shapes and setmaxnreg budgets):
+//   MMA issuer (warp 3): walks its tiles (one table word per 256-rating TMEM tile), waits for the stage barrier and
+//     issues tcgen05.mma cta_group::1 kind::f16, M = 128 -- long rows (kSym): one MMA per k-group, N = 240,
+//     [hi|r]^T [hi|r|0|lo'], the epilogue symmetrises; short rows: that with N = 256 plus N = 128 lo'^T [hi|r];
+//     tcgen05.commit frees operand stages / publishes accumulator tiles; owns the TMEM allocation (2 x 256 columns)
+//   stage workers: read their stages' descriptors from the precomputed stage table, prefetch column ids / ratings,
+//     arm the stage mbarrier, one elected lane issues the gathers (UTMALDG.2D.GATHER4, 4 rows x 128 B each), drop
+//     the split ratings into the landed rows, hand the stage to the issuer, refill the slot when its MMAs retire
+//   solver warpgroups (2 for long rows, 3 for short rows with direct staging): tcgen05.ld of row i of [A | b] into
+//     registers, + lambda*n_u, 6-step CG with named-barrier reductions, x written back; chunks of split rows store
+//     their partial [A|b] instead (reduced + solved by the unfused kernels)
+// Waits park the warp (try_wait with a suspend-time hint -> NANOSLEEP.SYNCS) and carry a watchdog.
 #include "common.cuh"
 
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -1126,7 +1132,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     const char* denv = getenv("CUMF_TC_DIRECT");
     const bool direct = !(denv && *denv == '0');        // default; CUMF_TC_DIRECT=0 selects the fp32 staging ring
     const char* renv = getenv("CUMF_TC_STAGE_ROWS");
-    const int kt = direct ? ((renv && atoi(renv) == 64) ? 64 : 32) : KT, sub = 256 / kt;
+    const int kt = direct ? ((renv && atoi(renv) == 32) ? 32 : 64) : KT, sub = 256 / kt;      // default 64 (measured: 32 is 3-5 % slower)
     // contiguous, cost-balanced partition of the (row-ordered) chunk list: cost = MMA k-steps
     // plus a per-chunk epilogue/solve term, so every CTA streams one contiguous rating range.
     const char* rc_env = getenv("CUMF_TC_ROW_COST");
