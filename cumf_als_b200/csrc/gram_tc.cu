@@ -74,7 +74,6 @@ constexpr int OP_GROUP_BYTES = 256;       // 8 rows x (2 K-core-matrices x 16 B)
 constexpr int OP_KCORE_BYTES = 128;       // one 8x16B core matrix: LBO
 constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 8192
 constexpr int MMA_WARP = 3;
-constexpr int REG_COLS = F;               // columns of row i of [A] a solver thread holds in registers (all of them)
 // Shape of the CTA (20 or 16 warps; the roles are fixed per warp, the setmaxnreg budgets per warpgroup).  The register
 // pool is what the launch allocated (threads x launch registers), the budgets must fit into it.
 //   fp32 staging, and direct staging for long rows (kSym):  warps 0-2 idle | 3 MMA issuer | 4-11 stage workers | 12-19 two
@@ -111,7 +110,6 @@ template <bool kSym, bool kDirect, int kRows> struct Cfg {
     static_assert(kGroups >= 1 && kGroups <= 4, "k-groups per stage (2-bit fields in the stage flags)");
 };
 constexpr int MAX_WG = 3;
-constexpr int SM_ROW_STRIDE = 36;         // floats per row of the shared-memory part: 36 = 4 (mod 32) keeps LDS.128 conflict-free
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 // "direct" staging (kDirect): the opposing factor is pre-split once per half-step into an fp16 table
 //   row j = [ hi_j (100) | 0 (12) | r slots (2) | 0 (14) | lo'_j (100) | 0 (28) ]      256 halfs = 512 B
@@ -341,17 +339,13 @@ __device__ __forceinline__ float wg_sum(float v, float* red4, int warp_in_wg, in
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
-// drain one TMEM accumulator tile into / onto this thread's copy of row i:
+// drain one TMEM accumulator tile into / onto this thread's copy of row i (all 100 columns in registers):
 //   kSym:  G = P/2 + S/2048 and its rating column (symmetrised later);   !kSym:  [A|b] = P + S/2048 directly.
-// Columns [0, kRegCols) live in registers, the rest in the thread's own shared-memory row `arow` (!kSym only).
 template <bool kFirst, bool kSym>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[REG_COLS], float& b, float* arow, bool active) {
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[F], float& b) {
     constexpr float kP = kSym ? 0.5f : 1.0f;
-    constexpr int RC = REG_COLS;
-    constexpr int RC16 = (RC / 16) * 16;        // 96 (all in registers) or 64
-    static_assert(RC == F || RC == RC16, "register part ends on a 16-column boundary");
 #pragma unroll
-    for (int cc = 0; cc < RC16; cc += 16) {
+    for (int cc = 0; cc < 96; cc += 16) {
         uint32_t p[16], s[16];
         tmem_ld16(taddr + cc, p);
         tmem_ld16(taddr + SCOL + cc, s);
@@ -362,44 +356,16 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[REG_COLS],
             a[cc + j] = kFirst ? v : a[cc + j] + v;
         }
     }
-#pragma unroll
-    for (int cc = RC16; cc < 96; cc += 16) {    // !kSym: columns 64..95 go to shared memory
-        uint32_t p[16], s[16];
-        tmem_ld16(taddr + cc, p);
-        tmem_ld16(taddr + SCOL + cc, s);
-        tmem_ld_wait();
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                float4 v = make_float4(fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j])),
-                                       fmaf(__uint_as_float(s[j + 1]), kLoInv, kP * __uint_as_float(p[j + 1])),
-                                       fmaf(__uint_as_float(s[j + 2]), kLoInv, kP * __uint_as_float(p[j + 2])),
-                                       fmaf(__uint_as_float(s[j + 3]), kLoInv, kP * __uint_as_float(p[j + 3])));
-                float4* dst = reinterpret_cast<float4*>(arow + (cc - RC) + j);
-                if (!kFirst) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                *dst = v;
-            }
-        }
-    }
     uint32_t p[4], s[4], bh[4], bl[4];
     tmem_ld4(taddr + 96, p);
     tmem_ld4(taddr + SCOL + 96, s);
     tmem_ld4(taddr + BCOL_HI, bh);      // hi^T r_hi, hi^T r_lo'
     if (!kSym) tmem_ld4(taddr + BCOL_LO, bl);      // lo'^T r_hi
     tmem_ld_wait();
-    float v4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v4[j] = fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j]));
-    if constexpr (RC == F) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[96 + j] = kFirst ? v4[j] : a[96 + j] + v4[j];
-    } else {
-        if (active) {
-            float4* dst = reinterpret_cast<float4*>(arow + (96 - RC));
-            float4 v = make_float4(v4[0], v4[1], v4[2], v4[3]);
-            if (!kFirst) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            *dst = v;
-        }
+    for (int j = 0; j < 4; ++j) {
+        const float v = fmaf(__uint_as_float(s[j]), kLoInv, kP * __uint_as_float(p[j]));
+        a[96 + j] = kFirst ? v : a[96 + j] + v;
     }
     const float tb = kSym ? fmaf(__uint_as_float(bh[1]), kLoInv, 0.5f * __uint_as_float(bh[0]))
                           : fmaf(__uint_as_float(bh[1]) + __uint_as_float(bl[0]), kLoInv, __uint_as_float(bh[0]));
@@ -871,8 +837,6 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
             const int i = quad * 32 + lane;               // row of A / unknown owned by this thread
             const bool active = i < F;
             const int bar_id = 1 + wg;
-            // !kSym: this thread's columns [kRegCols, F) of row i (only threads i < F own a row)
-            float* arow = sm.solver_scratch + (wg * F + (active ? i : 0)) * SM_ROW_STRIDE;
             // tiles appear in chunk-list order: all warpgroups walk the list, each drains only its chunks
             int q = 0;
             uint32_t seen0 = 0, seen1 = 0;                // tiles this warpgroup has taken from TMEM buffer 0 / 1
@@ -884,7 +848,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 if (c + 1 < c_end) ck_next = chunks[c + 1];        // hide the descriptor load behind this chunk
                 const int tiles = (chunk_steps<kRows>(ck) + C::kSubSteps - 1) / C::kSubSteps;
                 if (((c - c_begin) % C::kWG) != wg) { q += tiles; continue; }
-                float a[REG_COLS];
+                float a[F];
                 float bi = 0.f;
                 // warm start x_u (cg.cu:47): requested before the tile waits so its latency is hidden behind them
                 float* xrow = out + (size_t)ck.row * F;
@@ -898,8 +862,8 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     // tile = (hi^T hi)/2 + (hi^T lo')/2048 over <= SUB_STEPS k-steps; the tiles of one chunk
                     // are summed here in fp32 (round-to-nearest), which bounds the length of the tensor core's
                     // own (truncating) accumulation chain
-                    if (tile == 0) drain_tile<true, kSym>(taddr, a, bi, arow, active);
-                    else drain_tile<false, kSym>(taddr, a, bi, arow, active);
+                    if (tile == 0) drain_tile<true, kSym>(taddr, a, bi);
+                    else drain_tile<false, kSym>(taddr, a, bi);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);       // accumulator drained
@@ -942,9 +906,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     if (active) {
                         float4* dst = reinterpret_cast<float4*>(scratchA + (size_t)ck.slot * F * F + (size_t)i * F);
 #pragma unroll
-                        for (int j = 0; j < REG_COLS; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
-#pragma unroll
-                        for (int j = 0; j < (F - REG_COLS); j += 4) dst[(REG_COLS + j) >> 2] = *reinterpret_cast<const float4*>(arow + j);
+                        for (int j = 0; j < F; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
                         scratchB[(size_t)ck.slot * F + i] = bi;
                     }
                     continue;
@@ -957,17 +919,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                 auto spmv = [&](const float* sp, float self) -> float {   // four independent FMA chains, summed pairwise
                     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
-                    for (int j = 0; j < REG_COLS; j += 4) {
+                    for (int j = 0; j < F; j += 4) {
                         const float4 pv = *reinterpret_cast<const float4*>(sp + j);
                         y0 = fmaf(a[j], pv.x, y0); y1 = fmaf(a[j + 1], pv.y, y1);
                         y2 = fmaf(a[j + 2], pv.z, y2); y3 = fmaf(a[j + 3], pv.w, y3);
-                    }
-#pragma unroll
-                    for (int j = 0; j < (F - REG_COLS); j += 4) {     // same chains, coefficients from this thread's smem row
-                        const float4 av = *reinterpret_cast<const float4*>(arow + j);
-                        const float4 pv = *reinterpret_cast<const float4*>(sp + REG_COLS + j);
-                        y0 = fmaf(av.x, pv.x, y0); y1 = fmaf(av.y, pv.y, y1);
-                        y2 = fmaf(av.z, pv.z, y2); y3 = fmaf(av.w, pv.w, y3);
                     }
                     return fmaf(reg, self, (y0 + y1) + (y2 + y3));
                 };
