@@ -1,4 +1,4 @@
-"""The N>1 host logic on CPU: world_size-2 gloo run of the sharded driver (cumf_als_b200.dist) with
+"""The N>1 host logic on CPU: world_size-2 (and 4) gloo runs of the sharded driver (cumf_als_b200.dist) with
 the oracle standing in for the per-rank GPU engine.  Sharded result == single-process result,
 bit for bit (rows are independent given the opposing factor)."""
 import os
@@ -81,6 +81,26 @@ def test_two_rank_sharded_equals_single_process(tmp_path):
     assert float(a["train"]) == pytest.approx(float(hist[-1, 0]), rel=1e-5)
     assert float(a["test"]) == pytest.approx(float(hist[-1, 1]), rel=1e-5)
     assert float(a["test"]) == pytest.approx(float(b["test"]), rel=1e-12)
+
+
+@pytest.mark.timeout(300)
+def test_four_rank_sharded_equals_single_process(tmp_path):
+    """Same driver on 4 ranks (uneven rating-balanced blocks, one of them much shorter than the others): every replica
+    equals the unsharded oracle bit for bit -- the exchange covers every row exactly once at any world size."""
+    world, port = 4, 33000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from cumf_als_b200.data import init_factors, synth_ratings
+    from oracle import oracle as O
+    r = synth_ratings(160, 230, 7000, 900, seed=31)
+    theta0, X0 = init_factors(r.m, r.n, 20, seed=4)
+    th, X = theta0.copy(), X0.copy()
+    fin, hist = O.do_als(r, th, X, 20, 0.05, 2, 0)
+    tests = []
+    for rank in range(world):
+        a = np.load(tmp_path / f"rank{rank}.npz")
+        assert np.array_equal(a["x"], X) and np.array_equal(a["theta"], th)
+        tests.append(float(a["test"]))
+    assert tests[0] == pytest.approx(float(hist[-1, 1]), rel=1e-5) and max(tests) == min(tests)
 
 
 def test_shard_ranges_partition_every_row():
