@@ -63,14 +63,35 @@ class ShardedAls:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         assert len(self.x_ranges) == self.world and len(self.theta_ranges) == self.world
+        import os
+        self._p2p = (dist.is_initialized() and dist.get_backend(group) == "nccl" and
+                     os.environ.get("CUMF_EXCHANGE", "p2p") != "broadcast")
 
     def _exchange(self, full: torch.Tensor, ranges):
-        """Every rank broadcasts the row block it owns (uneven blocks: rating-balanced, not row-balanced)."""
+        """Every rank hands the row block it owns to every other rank (uneven blocks: rating-balanced, not
+        row-balanced, so this is not an ncclAllGather).  NCCL: one grouped launch of point-to-point sends/receives
+        (`batch_isend_irecv`: all blocks move at once over NVSwitch, 2 launches per iteration instead of 2 N broadcasts);
+        gloo (the CPU tests), or CUMF_EXCHANGE=broadcast: one broadcast per owner.  Same bytes land in the same places."""
         if self.world == 1:
+            return
+        peer = (lambda r: dist.get_global_rank(self.group, r)) if self.group else (lambda r: r)
+        if self._p2p and full.is_cuda:
+            lo_me, hi_me = ranges[self.rank]
+            ops = []
+            for r, (lo, hi) in enumerate(ranges):
+                if r == self.rank:
+                    continue
+                if hi_me > lo_me:
+                    ops.append(dist.P2POp(dist.isend, full[lo_me:hi_me], peer(r), self.group))
+                if hi > lo:
+                    ops.append(dist.P2POp(dist.irecv, full[lo:hi], peer(r), self.group))
+            if ops:
+                for work in dist.batch_isend_irecv(ops):
+                    work.wait()          # stream-ordered on NCCL: the next half-step's launch queues behind the exchange
             return
         for r, (lo, hi) in enumerate(ranges):
             if hi > lo:
-                dist.broadcast(full[lo:hi], src=dist.get_global_rank(self.group, r) if self.group else r, group=self.group)
+                dist.broadcast(full[lo:hi], src=peer(r), group=self.group)
 
     def step(self):
         """One ALS iteration: als.cu:727-961 with both half-steps sharded."""
