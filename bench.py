@@ -558,6 +558,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    # stdout carries exactly one JSON line: everything libraries print meanwhile ("NCCL version ...", the reference's
+    # progress lines) goes to stderr; print() below is pointed at the real stdout again just for the result
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print
+
+    def print(*a, **k):          # noqa: A001 -- the result line(s) of this script
+        os.write(real_stdout, (" ".join(str(x) for x in a) + "\n").encode())
+
     if args.impl == "reference":
         run_reference(args, w)
     elif args.sharding == "partial-gram":
