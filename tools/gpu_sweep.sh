@@ -4,7 +4,7 @@ set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out/sweep
 mkdir -p "$OUT"
-for rc in 96 300 1000 3000; do
+for rc in ${SWEEP_VALUES:-0 32 64 96}; do
   CUMF_TC_ROW_COST=$rc timeout -s KILL 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu > "$OUT/rowcost_$rc.json" 2> "$OUT/rowcost_$rc.err"
   python - "$OUT/rowcost_$rc.json" $rc <<'PY'
 import json,sys
