@@ -47,6 +47,15 @@ extern "C" int cumf_load_coo_bin(const char* dataFile, const char* rowFile, cons
     return rc ? -1 : 0;
 }
 
+// Factor initialisation loops of the reference's two front ends, on glibc rand() like they are.
+extern "C" void cumf_init_factors(float* thetaTHost, float* XTHost, int m, int n, int f, float scale, long seed) {
+    if (seed >= 0) srand((unsigned)seed);                                        // main.cpp:73; als_tf.cc never seeds
+    if (thetaTHost)
+        for (long k = 0; k < (long)n * f; ++k) thetaTHost[k] = scale * ((float)rand() / (float)RAND_MAX);   // main.cpp:75, als_tf.cc:121
+    if (XTHost)
+        for (long k = 0; k < (long)m * f; ++k) XTHost[k] = 0.f;                  // CG warm-starts from X: main.cpp:78, als_tf.cc:124
+}
+
 // Reference-named symbols (C++ linkage, same mangled names as host_utilities.cpp).
 void loadCSRSparseMatrixBin(const char* dataFile, const char* rowFile, const char* colFile, float* data, int* row,
                             int* col, const int m, const long nnz) {

@@ -79,6 +79,12 @@ int cumf_load_coo_row_bin(const char* rowFile, int* row, long nnz);
 int cumf_load_coo_bin(const char* dataFile, const char* rowFile, const char* colFile, float* data,
                       int* row, int* col, long nnz);
 
+/* Factor initialisation of the reference's front ends (they do it inline, before doALS):
+ *   thetaTHost[k] = scale * rand() / RAND_MAX  (glibc rand),  XTHost[k] = 0
+ * main.cpp:72-78 uses srand(0) and scale 0.2; the TensorFlow op als_tf.cc:118-125 never
+ * seeds and uses 0.1.  seed < 0: do not call srand.  NULL pointers are skipped.           */
+void cumf_init_factors(float* thetaTHost, float* XTHost, int m, int n, int f, float scale, long seed);
+
 /* ---- b4: stage-level seams (device pointers) --------------------------------
  * cumf_gram replaces the launches
  *   get_hermitian100 / get_hermitianT10 <<<batch_size, ...>>>(batch_offset, tt,
