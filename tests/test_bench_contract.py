@@ -1,0 +1,59 @@
+"""The bench.py output contract, checked on the JSON lines the last GPU run committed under profiles/ (no GPU needed):
+one line per arm with the keys the driver and the judge read."""
+import json
+from pathlib import Path
+
+import pytest
+
+PROFILES = Path(__file__).resolve().parents[1] / "profiles"
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "roofline", "clocks", "gpu_launches"}
+
+
+def _line(name):
+    p = PROFILES / name
+    if not p.exists():
+        pytest.skip(f"{name} not committed")
+    lines = [l for l in p.read_text().splitlines() if l.strip()]
+    assert len(lines) == 1, "bench.py prints exactly one line on stdout"
+    return json.loads(lines[0])
+
+
+@pytest.mark.parametrize("name", ["r1b_bench_ours.json", "r1b_bench_ours_box2.json"])
+def test_our_arm_line(name):
+    d = _line(name)
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["unit"] == "iterations/s" and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["dtype"] == "f32"
+    assert d["config"]["workload"] == "netflix" and d["config"]["f"] == 100 and d["config"]["nnz"] == 99072112
+    assert d["warmup"] >= 3 and d["value"] == pytest.approx(1e3 / d["ms_per_step"], rel=1e-6)
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9)
+    assert r["traffic"] is not None and 0 < r["frac"] < 1
+    e = d["e2e"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(e) and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                      # uploads and downloads are inside the e2e region
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert d["gpu_launches"] > 0
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"]))
+
+
+@pytest.mark.parametrize("name", ["r1b_bench_reference.json", "r1b_bench_reference_box2.json"])
+def test_reference_arm_line(name):
+    d = _line(name)
+    assert d["impl"] == "reference" and BASE_KEYS <= set(d)
+    ours = _line("r1b_bench_ours.json")
+    for k in ("metric", "unit", "higher_is_better"):
+        assert d[k] == ours[k]
+    assert d["config"]["workload"] == ours["config"]["workload"] and d["config"]["nnz"] == ours["config"]["nnz"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_two_gpu_line_is_whole_job_throughput():
+    d = _line("r1b_bench_2gpu_rows.json")
+    one = _line("r1b_bench_ours.json")
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["nnz"] == one["config"]["nnz"]
+    assert one["value"] < d["value"] < 2.2 * one["value"]
+    assert "e2e" in d and d["e2e"]["h2d_bytes_per_step"] > 0
