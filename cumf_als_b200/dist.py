@@ -54,6 +54,22 @@ def shard_ranges(csr_indptr, csc_indptr, world: int):
     return nnz_balanced_ranges(csr_indptr, world), nnz_balanced_ranges(csc_indptr, world)
 
 
+def exchange_plan(rank: int, ranges):
+    """Point-to-point operations of `rank` for the row-block exchange: ("send", peer, lo, hi) of its own block to every
+    other rank, ("recv", peer, lo, hi) of every other rank's block; empty blocks move nothing on either side, so every send
+    has exactly one matching receive (integer path, tested for every world size in tests/test_dist_gloo.py)."""
+    lo_me, hi_me = ranges[rank]
+    plan = []
+    for r, (lo, hi) in enumerate(ranges):
+        if r == rank:
+            continue
+        if hi_me > lo_me:
+            plan.append(("send", r, lo_me, hi_me))
+        if hi > lo:
+            plan.append(("recv", r, lo, hi))
+    return plan
+
+
 class ShardedAls:
     def __init__(self, engine, x_ranges, theta_ranges, nnz: int, nnz_test: int, group=None):
         self.e = engine
@@ -76,15 +92,8 @@ class ShardedAls:
             return
         peer = (lambda r: dist.get_global_rank(self.group, r)) if self.group else (lambda r: r)
         if self._p2p and full.is_cuda:
-            lo_me, hi_me = ranges[self.rank]
-            ops = []
-            for r, (lo, hi) in enumerate(ranges):
-                if r == self.rank:
-                    continue
-                if hi_me > lo_me:
-                    ops.append(dist.P2POp(dist.isend, full[lo_me:hi_me], peer(r), self.group))
-                if hi > lo:
-                    ops.append(dist.P2POp(dist.irecv, full[lo:hi], peer(r), self.group))
+            ops = [dist.P2POp(dist.isend if kind == "send" else dist.irecv, full[lo:hi], peer(r), self.group)
+                   for kind, r, lo, hi in exchange_plan(self.rank, ranges)]
             if ops:
                 for work in dist.batch_isend_irecv(ops):
                     work.wait()          # stream-ordered on NCCL: the next half-step's launch queues behind the exchange

@@ -103,6 +103,34 @@ def test_four_rank_sharded_equals_single_process(tmp_path):
     assert tests[0] == pytest.approx(float(hist[-1, 1]), rel=1e-5) and max(tests) == min(tests)
 
 
+def test_exchange_plan_sends_and_receives_pair_up():
+    """The NCCL row-block exchange is one grouped launch of sends and receives per rank: every send must meet exactly one
+    receive of the same rows on the peer (an unmatched one would hang the group), and together the receives of a rank
+    cover every row it does not own exactly once -- at every world size, with empty blocks in the partition."""
+    from cumf_als_b200.dist import exchange_plan
+    rng = np.random.default_rng(5)
+    for world in (2, 3, 4, 8):
+        for trial in range(20):
+            rows = int(rng.integers(world, 400))
+            cuts = np.sort(rng.integers(0, rows + 1, world - 1))          # repeated cut points -> empty blocks
+            bounds = [0, *cuts.tolist(), rows]
+            ranges = [(bounds[i], bounds[i + 1]) for i in range(world)]
+            plans = [exchange_plan(r, ranges) for r in range(world)]
+            for a in range(world):
+                sends = [(p, lo, hi) for k, p, lo, hi in plans[a] if k == "send"]
+                recvs = [(p, lo, hi) for k, p, lo, hi in plans[a] if k == "recv"]
+                for peer, lo, hi in sends:
+                    assert (lo, hi) == ranges[a] and hi > lo
+                    assert [(p, l, h) for k, p, l, h in plans[peer] if k == "recv" and p == a] == [(a, lo, hi)]
+                for peer, lo, hi in recvs:
+                    assert (lo, hi) == ranges[peer] and ("send", a, lo, hi) in plans[peer]
+                covered = np.zeros(rows, np.int32)
+                for _, lo, hi in recvs:
+                    covered[lo:hi] += 1
+                covered[ranges[a][0]:ranges[a][1]] += 1
+                assert (covered == 1).all()
+
+
 def test_shard_ranges_partition_every_row():
     from cumf_als_b200.data import synth_ratings
     from cumf_als_b200.dist import shard_ranges
