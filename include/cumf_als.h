@@ -184,7 +184,8 @@ int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const 
 int cumf_als_destroy(cumf_als_solver* s);
 /* cumf_als_destroy (and so cumf_doALS) keeps the large device buffers of the solver for the next
  * one instead of cudaFree-ing them (at most CUMF_CACHE_MB megabytes, default 16384; 0 disables);
- * this call returns them to the driver.  The reference frees everything (als.cu:1026-1033).   */
+ * this call returns them to the driver.  The reference frees everything (als.cu:1026-1033).
+ * Call it before cudaDeviceReset(): the cached pointers do not survive the context.           */
 int cumf_release_cached_memory(void);
 /* Train RMSE as a by-product of the theta half-step: when on (returns 1 if the solver can do it: whole matrix on this
  * GPU, fused CG path, cooRowIndex == CSR rows), cumf_als_update_theta also accumulates, per row, x^T b + x^T r + reg x^T x
