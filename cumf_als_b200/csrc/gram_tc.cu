@@ -76,15 +76,16 @@ constexpr int OP_STAGE_BYTES = OP_ROWS / 8 * OP_GROUP_BYTES;   // 8192
 constexpr int MMA_WARP = 3;
 // Shape of the CTA (20 or 16 warps; the roles are fixed per warp, the setmaxnreg budgets per warpgroup).  The register
 // pool is what the launch allocated (threads x launch registers), the budgets must fit into it.
-//   fp32 staging, and direct staging for long rows (kSym):  warps 0-2 idle | 3 MMA issuer | 4-11 stage workers | 12-19 two
-//     solver warpgroups; 640 threads x 96 registers = 61440 >= 128 (P + 2 S + 2 E).
+//   fp32 staging, and direct staging for long rows (kSym):  warps 0-2 idle | 3 MMA issuer | 4-11 stage workers (direct
+//     64-rating stages: five of them, one 32 KB ring slot each) | 12-19 two solver warpgroups;
+//     640 threads x 96 registers = 61440 >= 128 (P + 2 S + 2 E).
 //   direct staging for short rows (!kSym, "wide"): the launch is bound by the per-row drain + CG (ncu: the solver
 //     warpgroups are 85 % busy, the issuer waits for free TMEM tiles), and the direct workers only issue gathers, so
 //     three of them share the issuer's warpgroup and a THIRD solver warpgroup takes their place:
-//     warps 0-2 stage workers (4 ring slots each) | 3 MMA issuer | 4-15 three solver warpgroups;
+//     warps 0-2 stage workers (two 32 KB or four 16 KB ring slots each) | 3 MMA issuer | 4-15 three solver warpgroups;
 //     512 threads x 128 registers = 65536 = 128 (56 + 3 x 152).
-// (An earlier 3-warpgroup shape that kept columns [64,100) of every row in shared memory to fit the register file was
-// slower -- the CG shares the shared-memory pipe with staging and operand reads; here every row stays in registers.)
+// (An earlier 3-warpgroup shape that kept columns [64,100) of every row in shared memory to fit the 640-thread CTA's
+// register pool was slower; here every row stays in registers.)
 // kRows: ratings per stage -- 16 (fp32 staging: one MMA k-group per stage), 32 or 64 (direct staging: 2 / 4 k-groups per
 // barrier round trip, flag word and commit of the MMA-issuing warp).
 template <bool kSym, bool kDirect, int kRows> struct Cfg {
