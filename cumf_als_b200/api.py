@@ -58,7 +58,7 @@ SIGNATURES = {
     "cumf_plan_gram": (C.c_int, [_vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     "cumf_plan_destroy": (C.c_int, [_vp]),
     "cumf_plan_last_launches": (C.c_int, [_vp]),
-    "cumf_init_factors": (None, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_long]),
+    "cumf_init_factors": (None, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_long]),
     "cumf_release_cached_memory": (C.c_int, []),
     "cumf_plan_set_factor_rows": (C.c_int, [_vp, C.c_int]),
     "cumf_update_factor": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, C.c_int, C.c_float, _vp]),

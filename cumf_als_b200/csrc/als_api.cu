@@ -25,10 +25,11 @@ namespace cumf {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
-// Device buffers of a destroyed solver are kept for the next one (doALS is typically called again on inputs of the
-// same shape; cudaFree synchronises the device and cudaMalloc of gigabytes costs milliseconds).  Only buffers that
-// went through release_to_cache() -- i.e. whose work is known to be complete -- are reused; CUMF_CACHE_MB caps what is
-// retained (default 16384, 0 disables), cumf_release_cached_memory() returns it to the driver.
+// OPT-IN buffer cache.  By default (CUMF_CACHE_MB unset or 0) every device buffer of a solver is cudaFree'd when the
+// solver is destroyed, i.e. doALS returns with all its device memory released, like the reference (als.cu:1026-1033).
+// With CUMF_CACHE_MB=<n> up to n MiB of a destroyed solver's buffers are kept for the next one (a caller that runs doALS
+// repeatedly on inputs of the same shape saves the cudaMalloc/cudaFree round trips); only buffers that went through
+// release_to_cache() -- whose work is known to be complete -- are reused, cumf_release_cached_memory() returns them.
 namespace {
 struct CachedBuf { void* p; size_t bytes; int device; };
 std::vector<CachedBuf> g_buf_cache;
@@ -36,6 +37,8 @@ size_t g_buf_cache_bytes = 0;
 std::mutex g_buf_cache_mutex;
 constexpr size_t kCacheMinBytes = 256;     // (the 16-byte scalars are not worth a list entry)
 }  // namespace
+
+extern "C" int cumf_release_cached_memory(void);
 
 int DevBuf::alloc(size_t n) {
     release();
@@ -79,7 +82,7 @@ void DevBuf::release() {
 // the caller guarantees that no work touching the buffer is in flight
 void DevBuf::release_to_cache() {
     const char* v = getenv("CUMF_CACHE_MB");
-    const size_t cap = (size_t)((v && *v) ? atol(v) : 16384) << 20;
+    const size_t cap = (size_t)((v && *v) ? std::max(0L, atol(v)) : 0) << 20;
     std::unique_lock<std::mutex> lock(g_buf_cache_mutex);
     if (p && bytes >= kCacheMinBytes && g_buf_cache_bytes + bytes <= cap) {
         int dev = 0;
@@ -93,20 +96,6 @@ void DevBuf::release_to_cache() {
     lock.unlock();
     release();
 }
-extern "C" int cumf_release_cached_memory(void) {
-    std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
-    for (auto& c : g_buf_cache) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (dev != c.device) cudaSetDevice(c.device);
-        cudaFree(c.p);
-        if (dev != c.device) cudaSetDevice(dev);
-    }
-    g_buf_cache.clear();
-    g_buf_cache_bytes = 0;
-    return CUMF_OK;
-}
-
 // ---- pinned staging arena + copy kernel (see common.cuh) ---------------------------------------------
 namespace {
 unsigned char* g_stage = nullptr;
@@ -117,20 +106,44 @@ __global__ void copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __
 }
 }  // namespace
 
+// A cudaDeviceReset by the caller (the reference CLI ends with one, main.cpp:168; die() below) invalidates the arena:
+// probe it before reuse and drop a dangling pointer instead of writing through it.
+static bool stage_alive() {
+    if (!g_stage) return false;
+    unsigned int flags = 0;
+    if (cudaHostGetFlags(&flags, g_stage) == cudaSuccess) return true;
+    cudaGetLastError();
+    g_stage = nullptr;
+    g_stage_bytes = g_stage_used = 0;
+    g_stage_retired.clear();
+    return false;
+}
+
 void staging_reset() {
     g_stage_used = 0;
+    if (!stage_alive()) return;
     for (unsigned char* p : g_stage_retired) cudaFreeHost(p);
     g_stage_retired.clear();
+}
+
+static void staging_release() {
+    if (stage_alive()) {
+        for (unsigned char* p : g_stage_retired) cudaFreeHost(p);
+        cudaFreeHost(g_stage);
+    }
+    g_stage_retired.clear();
+    g_stage = nullptr;
+    g_stage_bytes = g_stage_used = 0;
 }
 
 int upload_via_kernel(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return CUMF_OK;
     CUMF_REQUIRE((bytes & 3u) == 0, "upload_via_kernel: size must be a multiple of 4");
     const size_t need = (bytes + 255) & ~(size_t)255;
-    if (g_stage_used + need > g_stage_bytes) {
+    if (!stage_alive() || g_stage_used + need > g_stage_bytes) {
         const size_t grow = std::max<size_t>(std::max<size_t>(g_stage_bytes * 2, (size_t)16 << 20), g_stage_used + need);
         unsigned char* fresh = nullptr;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), grow, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), grow, cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
             // no pinned memory to be had: fall back to the (blocking) copy engine path
             CUMF_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
@@ -205,17 +218,38 @@ __global__ void fill_ptrs_kernel(float** Ap, float** bp, float* A, float* b, int
         bp[k] = b + (size_t)k * f;       // devPtrYthetaTHost[k] = &ythetaT[... k*f] (als.cu:91-95)
     }
 }
-cublasHandle_t g_cublas = nullptr;
-std::mutex g_cublas_mu;
+struct CublasHandle {      // created per call on the current device (oracle mode only: not a hot path), destroyed on every exit path
+    cublasHandle_t h = nullptr;
+    ~CublasHandle() { if (h) cublasDestroy(h); }
+};
 }  // namespace
+
+// returns everything this library keeps between calls to the driver: cached device buffers and the pinned staging arena
+extern "C" int cumf_release_cached_memory(void) {
+    {
+        std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        for (auto& c : g_buf_cache) {
+            if (dev != c.device) cudaSetDevice(c.device);
+            cudaFree(c.p);
+            if (dev != c.device) cudaSetDevice(dev);
+        }
+        g_buf_cache.clear();
+        g_buf_cache_bytes = 0;
+    }
+    staging_release();
+    return CUMF_OK;
+}
 
 int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t st) {
     if (batch <= 0) return CUMF_OK;
-    std::lock_guard<std::mutex> lk(g_cublas_mu);
-    if (!g_cublas && cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
+    CublasHandle cb;
+    if (cublasCreate(&cb.h) != CUBLAS_STATUS_SUCCESS) {
         set_last_error("cublasCreate failed");
         return CUMF_ECUDA;
     }
+    cublasHandle_t g_cublas = cb.h;
     cublasSetStream(g_cublas, st);
     DevBuf ptrs, info;
     CUMF_TRY(ptrs.alloc(sizeof(float*) * 2 * (size_t)batch));
@@ -238,8 +272,6 @@ int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t
     // als.cu:108: the solution (left in the RHS) is copied into the factor
     CUMF_CUDA_TRY(cudaMemcpyAsync(d_x, d_b, sizeof(float) * (size_t)batch * f, cudaMemcpyDeviceToDevice, st));
     CUMF_CUDA_TRY(cudaStreamSynchronize(st));
-    ptrs.release();
-    info.release();
     return CUMF_OK;
 }
 
@@ -668,8 +700,6 @@ extern "C" int cumf_rmse(const float* d_val, const int* d_row, const int* d_col,
     double sse = 0.0;
     if (rc == CUMF_OK && cudaMemcpyAsync(&sse, out.p, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = CUMF_ECUDA;
     if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = CUMF_ECUDA;
-    part.release();
-    out.release();
     if (rc != CUMF_OK) return rc;
     if (sse_out) *sse_out = sse;
     if (rmse_out) *rmse_out = sqrtf((float)sse / (float)count);   // als.cu:991, 1018
@@ -1028,7 +1058,12 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
 extern "C" int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, void* stream) {
     CUMF_REQUIRE(s && iters >= 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    std::vector<cudaEvent_t> ev(2 * (size_t)iters + 1);
+    struct Events {
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (auto e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.v.assign(2 * (size_t)iters + 1, nullptr);
+    std::vector<cudaEvent_t>& ev = evs.v;
     for (auto& e : ev) CUMF_CUDA_TRY(cudaEventCreate(&e));
     CUMF_CUDA_TRY(cudaEventRecord(ev[0], st));
     int rc = CUMF_OK;
@@ -1053,7 +1088,6 @@ extern "C" int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, vo
         s->iterations += iters;
         if (ms_out) *ms_out = total;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
     return rc;
 }
 
@@ -1108,25 +1142,47 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
                         DEVICEID, solver, path, /*wait_uploads=*/false, thetaTHost, XTHost) != CUMF_OK)
         die("cumf_als_create");
     cumf_als_collect_train_sse(s, 1);
-    if (debug) printf("\tsetup (work plans; uploads continue in the background) run %f seconds.\n", wall_seconds() - t_setup);
+    if (debug) {
+        printf("\tsetup (work plans; uploads continue in the background) run %f seconds.\n", wall_seconds() - t_setup);
+        s->px->time_kernel = s->pt->time_kernel = true;     // CUDA events around the Gram(+fused solve) kernel
+    }
     if (!quiet) printf("*******start iterations...\n");
     float final_rmse = 0.f;
+    double kx_ms = 0.0, kt_ms = 0.0;      // running totals of the timed kernels (debug)
     for (int iter = 0; iter < ITERS; ++iter) {
         double t0 = wall_seconds();
         if (debug) printf("---------------------------ALS iteration %d, update X.----------------------------------\n", iter);
         if (cumf_als_update_x(s, nullptr) != CUMF_OK) die("update X");
         if (debug) {
+            // the reference's -DDEBUG line set (als.cu:821, 827/830, 844-845, 850), one batch: hermitiantime.sh sums
+            // field 5 of the "kernel run" lines, solvertime.sh field 5 of the "solver run" lines, print-test-result.sh
+            // field 4 of the "update X/theta run" lines.  "kernel" = the Gram kernel (fused path: Gram + RHS + CG in one
+            // launch), "solver" = whatever ran after it (the CG / LU kernels of the unfused path, the split-row tail).
             cudaStreamSynchronize(0);
-            if (solver == CUMF_SOLVER_CG) printf("\tCG solver with fp32.\n");
-            printf("update X run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, m, f);
+            const double wall = wall_seconds() - t0;
+            const double k = plan_collect_kernel_ms(s->px);
+            const double kern = (k - kx_ms) * 1e-3;
+            kx_ms = k;
+            printf("\tupdate X kernel run %f seconds, gridSize: %d, blockSize %d.\n", kern, m, f);
+            printf(solver == CUMF_SOLVER_CG ? "\tCG solver with fp32.\n" : "\tLU solver (cuBLAS getrfBatched).\n");
+            printf("\tinvoke updateX with batch_size: %d, batch_offset: %d..\n", m, 0);
+            printf("\tupdateX solver run seconds: %f \n", std::max(0.0, wall - kern));
+            printf("update X run %f seconds, gridSize: %d, blockSize %d.\n", wall, m, f);
             t0 = wall_seconds();
             printf("---------------------------------- ALS iteration %d, update theta ----------------------------------\n", iter);
         }
         if (cumf_als_update_theta(s, nullptr) != CUMF_OK) die("update theta");
         if (debug) {
-            cudaStreamSynchronize(0);
-            if (solver == CUMF_SOLVER_CG) printf("\tCG solver with fp32.\n");
-            printf("update theta run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, n, f);
+            cudaStreamSynchronize(0);      // als.cu:928, 931, 942/945, 957, 961-963
+            const double wall = wall_seconds() - t0;
+            const double k = plan_collect_kernel_ms(s->pt);
+            const double kern = (k - kt_ms) * 1e-3;
+            kt_ms = k;
+            printf("\tupdate Theta kernel run %f seconds, gridSize: %d, blockSize %d.\n", kern, n, f);
+            printf("*******invoke updateTheta with batch_size: %d, batch_offset: %d.\n", n, 0);
+            printf(solver == CUMF_SOLVER_CG ? "\tCG solver with fp32.\n" : "\tLU solver (cuBLAS getrfBatched).\n");
+            printf("\tupdateTheta solver run seconds: %f \n", std::max(0.0, wall - kern));
+            printf("update theta run %f seconds, gridSize: %d, blockSize %d.\n", wall, n, f);
             printf("Calculate RMSE.\n");
         }
         double tr = 0.0, te = 0.0;

@@ -63,12 +63,22 @@ struct SplitRow {
     int nnz;        // ratings in the whole row (for the lambda*n_u term)
 };
 
+// Owning device allocation (move-only; the destructor frees, so early returns do not leak).
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
     int alloc(size_t n);
     void release();
-    void release_to_cache();   // keep the allocation for the next DevBuf::alloc of a similar size (als_api.cu)
+    void release_to_cache();   // opt-in (CUMF_CACHE_MB > 0): keep the allocation for the next DevBuf::alloc of a similar size
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

@@ -196,11 +196,8 @@ int launch_gram_simt(const Chunk* d_chunks, int c0, int c1, const int* d_colidx,
     threads = ((threads + 31) / 32) * 32;
     if (threads < 32) threads = 32;
     const size_t smem = (size_t)(2 * KC * f + 2 * KC) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUMF_CUDA_TRY(cudaFuncSetAttribute(gram_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
+    // per device and cheap: set before every launch (f = 200 needs 51 KB, above the 48 KB default)
+    CUMF_CUDA_TRY(cudaFuncSetAttribute(gram_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     gram_simt_kernel<<<c1 - c0, threads, smem, st>>>(d_chunks, c0, d_colidx, d_rhs ? d_val : nullptr, d_factor, f,
                                                      lambda, out_row_base, d_tt, d_rhs, d_scratchA, d_scratchB);
     CUMF_CUDA_TRY(cudaGetLastError());

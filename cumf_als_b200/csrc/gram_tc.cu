@@ -997,6 +997,11 @@ struct TcWork {
     int factor_rows = 0;                // largest column id + 1 found in scanned_colidx[0, idx_span)
     DevBuf split_tab;                   // [factor_rows + 1][256] fp16, last row zero
     DevBuf max_idx;
+    // with a row-count hint the index scan runs asynchronously (no stream synchronisation on the hot path): its result
+    // lands in pinned host memory and is checked by the next launch of this plan
+    int* h_max_idx = nullptr;           // pinned
+    cudaEvent_t max_idx_ready = nullptr;
+    bool max_idx_pending = false;
     CUtensorMap split_map;              // 2-D view [factor_rows + 1][256] fp16, box {64, 1}, SWIZZLE_128B
 };
 
@@ -1061,7 +1066,10 @@ void tc_plan_destroy(TcWork* w, bool cache);
 int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
 // rows of the opposing factor, when the caller knows them: saves the index scan (and its stream synchronisation) of
 // the first direct-staging launch
-void tc_plan_set_factor_rows(TcWork* w, int rows) { if (w && rows > 0) w->hint_rows = rows; }
+// (also invalidates the cached scan: the next launch validates the index buffer it is given against `rows`)
+void tc_plan_set_factor_rows(TcWork* w, int rows) {
+    if (w && rows > 0) { w->hint_rows = rows; w->scanned_colidx = nullptr; }
+}
 int tc_sse_terms_per_cta() { return MAX_WG; }
 
 bool tc_path_supports(int f) {
@@ -1181,6 +1189,8 @@ void tc_plan_destroy(TcWork* w, bool cache) {
     rel(w->chunk_meta);
     rel(w->split_tab);
     rel(w->max_idx);
+    if (w->max_idx_ready) cudaEventDestroy(w->max_idx_ready);
+    if (w->h_max_idx) cudaFreeHost(w->h_max_idx);
     delete w;
 }
 
@@ -1208,9 +1218,31 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
     CUMF_CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     CUMF_REQUIRE((reinterpret_cast<uintptr_t>(d_factor) & 15u) == 0, "the factor matrix must be 16-byte aligned for TMA");
     if (w->direct) {
+        // a hinted plan's asynchronous index validation (below): an id beyond the table would be gathered as zeros
+        if (w->max_idx_pending && cudaEventQuery(w->max_idx_ready) == cudaSuccess) {
+            w->max_idx_pending = false;
+            if (*w->h_max_idx >= w->factor_rows) {
+                set_last_error("column id " + std::to_string(*w->h_max_idx) + " exceeds the opposing factor's " +
+                               std::to_string(w->factor_rows) + " rows (cumf_plan_set_factor_rows)");
+                w->scanned_colidx = nullptr;
+                return CUMF_EINVAL;
+            }
+        }
         // rows of the opposing factor the plan can gather = largest column id + 1 (one scan per plan and index array)
         if (w->scanned_colidx != d_colidx) {
             int rows = w->hint_rows;
+            if (rows > 0) {
+                // trust the hint for this launch, validate it behind the launch without synchronising
+                if (!w->max_idx.p) CUMF_TRY(w->max_idx.alloc(sizeof(int)));
+                if (!w->h_max_idx) CUMF_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&w->h_max_idx), sizeof(int), cudaHostAllocDefault));
+                if (!w->max_idx_ready) CUMF_CUDA_TRY(cudaEventCreateWithFlags(&w->max_idx_ready, cudaEventDisableTiming));
+                CUMF_CUDA_TRY(cudaMemsetAsync(w->max_idx.p, 0, sizeof(int), st));
+                max_index_kernel<<<592, 256, 0, st>>>(d_colidx, w->idx_span, w->max_idx.as<int>());
+                CUMF_CUDA_TRY(cudaMemcpyAsync(w->h_max_idx, w->max_idx.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CUMF_CUDA_TRY(cudaEventRecord(w->max_idx_ready, st));
+                w->max_idx_pending = true;
+                *launches += 1;
+            }
             if (rows <= 0) {
                 if (!w->max_idx.p) CUMF_TRY(w->max_idx.alloc(sizeof(int)));
                 CUMF_CUDA_TRY(cudaMemsetAsync(w->max_idx.p, 0, sizeof(int), st));

@@ -48,10 +48,12 @@ extern "C" int cumf_load_coo_bin(const char* dataFile, const char* rowFile, cons
 }
 
 // Factor initialisation loops of the reference's two front ends, on glibc rand() like they are.
-extern "C" void cumf_init_factors(float* thetaTHost, float* XTHost, int m, int n, int f, float scale, long seed) {
+// `scale` is a double like the literals 0.2 (main.cpp:75) and 0.1 (als_tf.cc:121): the product is formed in double and
+// rounded once, so the values are bit-identical to the front ends' own loops.
+extern "C" void cumf_init_factors(float* thetaTHost, float* XTHost, int m, int n, int f, double scale, long seed) {
     if (seed >= 0) srand((unsigned)seed);                                        // main.cpp:73; als_tf.cc never seeds
     if (thetaTHost)
-        for (long k = 0; k < (long)n * f; ++k) thetaTHost[k] = scale * ((float)rand() / (float)RAND_MAX);   // main.cpp:75, als_tf.cc:121
+        for (long k = 0; k < (long)n * f; ++k) thetaTHost[k] = (float)(scale * (double)((float)rand() / (float)RAND_MAX));   // main.cpp:75, als_tf.cc:121
     if (XTHost)
         for (long k = 0; k < (long)m * f; ++k) XTHost[k] = 0.f;                  // CG warm-starts from X: main.cpp:78, als_tf.cc:124
 }

@@ -55,8 +55,14 @@ int cumf_version(void);
  * iteration's test RMSE (als.cu:1018, 1034).  X_BATCH / THETA_BATCH are
  * accepted and advisory: results do not depend on them.
  * Environment knobs (all optional): CUMF_SOLVER=cg|lu, CUMF_PATH=auto|simt|tc,
- * CUMF_DEBUG=1 (prints the reference's -DDEBUG timing lines, als.cu:821-963),
- * CUMF_QUIET=1 (no stdout).                                                  */
+ * CUMF_DEBUG=1 (prints the reference's -DDEBUG line set -- "update X kernel
+ * run", "updateX solver run seconds", "update X run", the theta twins and
+ * "Calculate RMSE." (als.cu:821, 845, 850, 928, 957, 961-963) -- so that
+ * hermitiantime.sh / solvertime.sh / print-test-result.sh read our logs),
+ * CUMF_QUIET=1 (no stdout), CUMF_CACHE_MB=<n> (opt-in: keep up to n MiB of
+ * device buffers for the next call; default 0 = everything is freed on
+ * return like als.cu:1026-1033), CUMF_GPUS=<n> (row-shard the half-steps over
+ * n GPUs of this node inside the call, DEVICEID = first device).             */
 float cumf_doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
                  const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
                  const int* cooRowIndexHostPtr, float* thetaTHost, float* XTHost,
@@ -83,7 +89,7 @@ int cumf_load_coo_bin(const char* dataFile, const char* rowFile, const char* col
  *   thetaTHost[k] = scale * rand() / RAND_MAX  (glibc rand),  XTHost[k] = 0
  * main.cpp:72-78 uses srand(0) and scale 0.2; the TensorFlow op als_tf.cc:118-125 never
  * seeds and uses 0.1.  seed < 0: do not call srand.  NULL pointers are skipped.           */
-void cumf_init_factors(float* thetaTHost, float* XTHost, int m, int n, int f, float scale, long seed);
+void cumf_init_factors(float* thetaTHost, float* XTHost, int m, int n, int f, double scale, long seed);
 
 /* ---- b4: stage-level seams (device pointers) --------------------------------
  * cumf_gram replaces the launches

@@ -44,7 +44,8 @@ def test_init_factors_is_glibc_rand_like_the_front_ends():
     as_p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     lib.cumf_init_factors(as_p(th), as_p(x), m, n, f, 0.2, 0)                   # main.cpp:72-78: srand(0), 0.2 * rand()/RAND_MAX
     libc.srand(0)
-    want = np.array([np.float32(0.2) * (np.float32(libc.rand()) / np.float32(2147483647)) for _ in range(n * f)], np.float32)
+    # the front ends multiply by the DOUBLE literal and round once (main.cpp:75: 0.2*((float)rand()/(float)RAND_MAX))
+    want = np.array([np.float32(0.2 * float(np.float32(libc.rand()) / np.float32(2147483647))) for _ in range(n * f)], np.float32)
     assert np.array_equal(th, want) and not x.any()
     nxt = np.empty(n * f, np.float32)
     lib.cumf_init_factors(as_p(nxt), None, m, n, f, 0.1, -1)                   # als_tf.cc:118-123: no srand -> the sequence continues

@@ -33,7 +33,7 @@ struct Idx16 { int v[KT]; };
 // kg / ch: byte strides between 8-row k-groups and between 64-element chunks inside a stage
 __global__ void __launch_bounds__(128, 1)
 probe(const __grid_constant__ CUtensorMap tmap, Idx16 idx, int kg, int ch, uint64_t desc_tmpl, uint32_t idesc,
-      unsigned char* out_smem, float* out_d, int* flags) {
+      unsigned char* out_smem, float* out_d, int* flags, int a_off_bytes, int b_off_bytes) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* stage = smem_raw;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + STAGE_BYTES);
@@ -86,11 +86,14 @@ probe(const __grid_constant__ CUtensorMap tmap, Idx16 idx, int kg, int ch, uint6
 
     if (tid == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t d = desc_tmpl | (uint64_t)((smem_u32(stage) & 0x3FFFFu) >> 4);
+        // operand start addresses may sit inside a swizzle atom (multiples of 16 bytes = 8 MN elements): round 2 asks whether
+        // the hardware applies the 128B XOR pattern to the final address, as TMA does
+        const uint64_t da = desc_tmpl | (uint64_t)(((smem_u32(stage) + (uint32_t)a_off_bytes) & 0x3FFFFu) >> 4);
+        const uint64_t db = desc_tmpl | (uint64_t)(((smem_u32(stage) + (uint32_t)b_off_bytes) & 0x3FFFFu) >> 4);
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_base), "l"(d), "l"(d), "r"(idesc), "r"(0u) : "memory");
+            ::"r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(0u) : "memory");
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bars[1])) : "memory");
     }
     const bool mma_done = bounded_wait(&bars[1], 0);
@@ -122,6 +125,11 @@ int main(int argc, char** argv) {
     const int kg = arr == 0 ? 4096 : 1024, ch = arr == 0 ? 1024 : 2048;
     const int lbo = argc > 2 ? atoi(argv[2]) : ch;     // MN-major SW128: leading = next 64-element chunk
     const int sbo = argc > 3 ? atoi(argv[3]) : kg;     //                 stride  = next 8-row k-group
+    // round 2: operand windows that start inside a swizzle atom.  a_off / b_off = first MN element of the A / B operand
+    // (multiples of 8), n = UMMA N; A is 128 elements from a_off, B n elements from b_off (windows must end <= 256)
+    const int a_off = argc > 4 ? atoi(argv[4]) : 0;
+    const int b_off = argc > 5 ? atoi(argv[5]) : 0;
+    const int nn = argc > 6 ? atoi(argv[6]) : 256;
     const int rows = 64;
     std::vector<__half> h((size_t)rows * COLS);
     auto tval = [](int r, int c) { return (float)(((r * 7 + c * 3) % 17) - 8); };
@@ -163,10 +171,12 @@ int main(int argc, char** argv) {
     // MN-major SWIZZLE_128B descriptor: version 1 (bit 46), layout type 2 (bits 61..63)
     const uint64_t desc_tmpl = ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
     // c F32, a/b F16, both MN-major (bits 15, 16), N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    auto elem_bytes = [&](int e) { return (e >> 6) * ch + ((e & 63) >> 3) * 16; };
+    printf("  operand windows: A = MN [%d, %d), B = MN [%d, %d) (N = %d)\n", a_off, a_off + 128, b_off, b_off + nn, nn);
     const int smem = STAGE_BYTES + 128;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    probe<<<1, 128, smem>>>(tmap, idx, kg, ch, desc_tmpl, idesc, d_smem, d_out, d_flags);
+    probe<<<1, 128, smem>>>(tmap, idx, kg, ch, desc_tmpl, idesc, d_smem, d_out, d_flags, elem_bytes(a_off), elem_bytes(b_off));
     cudaError_t e = cudaDeviceSynchronize();
     int flags[4];
     cudaMemcpy(flags, d_flags, 16, cudaMemcpyDeviceToHost);
@@ -206,16 +216,16 @@ int main(int argc, char** argv) {
         std::vector<float> o((size_t)128 * COLS);
         cudaMemcpy(o.data(), d_out, o.size() * 4, cudaMemcpyDeviceToHost);
         int bad = 0;
-        for (int i = 0; i < 128; ++i)
-            for (int j = 0; j < COLS; ++j) {
+        for (int i = 0; i < 128 && a_off + i < COLS; ++i)
+            for (int j = 0; j < nn && b_off + j < COLS; ++j) {
                 float acc = 0.f;
-                for (int k = 0; k < KT; ++k) acc += g[(size_t)k * COLS + i] * g[(size_t)k * COLS + j];
+                for (int k = 0; k < KT; ++k) acc += g[(size_t)k * COLS + a_off + i] * g[(size_t)k * COLS + b_off + j];
                 if (o[(size_t)i * COLS + j] != acc) {
                     if (bad < 6) printf("  D mismatch i=%d j=%d got %g want %g\n", i, j, o[(size_t)i * COLS + j], acc);
                     ++bad;
                 }
             }
-        printf("  MMA result: %d mismatches of %d  -> %s\n", bad, 128 * COLS, bad == 0 ? "DESCRIPTOR OK" : "descriptor wrong");
+        printf("  MMA result: %d mismatches of %d  -> %s\n", bad, 128 * nn, bad == 0 ? "DESCRIPTOR OK" : "descriptor wrong");
     }
     return 0;
 }
