@@ -129,9 +129,38 @@ void tc_plan_destroy(TcWork* w, bool cache = false);
 int tc_plan_grid(const TcWork* w);
 void tc_plan_set_factor_rows(TcWork* w, int rows);
 int tc_sse_terms_per_cta();
+// optional extras of the generic-f kernel: store mode (unsplit rows written as [A + lambda n I | b] to d_tt / d_rhs instead of
+// being solved) and replicas of the output factor on peer GPUs that receive every solved row from the solver epilogue
+struct TcExtra {
+    float* d_tt = nullptr; float* d_rhs = nullptr; int tt_row_base = 0;
+    float* const* peer_out = nullptr; int n_peer_out = 0;
+};
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,
                      const int* d_colidx, const float* d_val, const float* d_factor, float* d_out,
                      int f, float lambda, float cg_iter, float* d_scratchA, float* d_scratchB,
-                     cudaStream_t st, int* launches, double* d_sse_terms = nullptr);
+                     cudaStream_t st, int* launches, double* d_sse_terms = nullptr, const TcExtra* extra = nullptr);
+int tc_plan_impl(const TcWork* w);
+
+// Generic-f fused kernel (gram_tc2.cuh / gram_tc2.cu): plan-time geometry of the variant that will run, and one half-step.
+struct Tc2Info { int krows, sub, nbuf, nsys, tab_cols, nb; };
+bool tc2_plan_info(int f, bool sym, Tc2Info* out);
+int tc2_fill_stage_table(const Chunk* d_chunks, const int* d_stage_base, const int* d_chunk_meta, int nchunks, void* d_table,
+                         const Tc2Info& info, cudaStream_t st);
+struct Tc2Launch {
+    int f = 0; bool sym = false; int grid = 0;
+    const Chunk* d_chunks = nullptr; const int* d_chunk_meta = nullptr; const int* d_cta_ptr = nullptr;
+    const void* d_stage_tab = nullptr; const int* d_cta_stage_ptr = nullptr;
+    const int* d_colidx = nullptr; const float* d_val = nullptr; long long val_span = 0;
+    const float* d_factor = nullptr; int factor_rows = 0;
+    void* d_table = nullptr; const void* tensor_map = nullptr;      // fp16 split table [factor_rows + 1][tab_cols] and its CUtensorMap
+    unsigned* d_absmax = nullptr; float* d_scales = nullptr;        // 2 words / 4 floats of per-launch scale state
+    float* d_out = nullptr; float* const* peer_out = nullptr; int n_peer_out = 0;
+    float lambda = 0.f, cg_iter = 0.f;
+    float* d_scratchA = nullptr; float* d_scratchB = nullptr;
+    float* d_tt = nullptr; float* d_rhs = nullptr; int tt_row_base = 0;
+    double* d_sse_terms = nullptr;
+};
+int tc2_update(const Tc2Launch& a, cudaStream_t st, int* launches);
+int tc2_sse_terms_per_cta();
 
 }  // namespace cumf

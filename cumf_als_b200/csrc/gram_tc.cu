@@ -111,6 +111,9 @@ template <bool kSym, bool kDirect, int kRows> struct Cfg {
     static_assert(kGroups >= 1 && kGroups <= 4, "k-groups per stage (2-bit fields in the stage flags)");
 };
 constexpr int MAX_WG = 3;
+#ifndef CUMF_TC_IMPL_DEFAULT_F100
+#define CUMF_TC_IMPL_DEFAULT_F100 1       // f = 100 without CUMF_TC_IMPL: the kernel of this file (1) or gram_tc2.cuh (2)
+#endif
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 // "direct" staging (kDirect): the opposing factor is pre-split once per half-step into an fp16 table
 //   row j = [ hi_j (100) | 0 (12) | r slots (2) | 0 (14) | lo'_j (100) | 0 (28) ]      256 halfs = 512 B
@@ -999,6 +1002,10 @@ struct TcWork {
     DevBuf max_idx;
     // with a row-count hint the index scan runs asynchronously (no stream synchronisation on the hot path): its result
     // lands in pinned host memory and is checked by the next launch of this plan
+    // generic-f kernel (gram_tc2.cuh): impl == 2
+    int impl = 1, f = F;
+    Tc2Info info2{};
+    DevBuf absmax, scales;              // per-launch scale state of the generic-f kernel
     int* h_max_idx = nullptr;           // pinned
     cudaEvent_t max_idx_ready = nullptr;
     bool max_idx_pending = false;
@@ -1025,11 +1032,11 @@ static EncodeFn tensor_map_encoder() {
 
 // pre-split fp16 table [rows][256]: tile::gather4 fetches four {64, 1} boxes (one 128-byte swizzle line per row);
 // coordinates beyond `rows` are out of bounds and read as zero
-static int encode_split_map(CUtensorMap* map, const void* d_table, long long rows) {
+static int encode_split_map(CUtensorMap* map, const void* d_table, long long rows, int cols = SPLIT_COLS) {
     EncodeFn encode = tensor_map_encoder();
     if (!encode) return CUMF_ECUDA;
-    const cuuint64_t gdim[2] = {(cuuint64_t)SPLIT_COLS, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)SPLIT_ROW_BYTES};
+    const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
     const cuuint32_t box[2] = {(cuuint32_t)SPLIT_CHUNK, 1u};
     const cuuint32_t estride[2] = {1u, 1u};
     const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(d_table), gdim, gstride, box, estride,
@@ -1064,6 +1071,7 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
 void tc_plan_destroy(TcWork* w, bool cache);
 
 int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
+int tc_plan_impl(const TcWork* w) { return w ? w->impl : 0; }
 // rows of the opposing factor, when the caller knows them: saves the index scan (and its stream synchronisation) of
 // the first direct-staging launch
 // (also invalidates the cached scan: the next launch validates the index buffer it is given against `rows`)
@@ -1075,14 +1083,24 @@ int tc_sse_terms_per_cta() { return MAX_WG; }
 bool tc_path_supports(int f) {
     const char* off = getenv("CUMF_DISABLE_TC");
     if (off && *off == '1') return false;
-    return f == F;
+    return f >= 10 && f <= 200 && f % 10 == 0;
+}
+
+// which fused kernel serves rank f: gram_tc2.cuh (generic f, one accumulator) unless CUMF_TC_IMPL=1 asks for the round-1
+// f = 100 kernel of this file
+static int tc_impl_for(int f) {
+    const char* e = getenv("CUMF_TC_IMPL");
+    if (f == F && e && *e == '1') return 1;
+    if (f == F && !(e && *e)) return CUMF_TC_IMPL_DEFAULT_F100;
+    return 2;
 }
 
 int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* d_chunks, const std::vector<SplitRow>&, int, int f) {
-    if (f != F) {
-        set_last_error("fused tcgen05 kernel handles f = 100 only");
+    if (!tc_path_supports(f)) {
+        set_last_error("the fused tcgen05 kernels handle f = 10, 20, ..., 200");
         return CUMF_EUNSUPPORTED;
     }
+    const int impl = tc_impl_for(f);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1091,12 +1109,29 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     if (grid < 1) grid = 1;
     const int n = (int)chunks.size();
     if (grid > n) grid = std::max(1, n);
-    // staging variant: "direct" (pre-split fp16 table gathered straight into the UMMA operand, 32-rating stages) or the
+    // long chunks -> the symmetric variant (the tensor core forms half of the cross term, the epilogue transposes): pays from
+    // ~1024 ratings per chunk on average; measured on Netflix (round 1): X side (5.6 k ratings/chunk) 9.6 -> 8.6 ms, theta side
+    // (206 ratings/chunk) 14.8 -> 16.2 ms
+    long long total_ratings = 0;
+    for (int c = 0; c < n; ++c) total_ratings += chunks[c].end - chunks[c].begin;
+    bool sym = false;
+    {
+        const char* m = getenv("CUMF_TC_SYM");
+        sym = (m && *m) ? (*m == '1') : (n > 0 && total_ratings >= 1024LL * n);
+        if (impl == 2 && f > F) sym = false;          // the generic kernel's symmetric variant exists for f <= 100
+    }
+    Tc2Info info2{};
+    if (impl == 2 && !tc2_plan_info(f, sym, &info2)) {
+        set_last_error("no generic-f kernel variant for f = " + std::to_string(f));
+        return CUMF_EUNSUPPORTED;
+    }
+    // staging variant of the f = 100 kernel: "direct" (pre-split fp16 table gathered straight into the UMMA operand) or the
     // fp32 ring + in-kernel conversion (16-rating stages)
     const char* denv = getenv("CUMF_TC_DIRECT");
-    const bool direct = !(denv && *denv == '0');        // default; CUMF_TC_DIRECT=0 selects the fp32 staging ring
+    const bool direct = impl == 2 || !(denv && *denv == '0');        // default; CUMF_TC_DIRECT=0 selects the fp32 staging ring
     const char* renv = getenv("CUMF_TC_STAGE_ROWS");
-    const int kt = direct ? ((renv && atoi(renv) == 32) ? 32 : 64) : KT, sub = 256 / kt;      // default 64 (measured: 32 is 3-5 % slower)
+    const int kt = impl == 2 ? info2.krows : (direct ? ((renv && atoi(renv) == 32) ? 32 : 64) : KT);      // default 64 (measured: 32 is 3-5 % slower)
+    const int sub = 256 / kt;
     // contiguous, cost-balanced partition of the (row-ordered) chunk list: cost = MMA k-steps
     // plus a per-chunk epilogue/solve term, so every CTA streams one contiguous rating range.
     const char* rc_env = getenv("CUMF_TC_ROW_COST");
@@ -1133,16 +1168,14 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     w->nchunks = n;
     w->direct = direct;
     w->stage_rows = kt;
+    w->impl = impl;
+    w->f = f;
+    w->info2 = info2;
+    w->sym = sym;
     for (int c = 0; c < n; ++c) w->idx_span = std::max<long long>(w->idx_span, chunks[c].end);
-    {   // per-chunk epilogue cost (transpose) vs per-k-step MMA saving: the symmetric mode pays from ~32 k-steps per chunk;
-        // measured on Netflix: X side (348 k-steps/chunk) 9.6 -> 8.6 ms, theta side (13 k-steps/chunk) 14.8 -> 16.2 ms
-        const char* m = getenv("CUMF_TC_SYM");
-        const long long sym_min_ratings = 1024;      // per chunk on average (staged ratings: 64 k-steps of 16)
-        w->sym = (m && *m) ? (*m == '1') : (n > 0 && (long long)stage_base[n] * kt >= sym_min_ratings * n);
-    }
     // what the MMA issuer would otherwise count: first tile of every chunk within its CTA, chunk parity within its CTA
     std::vector<int> chunk_meta(std::max(n, 1), 0);
-    const int n_wg = (direct && !w->sym) ? 3 : 2;       // Cfg<>::kWG of the variant that will run
+    const int n_wg = impl == 2 ? info2.nsys : ((direct && !w->sym) ? 3 : 2);       // systems in flight of the variant that will run
     static_assert(Cfg<false, true, 32>::kWG == 3 && Cfg<false, true, 64>::kWG == 3 && Cfg<true, true, 32>::kWG == 2 &&
                   Cfg<true, true, 64>::kWG == 2 && Cfg<true, false, 16>::kWG == 2 && Cfg<false, false, 16>::kWG == 2, "solver warpgroups");
     for (int b = 0; b < grid; ++b) {
@@ -1167,8 +1200,12 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
         rc = CUMF_ECUDA;
     }
     if (rc == CUMF_OK && n > 0) {
-        auto fill = kt == 64 ? fill_stage_table_kernel<64, 4> : (kt == 32 ? fill_stage_table_kernel<32, 8> : fill_stage_table_kernel<KT, SUB_STEPS>);
-        fill<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n, w->stage_tab.as<StageDesc>());
+        if (impl == 2) {
+            rc = tc2_fill_stage_table(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n, w->stage_tab.p, info2, 0);
+        } else {
+            auto fill = kt == 64 ? fill_stage_table_kernel<64, 4> : (kt == 32 ? fill_stage_table_kernel<32, 8> : fill_stage_table_kernel<KT, SUB_STEPS>);
+            fill<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n, w->stage_tab.as<StageDesc>());
+        }
         if (cudaStreamSynchronize(0) != cudaSuccess) {      // not the device: uploads may be running on another stream
             set_last_error(std::string("tc_plan_create: stage table: ") + cudaGetErrorString(cudaGetLastError()));
             rc = CUMF_ECUDA;
@@ -1189,6 +1226,8 @@ void tc_plan_destroy(TcWork* w, bool cache) {
     rel(w->chunk_meta);
     rel(w->split_tab);
     rel(w->max_idx);
+    rel(w->absmax);
+    rel(w->scales);
     if (w->max_idx_ready) cudaEventDestroy(w->max_idx_ready);
     if (w->h_max_idx) cudaFreeHost(w->h_max_idx);
     delete w;
@@ -1196,12 +1235,16 @@ void tc_plan_destroy(TcWork* w, bool cache) {
 
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d_colidx, const float* d_val,
                      const float* d_factor, float* d_out, int f, float lambda, float cg_iter, float* d_scratchA,
-                     float* d_scratchB, cudaStream_t st, int* launches, double* d_sse_terms) {
-    if (!w || f != F) {
+                     float* d_scratchB, cudaStream_t st, int* launches, double* d_sse_terms, const TcExtra* extra) {
+    if (!w || f != w->f) {
         set_last_error("tc_update_factor: bad plan");
         return CUMF_EINVAL;
     }
     if (nchunks == 0) return CUMF_OK;
+    if (w->impl != 2 && extra && (extra->d_tt || extra->n_peer_out > 0)) {
+        set_last_error("tc_update_factor: direct stores / peer outputs need the generic-f kernel (CUMF_TC_IMPL=2)");
+        return CUMF_EUNSUPPORTED;
+    }
     // kernel variant: (long rows -> symmetric single-MMA mode) x (staging, stage size)
     using KernelFn = void (*)(const Chunk*, const int*, const StageDesc*, const int*, const int*, const float*, const CUtensorMap, float*,
                               float, float, float*, float*, uint64_t, double*, int);
@@ -1254,12 +1297,32 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
                 rows = h_max + 1;
             }
             if (rows != w->factor_rows || !w->split_tab.p) {
+                const int cols = w->impl == 2 ? w->info2.tab_cols : SPLIT_COLS;
                 w->split_tab.release();
-                CUMF_TRY(w->split_tab.alloc((size_t)(rows + 1) * SPLIT_ROW_BYTES));
-                CUMF_TRY(encode_split_map(&w->split_map, w->split_tab.p, (long long)rows + 1));
+                CUMF_TRY(w->split_tab.alloc((size_t)(rows + 1) * cols * 2));
+                CUMF_TRY(encode_split_map(&w->split_map, w->split_tab.p, (long long)rows + 1, cols));
                 w->factor_rows = rows;
             }
             w->scanned_colidx = d_colidx;
+        }
+        if (w->impl == 2) {
+            if (!w->absmax.p) CUMF_TRY(w->absmax.alloc(4 * sizeof(unsigned)));
+            if (!w->scales.p) CUMF_TRY(w->scales.alloc(4 * sizeof(float)));
+            Tc2Launch a;
+            a.f = f; a.sym = w->sym; a.grid = w->grid;
+            a.d_chunks = d_chunks; a.d_chunk_meta = w->chunk_meta.as<int>(); a.d_cta_ptr = w->cta_ptr.as<int>();
+            a.d_stage_tab = w->stage_tab.p; a.d_cta_stage_ptr = w->cta_stage_ptr.as<int>();
+            a.d_colidx = d_colidx; a.d_val = d_val; a.val_span = w->idx_span;
+            a.d_factor = d_factor; a.factor_rows = w->factor_rows;
+            a.d_table = w->split_tab.p; a.tensor_map = &w->split_map;
+            a.d_absmax = w->absmax.as<unsigned>(); a.d_scales = w->scales.as<float>();
+            a.d_out = d_out; a.lambda = lambda; a.cg_iter = cg_iter;
+            a.d_scratchA = d_scratchA; a.d_scratchB = d_scratchB; a.d_sse_terms = d_sse_terms;
+            if (extra) {
+                a.d_tt = extra->d_tt; a.d_rhs = extra->d_rhs; a.tt_row_base = extra->tt_row_base;
+                a.peer_out = extra->peer_out; a.n_peer_out = extra->n_peer_out;
+            }
+            return tc2_update(a, st, launches);
         }
         const size_t pieces = (size_t)(w->factor_rows + 1) * 32;
         split_factor_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(d_factor, w->factor_rows, w->split_tab.as<uint4>());
