@@ -3,10 +3,6 @@
 set -x
 OUT=gpurun_out/r2b
 mkdir -p $OUT
-for f in 100 10 60 120 130 200; do
-  timeout 120 python tools/tc2_bringup.py $f > $OUT/bringup_f$f.log 2>&1
-done
-timeout 120 python tools/tc2_bringup.py 100 1 > $OUT/bringup_f100_sym.log 2>&1
 for t in test_tc2_gram_vs_oracle test_tc2_gram_small_and_large_values test_tc2_half_step_vs_simt test_tc2_half_step_sym_variant_vs_simt \
          test_tc2_deterministic_and_partial_row_range test_tc2_doals_vs_oracle_and_simt test_tc2_plan_gram_ranges_vs_oracle; do
   timeout 600 python -m pytest tests/test_gpu_generic_f.py -q -s -m gpu -k $t > $OUT/pytest_$t.log 2>&1
@@ -16,6 +12,5 @@ CUMF_TC_IMPL=2 timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-c
 timeout 600 python bench.py --workload netflix_f200 --steps 5 --warmup 2 --no-cpu > $OUT/bench_f200.json 2> $OUT/bench_f200.err
 timeout 600 python bench.py --workload ml10m --steps 10 --warmup 3 --no-cpu > $OUT/bench_ml10m.json 2> $OUT/bench_ml10m.err
 CUMF_TC_IMPL=2 timeout 600 python bench.py --workload yahoo --steps 5 --warmup 2 --no-cpu --no-e2e > $OUT/bench_yahoo_v2.json 2> $OUT/bench_yahoo_v2.err
-tail -3 $OUT/bringup_*.log
 tail -4 $OUT/pytest_*.log
 cat $OUT/*.json
