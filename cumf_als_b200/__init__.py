@@ -7,6 +7,7 @@ There is no CPU or PyTorch fallback: importing the bindings without the built
 library, or calling them without a B200, raises.
 """
 from .api import (  # noqa: F401
+    AlsGroup,
     AlsSolver,
     CumfError,
     PATH_AUTO,
@@ -26,6 +27,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "AlsSolver", "CumfError", "Plan", "PATH_AUTO", "PATH_SIMT", "PATH_TC", "SOLVER_CG", "SOLVER_LU",
+    "AlsGroup", "AlsSolver", "CumfError", "Plan", "PATH_AUTO", "PATH_SIMT", "PATH_TC", "SOLVER_CG", "SOLVER_LU",
     "cg", "do_als", "gram", "library_path", "load_library", "lu", "rmse", "update_factor",
 ]

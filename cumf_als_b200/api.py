@@ -76,6 +76,20 @@ SIGNATURES = {
     "cumf_als_sse": (C.c_int, [_vp, _f64p, _f64p, _vp]),
     "cumf_als_iterate": (C.c_int, [_vp, C.c_int, _f32p, _vp]),
     "cumf_als_timers": (C.c_int, [_vp, _f64p, C.c_int]),
+    "cumf_als_ipc_blob_bytes": (C.c_int, []),
+    "cumf_als_ipc_export": (C.c_int, [_vp, _vp]),
+    "cumf_als_ipc_import": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "cumf_als_peer_barrier": (C.c_int, [_vp, _vp]),
+    "cumf_group_create": (C.c_int, [C.POINTER(_vp)] + [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_long, C.c_long,
+                                                                     C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cumf_group_destroy": (C.c_int, [_vp]),
+    "cumf_group_size": (C.c_int, [_vp]),
+    "cumf_group_shard": (_vp, [_vp, C.c_int]),
+    "cumf_group_set_factors": (C.c_int, [_vp, _vp, _vp]),
+    "cumf_group_get_factors": (C.c_int, [_vp, _vp, _vp]),
+    "cumf_group_iterate": (C.c_int, [_vp, C.c_int, _f32p]),
+    "cumf_group_collect_train_sse": (C.c_int, [_vp, C.c_int]),
+    "cumf_group_sse": (C.c_int, [_vp, _f64p, _f64p]),
 }
 # C++-linkage symbols the reference's main.cpp / als_tf.cc bind (als.h:676-681, host_utilities.h:31-40)
 MANGLED_SYMBOLS = [
@@ -343,9 +357,85 @@ class AlsSolver:
         keys = ["x_ms", "theta_ms", "gram_x_ms", "gram_theta_ms", "launches", "iterations"]
         return dict(zip(keys, list(out)))
 
+    # ---- multi-GPU, one process per GPU: connect the ranks' replicas through CUDA IPC (include/cumf_als.h) ----
+    def ipc_export(self) -> bytes:
+        n = load_library().cumf_als_ipc_blob_bytes()
+        buf = C.create_string_buffer(n)
+        _check(load_library().cumf_als_ipc_export(self._h, buf), "cumf_als_ipc_export")
+        return buf.raw
+
+    def ipc_import(self, blobs, rank: int) -> None:
+        """`blobs`: every rank's ipc_export() in rank order.  Afterwards update_x / update_theta also write the peers'
+        replicas and iterate() ends every half-step with the device-side barrier."""
+        joined = b"".join(blobs)
+        _check(load_library().cumf_als_ipc_import(self._h, joined, len(blobs), rank), "cumf_als_ipc_import")
+
+    def peer_barrier(self, stream=None) -> None:
+        _check(load_library().cumf_als_peer_barrier(self._h, _stream_ptr(stream)), "cumf_als_peer_barrier")
+
     def close(self) -> None:
         if self._h:
             load_library().cumf_als_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class AlsGroup:
+    """cumf_als_group: n row shards on n devices of this node, driven from one process (what cumf_doALS does under
+    CUMF_GPUS=n).  Same host arrays as AlsSolver; factors are full replicas on every device."""
+
+    def __init__(self, csr_indptr, csr_indices, csr_data, csc_indices, csc_indptr, csc_data, coo_row,
+                 test_row, test_col, test_val, m: int, n: int, f: int, lam: float, n_devices: int, first_device: int = 0,
+                 solver: int = SOLVER_CG, path: int = PATH_AUTO):
+        lib = load_library()
+        self.m, self.n, self.f, self.lam = m, n, f, lam
+        self.nnz = int(np.asarray(csr_indptr)[-1])
+        self.nnz_test = 0 if test_val is None else int(np.asarray(test_val).size)
+        arrs = [
+            _host(csr_indptr, np.int32), _host(csr_indices, np.int32), _host(csr_data, np.float32),
+            _host(csc_indices, np.int32), _host(csc_indptr, np.int32), _host(csc_data, np.float32),
+            None if coo_row is None else _host(coo_row, np.int32),
+            None if test_row is None else _host(test_row, np.int32),
+            None if test_col is None else _host(test_col, np.int32),
+            None if test_val is None else _host(test_val, np.float32),
+        ]
+        self._h = _vp()
+        _check(lib.cumf_group_create(C.byref(self._h), *[_hp(a) for a in arrs], m, n, f, self.nnz, self.nnz_test, lam,
+                                     first_device, n_devices, solver, path), "cumf_group_create")
+
+    def set_factors(self, thetaT, XT) -> None:
+        t, x = _host(thetaT, np.float32), _host(XT, np.float32)
+        _check(load_library().cumf_group_set_factors(self._h, _hp(t), _hp(x)), "cumf_group_set_factors")
+
+    def get_factors(self):
+        t = np.empty((self.n, self.f), np.float32)
+        x = np.empty((self.m, self.f), np.float32)
+        _check(load_library().cumf_group_get_factors(self._h, _hp(t), _hp(x)), "cumf_group_get_factors")
+        return t, x
+
+    def collect_train_sse(self, on: bool = True) -> bool:
+        return load_library().cumf_group_collect_train_sse(self._h, int(on)) == 1
+
+    def iterate(self, iters: int = 1) -> float:
+        ms = C.c_float(0)
+        _check(load_library().cumf_group_iterate(self._h, iters, C.byref(ms)), "cumf_group_iterate")
+        return ms.value
+
+    def rmse(self):
+        a, b = C.c_double(0), C.c_double(0)
+        _check(load_library().cumf_group_sse(self._h, C.byref(a), C.byref(b)), "cumf_group_sse")
+        f32 = np.float32
+        return (float(np.sqrt(f32(a.value) / f32(self.nnz))) if self.nnz else 0.0,
+                float(np.sqrt(f32(b.value) / f32(self.nnz_test))) if self.nnz_test else 0.0)
+
+    def close(self) -> None:
+        if self._h:
+            load_library().cumf_group_destroy(self._h)
             self._h = _vp()
 
     def __del__(self):

@@ -13,7 +13,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include "common.cuh"
 
@@ -124,6 +126,30 @@ void staging_reset() {
     if (!stage_alive()) return;
     for (unsigned char* p : g_stage_retired) cudaFreeHost(p);
     g_stage_retired.clear();
+}
+
+static std::mutex g_stage_mutex;
+StagingSection::StagingSection() {
+    g_stage_mutex.lock();
+    held = true;
+    staging_reset();
+}
+int StagingSection::finish(cudaStream_t st) {
+    if (!held) return CUMF_OK;
+    const cudaError_t e = cudaStreamSynchronize(st);
+    held = false;
+    g_stage_mutex.unlock();
+    if (e != cudaSuccess) {
+        set_last_error(std::string("plan upload: ") + cudaGetErrorString(e));
+        return CUMF_ECUDA;
+    }
+    return CUMF_OK;
+}
+StagingSection::~StagingSection() {
+    if (held) {
+        cudaStreamSynchronize(last);
+        g_stage_mutex.unlock();
+    }
 }
 
 static void staging_release() {
@@ -327,10 +353,6 @@ static int plan_create_core(cumf_plan** out, const long long* h_begin, const lon
     CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
     CUMF_TRY(check_f(f));
     CUMF_TRY(check_device());
-    // plan metadata goes to the device through the pinned staging arena (one plan at a time)
-    static std::mutex plan_mutex;
-    std::lock_guard<std::mutex> plan_lock(plan_mutex);
-    staging_reset();
     cumf_plan* p = new cumf_plan();
     p->rows = rows; p->row_begin = row_begin; p->row_end = row_end; p->f = f;
     if (path == CUMF_PATH_AUTO) path = tc_path_supports(f) ? CUMF_PATH_TC : CUMF_PATH_SIMT;
@@ -379,11 +401,17 @@ static int plan_create_core(cumf_plan** out, const long long* h_begin, const lon
     p->row_chunk_ptr[owned] = (int)p->chunks.size();
 
     int rc = p->d_chunks.alloc(sizeof(Chunk) * std::max<size_t>(1, p->chunks.size()));
-    if (rc == CUMF_OK && !p->chunks.empty())
-        rc = upload_via_kernel(p->d_chunks.p, p->chunks.data(), sizeof(Chunk) * p->chunks.size(), 0);
     if (rc == CUMF_OK) rc = p->d_splits.alloc(sizeof(SplitRow) * std::max<size_t>(1, p->splits.size()));
-    if (rc == CUMF_OK && !p->splits.empty())
-        rc = upload_via_kernel(p->d_splits.p, p->splits.data(), sizeof(SplitRow) * p->splits.size(), 0);
+    if (rc == CUMF_OK) {
+        // plan metadata goes to the device through the pinned staging arena (process-wide, one section at a time)
+        StagingSection sec;
+        if (!p->chunks.empty())
+            rc = upload_via_kernel(p->d_chunks.p, p->chunks.data(), sizeof(Chunk) * p->chunks.size(), 0);
+        if (rc == CUMF_OK && !p->splits.empty())
+            rc = upload_via_kernel(p->d_splits.p, p->splits.data(), sizeof(SplitRow) * p->splits.size(), 0);
+        const int rc2 = sec.finish(0);
+        if (rc == CUMF_OK) rc = rc2;
+    }
     const size_t ff = (size_t)f * f;
     if (rc == CUMF_OK && slot > 0) {
         rc = p->scratchA.alloc(sizeof(float) * ff * slot);
@@ -405,11 +433,6 @@ static int plan_create_core(cumf_plan** out, const long long* h_begin, const lon
             rc = p->tt.alloc(sizeof(float) * ff * p->batch_rows);
             if (rc == CUMF_OK) rc = p->rhs.alloc(sizeof(float) * (size_t)f * p->batch_rows);
         }
-    }
-    // the staged copies (legacy default stream) must have read the arena before the next plan recycles it
-    if (rc == CUMF_OK && cudaStreamSynchronize(0) != cudaSuccess) {
-        set_last_error(std::string("plan upload: ") + cudaGetErrorString(cudaGetLastError()));
-        rc = CUMF_ECUDA;
     }
     if (rc != CUMF_OK) {
         if (rc == CUMF_ECUDA && g_last_error.empty()) set_last_error("plan upload failed");
@@ -517,21 +540,36 @@ static double plan_collect_kernel_ms(cumf_plan* p) {
     return p->kernel_ms_total;
 }
 
+// x = d_out + row_base * f: the batch's rows of the factor; peers (optional) receive the same rows
 static int solve_batch(float* tt, float* x, float* rhs, int batch, int f, int solver, float cg_iter, cudaStream_t st,
-                       int* launches) {
+                       int* launches, const PeerOut* peers = nullptr, int row_base = 0) {
     if (solver == CUMF_SOLVER_LU) {
         CUMF_TRY(launch_lu(tt, x, rhs, batch, f, st));
         *launches += 1;   // our pointer-fill kernel; the cuBLAS kernels are library code
+        if (peers)        // oracle mode: plain peer copies of the solved block
+            for (int k = 0; k < peers->n; ++k)
+                CUMF_CUDA_TRY(cudaMemcpyAsync(peers->p[k] + (size_t)row_base * f, x, sizeof(float) * (size_t)batch * f, cudaMemcpyDefault, st));
     } else {
-        CUMF_TRY(launch_cg(tt, x, rhs, batch, f, cg_iter, nullptr, st));
+        CUMF_TRY(launch_cg(tt, x, rhs, batch, f, cg_iter, nullptr, st, 0.f, nullptr, peers, row_base));
         *launches += 1;
     }
     return CUMF_OK;
 }
 
+static int update_factor_impl(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
+                              float* d_out, float lambda, int solver, float cgIter, void* stream, const PeerOut* peers);
+
 extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
                                   float* d_out, float lambda, int solver, float cgIter, void* stream) {
+    return update_factor_impl(p, d_colidx, d_val, d_factor, d_out, lambda, solver, cgIter, stream, nullptr);
+}
+
+// peers (optional): replicas of d_out on other GPUs that receive every updated row (the row-block exchange of the sharded
+// half-step, done by the solver epilogues themselves)
+static int update_factor_impl(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
+                              float* d_out, float lambda, int solver, float cgIter, void* stream, const PeerOut* peers) {
     CUMF_REQUIRE(p && d_colidx && d_val && d_factor && d_out, "null pointer");
+    if (peers && peers->n == 0) peers = nullptr;
     CUMF_REQUIRE(solver == CUMF_SOLVER_CG || solver == CUMF_SOLVER_LU, "unknown solver");
     cudaStream_t st = (cudaStream_t)stream;
     const int f = p->f;
@@ -555,15 +593,17 @@ extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float
         }
         cudaEvent_t e0, e1;
         plan_time_begin(p, st, &e0, &e1);
+        const TcExtra extra = tc_extra_from(peers);
         CUMF_TRY(tc_update_factor(p->tc, d_chunks, (int)p->chunks.size(), d_colidx, d_val, d_factor, d_out,
-                                  f, lambda, cgIter, p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches, terms));
+                                  f, lambda, cgIter, p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches, terms,
+                                  peers ? &extra : nullptr));
         plan_time_end(p, st, e0, e1);
         // rows that were split across CTAs: reduce their partials into a compact batch, solve it
         if (ns > 0) {
             CUMF_TRY(launch_split_reduce(d_splits, 0, ns, f, lambda, /*compact=*/1, 0, p->tt.as<float>(),
                                          p->rhs.as<float>(), p->scratchA.as<float>(), p->scratchB.as<float>(), st));
             CUMF_TRY(launch_cg(p->tt.as<float>(), d_out, p->rhs.as<float>(), ns, f, cgIter, d_splits, st, lambda,
-                               terms ? terms + tc_sse_terms_per_cta() * tc_plan_grid(p->tc) : nullptr));
+                               terms ? terms + tc_sse_terms_per_cta() * tc_plan_grid(p->tc) : nullptr, peers));
             launches += 2;
         }
         p->sse_terms_valid = (terms != nullptr);
@@ -599,7 +639,7 @@ extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float
         }
         s_lo = s_hi;
         CUMF_TRY(solve_batch(p->tt.as<float>(), d_out + (size_t)row_base * f, p->rhs.as<float>(), b1 - b0, f, solver,
-                             cgIter, st, &launches));
+                             cgIter, st, &launches, peers, row_base));
     }
     p->last_launches = launches;
     return CUMF_OK;
@@ -720,7 +760,7 @@ struct cumf_als_solver {
     DevBuf csr_col, csr_val, csc_row, csc_val;
     DevBuf coo_row;                     // cooRowIndex for the owned CSR slice (train RMSE pairing, als.cu:979-980)
     DevBuf test_row, test_col, test_val;
-    long train_cnt = 0, test_cnt = 0;
+    long train_cnt = 0, test_cnt = 0, csc_cnt = 0;
     DevBuf theta, x;                    // full replicas
     DevBuf sse, partials;
     // uploads run on their own (non-blocking) stream; the first use of each group waits on its event, so the
@@ -740,6 +780,16 @@ struct cumf_als_solver {
     bool prep_coo = false, prep_r2 = false;
     cumf_plan* px = nullptr;
     cumf_plan* pt = nullptr;
+    // multi-GPU (row sharding): this shard is rank `rank` of `nranks`; peer_x / peer_theta are the other
+    // ranks' factor replicas (peer access in one process, CUDA IPC across processes), flags / peer_flags the epoch words of
+    // the device-side barrier that ends every half-step
+    int rank = 0, nranks = 1;
+    PeerOut peer_x{}, peer_theta{};
+    DevBuf flags;                                   // [8] unsigned long long, written by the peers
+    unsigned long long* peer_flags[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [r] = rank r's flags (own: local)
+    unsigned long long epoch = 0;
+    std::vector<void*> ipc_opened;
+    cudaStream_t run_stream = nullptr;              // a group gives every shard its own stream (two shards may share a device in tests)
     // timers
     double ms_x = 0, ms_theta = 0;
     long launches = 0, iterations = 0;
@@ -750,6 +800,9 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     cudaSetDevice(s->device);
     if (s->up_stream) cudaStreamSynchronize(s->up_stream);
     cudaDeviceSynchronize();            // what cudaFree would do implicitly: nothing may still use the buffers kept for reuse
+    for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
+    s->ipc_opened.clear();
+    if (s->run_stream) { cudaStreamDestroy(s->run_stream); s->run_stream = nullptr; }
     s->csr_col.release_to_cache(); s->csr_val.release_to_cache(); s->csc_row.release_to_cache(); s->csc_val.release_to_cache();
     s->coo_row.release_to_cache(); s->test_row.release_to_cache(); s->test_col.release_to_cache(); s->test_val.release_to_cache();
     s->theta.release_to_cache(); s->x.release_to_cache(); s->sse.release(); s->partials.release();
@@ -839,8 +892,9 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
     cumf_plan_set_factor_rows(s->pt, m);
     // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
-    s->can_collect_sse = (x_begin == 0 && x_end == m && t_begin == 0 && t_end == n && s->pt->path == CUMF_PATH_TC &&
-                          solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr && env_long("CUMF_SSE_DIRECT", 0) == 0);
+    // (a shard's by-product covers the ratings of its theta rows = its CSC slice; over all shards that is every rating once)
+    s->can_collect_sse = (s->pt->path == CUMF_PATH_TC && solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr &&
+                          env_long("CUMF_SSE_DIRECT", 0) == 0);
     if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
     if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
     if ((rc = s->prep.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
@@ -850,6 +904,7 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
         s->train_cnt = (long)xn;
     }
+    s->csc_cnt = (long)tn;
     if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
         // samples the reference's launch covers: 256*((nnz_test-1)/256) (als.cu:1006); this
         // shard's share is the contiguous slice proportional to its X row range.
@@ -931,16 +986,16 @@ extern "C" int cumf_als_update_x(cumf_als_solver* s, void* stream) {
     CUMF_REQUIRE(s, "null pointer");
     CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_csr, 0));
     s->theta_fresh = false;
-    CUMF_TRY(cumf_update_factor(s->px, s->csr_col.as<int>(), s->csr_val.as<float>(), s->theta.as<float>(),
-                                s->x.as<float>(), s->lambda, s->solver, s->cg_iter, stream));
+    CUMF_TRY(update_factor_impl(s->px, s->csr_col.as<int>(), s->csr_val.as<float>(), s->theta.as<float>(),
+                                s->x.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_x));
     s->launches += s->px->last_launches;
     return CUMF_OK;
 }
 extern "C" int cumf_als_update_theta(cumf_als_solver* s, void* stream) {
     CUMF_REQUIRE(s, "null pointer");
     CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_csc, 0));
-    CUMF_TRY(cumf_update_factor(s->pt, s->csc_row.as<int>(), s->csc_val.as<float>(), s->x.as<float>(),
-                                s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream));
+    CUMF_TRY(update_factor_impl(s->pt, s->csc_row.as<int>(), s->csc_val.as<float>(), s->x.as<float>(),
+                                s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_theta));
     s->launches += s->pt->last_launches;
     s->theta_fresh = s->pt->sse_terms_valid;
     return CUMF_OK;
@@ -996,7 +1051,7 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
             s->sum_r2 = h_r2;
         }
         if (s->sum_r2 < 0.0) {
-            CUMF_TRY(launch_sumsq(s->csc_val.as<float>(), (long)s->train_cnt, d, s->partials.as<double>(), sse_partial_capacity(), st));
+            CUMF_TRY(launch_sumsq(s->csc_val.as<float>(), s->csc_cnt, d, s->partials.as<double>(), sse_partial_capacity(), st));
             double h_r2 = 0.0;
             CUMF_CUDA_TRY(cudaMemcpyAsync(&h_r2, d, sizeof(double), cudaMemcpyDeviceToHost, st));
             CUMF_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1026,11 +1081,15 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
         CUMF_CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(double), st));
     }
     if (train_sse && s->train_cnt > 0 && !train_done) {
-        if (s->train_mode == 1) {
+        // a shard that was asked for the by-product counts the ratings of its CSC slice: its streaming fall-back must walk
+        // the same set (by columns), or the sum over the shards would count ratings twice
+        const bool whole_matrix = (s->xb == 0 && s->xe == s->m && s->tb == 0 && s->te == s->n);
+        const int mode = (s->pt->collect_sse && !whole_matrix && s->train_mode != 0) ? 1 : s->train_mode;
+        if (mode == 1) {
             CUMF_TRY(launch_sse_chunks(s->pt->d_chunks.as<Chunk>(), (int)s->pt->chunks.size(), s->csc_row.as<int>(),
                                        s->csc_val.as<float>(), s->theta.as<float>(), s->x.as<float>(), 1, s->f, d,
                                        s->partials.as<double>(), sse_partial_capacity(), st));
-        } else if (s->train_mode == 2) {
+        } else if (mode == 2) {
             CUMF_TRY(launch_sse_chunks(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->csr_col.as<int>(),
                                        s->csr_val.as<float>(), s->x.as<float>(), s->theta.as<float>(), 0, s->f, d,
                                        s->partials.as<double>(), sse_partial_capacity(), st));
@@ -1055,6 +1114,8 @@ extern "C" int cumf_als_sse(cumf_als_solver* s, double* train_sse, double* test_
     return CUMF_OK;
 }
 
+extern "C" int cumf_als_peer_barrier(cumf_als_solver* s, void* stream);
+
 extern "C" int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, void* stream) {
     CUMF_REQUIRE(s && iters >= 0, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1069,8 +1130,10 @@ extern "C" int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, vo
     int rc = CUMF_OK;
     for (int it = 0; it < iters && rc == CUMF_OK; ++it) {
         rc = cumf_als_update_x(s, stream);
+        if (rc == CUMF_OK) rc = cumf_als_peer_barrier(s, stream);        // no-op for a single rank
         if (rc == CUMF_OK && cudaEventRecord(ev[2 * it + 1], st) != cudaSuccess) rc = CUMF_ECUDA;
         if (rc == CUMF_OK) rc = cumf_als_update_theta(s, stream);
+        if (rc == CUMF_OK) rc = cumf_als_peer_barrier(s, stream);
         if (rc == CUMF_OK && cudaEventRecord(ev[2 * it + 2], st) != cudaSuccess) rc = CUMF_ECUDA;
     }
     if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) {
@@ -1104,6 +1167,275 @@ extern "C" int cumf_als_timers(cumf_als_solver* s, double* out6, int reset) {
     return CUMF_OK;
 }
 
+
+// ---------------------------------------------------------------------------------
+// Multi-GPU row sharding inside the library (replaces the X_BATCH / THETA_BATCH loop of als.cu:768-777
+// and the peer-copy scheme of hugewiki.cu:2562-2572, 2744-2745).  Rank g owns rating-balanced row ranges of X and theta,
+// holds full replicas of both factors, and its solver epilogues store every updated row into all replicas (PeerOut), so
+// the exchange overlaps the half-step; a device-side flag barrier (one tiny kernel per half-step) orders the half-steps.
+// Two ways to connect the ranks:
+//   * cumf_group_* / doALS with CUMF_GPUS=n : one process, n devices, one host thread per device
+//   * cumf_als_ipc_export / _import        : one process per GPU (torchrun, MPI), CUDA IPC handles exchanged by the caller
+// ---------------------------------------------------------------------------------
+namespace cumf_multi {
+struct FlagPtrs { unsigned long long* p[8]; };
+// thread r of rank `me`: publish my epoch in rank r's flag word [me], then wait until rank r has published its own in mine
+__global__ void peer_barrier_kernel(FlagPtrs flags, int me, int nranks, unsigned long long epoch) {
+    const int r = threadIdx.x;
+    if (r >= nranks || r == me) return;
+    __threadfence_system();                                       // this GPU's earlier writes (peer rows) before the flag
+    volatile unsigned long long* theirs = flags.p[r] + me;
+    *theirs = epoch;
+    __threadfence_system();
+    volatile unsigned long long* mine = flags.p[me] + r;
+    unsigned long long spins = 0;
+    while (*mine < epoch) {
+        __nanosleep(200);
+        if (++spins > (1ull << 26)) __trap();                     // ~13 s: a peer died; fail the launch instead of hanging
+    }
+    __threadfence_system();
+}
+}  // namespace cumf_multi
+
+extern "C" int cumf_als_peer_barrier(cumf_als_solver* s, void* stream) {
+    CUMF_REQUIRE(s, "null pointer");
+    if (s->nranks <= 1) return CUMF_OK;
+    cumf_multi::FlagPtrs fp;
+    for (int r = 0; r < 8; ++r) fp.p[r] = s->peer_flags[r];
+    ++s->epoch;
+    cumf_multi::peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fp, s->rank, s->nranks, s->epoch);
+    CUMF_CUDA_TRY(cudaGetLastError());
+    s->launches += 1;
+    return CUMF_OK;
+}
+
+// blob = 3 CUDA IPC handles (X replica, theta replica, barrier flags), 64 bytes each
+extern "C" int cumf_als_ipc_blob_bytes(void) { return 3 * (int)sizeof(cudaIpcMemHandle_t); }
+
+static int solver_alloc_flags(cumf_als_solver* s) {
+    if (s->flags.p) return CUMF_OK;
+    CUMF_TRY(s->flags.alloc(8 * sizeof(unsigned long long)));
+    CUMF_CUDA_TRY(cudaMemset(s->flags.p, 0, 8 * sizeof(unsigned long long)));
+    return CUMF_OK;
+}
+
+extern "C" int cumf_als_ipc_export(cumf_als_solver* s, void* blob) {
+    CUMF_REQUIRE(s && blob, "null pointer");
+    CUMF_CUDA_TRY(cudaSetDevice(s->device));
+    CUMF_TRY(solver_alloc_flags(s));
+    cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(blob);
+    CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[0], s->x.p));
+    CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[1], s->theta.p));
+    CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[2], s->flags.p));
+    return CUMF_OK;
+}
+
+// blobs: nranks blobs in rank order (this rank's own entry is ignored).  After this call every half-step of this solver
+// also updates the peers' replicas, and cumf_als_iterate ends every half-step with the device-side barrier; every rank must
+// call it, with the same nranks, before any of them runs a half-step.
+extern "C" int cumf_als_ipc_import(cumf_als_solver* s, const void* blobs, int nranks, int my_rank) {
+    CUMF_REQUIRE(s && blobs, "null pointer");
+    CUMF_REQUIRE(nranks >= 1 && nranks <= 8 && my_rank >= 0 && my_rank < nranks, "1 <= nranks <= 8 ranks are supported");
+    CUMF_CUDA_TRY(cudaSetDevice(s->device));
+    CUMF_TRY(solver_alloc_flags(s));
+    s->rank = my_rank;
+    s->nranks = nranks;
+    s->peer_x.n = s->peer_theta.n = 0;
+    s->peer_flags[my_rank] = s->flags.as<unsigned long long>();
+    const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(blobs);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == my_rank) continue;
+        void* p[3] = {nullptr, nullptr, nullptr};
+        for (int k = 0; k < 3; ++k) {
+            CUMF_CUDA_TRY(cudaIpcOpenMemHandle(&p[k], h[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+            s->ipc_opened.push_back(p[k]);
+        }
+        s->peer_x.p[s->peer_x.n++] = reinterpret_cast<float*>(p[0]);
+        s->peer_theta.p[s->peer_theta.n++] = reinterpret_cast<float*>(p[1]);
+        s->peer_flags[r] = reinterpret_cast<unsigned long long*>(p[2]);
+    }
+    return CUMF_OK;
+}
+
+// ---- one process, n devices -------------------------------------------------------------------------------------------
+struct cumf_als_group {
+    std::vector<cumf_als_solver*> s;
+    int m = 0, n = 0, f = 0;
+    long nnz = 0, nnz_test = 0;
+    std::vector<std::string> errors;        // per shard (g_last_error is thread-local)
+};
+
+// contiguous row ranges with (nearly) equal numbers of ratings: the deterministic replacement of hugewiki's dynamic batch
+// queue (hugewiki.cu:2446-2496); same integer arithmetic as cumf_als_b200.data.nnz_balanced_ranges
+static std::vector<std::pair<int, int>> nnz_balanced_ranges(const int* ptr, int rows, int parts) {
+    std::vector<int> bounds(1, 0);
+    const long long total = ptr[rows];
+    for (int g = 1; g < parts; ++g) {
+        const long long target = total * g / parts;
+        int b = (int)(std::lower_bound(ptr, ptr + rows + 1, target, [](int a, long long t) { return (long long)a < t; }) - ptr);
+        b = std::min(std::max(b, bounds.back()), rows);
+        bounds.push_back(b);
+    }
+    bounds.push_back(rows);
+    std::vector<std::pair<int, int>> out;
+    for (int g = 0; g < parts; ++g) out.emplace_back(bounds[g], bounds[g + 1]);
+    return out;
+}
+
+template <typename Fn> static void for_each_shard_parallel(int n, Fn fn) {
+    std::vector<std::thread> th;
+    for (int g = 1; g < n; ++g) th.emplace_back([=]() { fn(g); });
+    fn(0);
+    for (auto& t : th) t.join();
+}
+
+extern "C" int cumf_group_destroy(cumf_als_group* g) {
+    if (!g) return CUMF_OK;
+    // every device must be idle before any replica goes away: the peers' epilogues write into it
+    for (auto* s : g->s) if (s) { cudaSetDevice(s->device); cudaDeviceSynchronize(); }
+    for_each_shard_parallel((int)g->s.size(), [&](int k) { if (g->s[k]) cumf_als_destroy(g->s[k]); });
+    delete g;
+    return CUMF_OK;
+}
+
+static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                             const float* csrValHostPtr, const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr,
+                             const float* cscValHostPtr, const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                             const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f, long nnz,
+                             long nnz_test, float lambda, int first_device, int n_devices, int solver, int path,
+                             bool wait_uploads, const float* thetaTHost, const float* XTHost) {
+    CUMF_REQUIRE(out && csrRowIndexHostPtr && cscColIndexHostPtr, "null pointer");
+    CUMF_REQUIRE(n_devices >= 1 && n_devices <= 8, "1 .. 8 devices");
+    int have = 0;
+    CUMF_CUDA_TRY(cudaGetDeviceCount(&have));
+    // test hook: every shard on first_device (own stream each), so one GPU exercises the peer stores and the barrier
+    const bool same_device = env_long("CUMF_GROUP_SAME_DEVICE", 0) != 0;
+    CUMF_REQUIRE(first_device >= 0 && first_device + (same_device ? 1 : n_devices) <= have, "not that many devices on this node");
+    auto device_of = [=](int k) { return same_device ? first_device : first_device + k; };
+    cumf_als_group* g = new cumf_als_group();
+    g->m = m; g->n = n; g->f = f; g->nnz = nnz; g->nnz_test = nnz_test;
+    g->s.assign(n_devices, nullptr);
+    g->errors.assign(n_devices, std::string());
+    const auto xr = nnz_balanced_ranges(csrRowIndexHostPtr, m, n_devices);
+    const auto tr = nnz_balanced_ranges(cscColIndexHostPtr, n, n_devices);
+    std::vector<int> rcs(n_devices, CUMF_OK);
+    // one host thread per device: work plans, allocations and the (asynchronous) uploads of all shards proceed in parallel,
+    // every GPU pulls its slice over its own PCIe link
+    for_each_shard_parallel(n_devices, [&](int k) {
+        rcs[k] = als_create_impl(&g->s[k], csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
+                                 cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
+                                 cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, xr[k].first,
+                                 xr[k].second, tr[k].first, tr[k].second, device_of(k), solver, path, wait_uploads,
+                                 thetaTHost, XTHost);
+        if (rcs[k] == CUMF_OK) rcs[k] = solver_alloc_flags(g->s[k]);
+        if (rcs[k] == CUMF_OK && cudaStreamCreateWithFlags(&g->s[k]->run_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_last_error("cumf_group_create: cannot create a stream");
+            rcs[k] = CUMF_ECUDA;
+        }
+        if (rcs[k] == CUMF_OK && !same_device) {
+            for (int j = 0; j < n_devices; ++j) {
+                if (j == k) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(first_device + j, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) { set_last_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); rcs[k] = CUMF_ECUDA; }
+            }
+        }
+        if (rcs[k] != CUMF_OK) g->errors[k] = cumf_last_error();
+    });
+    for (int k = 0; k < n_devices; ++k)
+        if (rcs[k] != CUMF_OK) {
+            set_last_error("shard " + std::to_string(k) + ": " + g->errors[k]);
+            const int rc = rcs[k];
+            cumf_group_destroy(g);
+            return rc;
+        }
+    for (int k = 0; k < n_devices; ++k) {
+        cumf_als_solver* s = g->s[k];
+        s->rank = k;
+        s->nranks = n_devices;
+        for (int j = 0; j < n_devices; ++j) {
+            s->peer_flags[j] = g->s[j]->flags.as<unsigned long long>();
+            if (j == k) continue;
+            s->peer_x.p[s->peer_x.n++] = g->s[j]->x.as<float>();
+            s->peer_theta.p[s->peer_theta.n++] = g->s[j]->theta.as<float>();
+        }
+    }
+    *out = g;
+    return CUMF_OK;
+}
+
+extern "C" int cumf_group_create(cumf_als_group** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                                 const float* csrValHostPtr, const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr,
+                                 const float* cscValHostPtr, const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                                 const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f, long nnz,
+                                 long nnz_test, float lambda, int first_device, int n_devices, int solver, int path) {
+    return group_create_impl(out, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr, cscColIndexHostPtr,
+                             cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr, cooColIndexTestHostPtr, cooValHostTestPtr,
+                             m, n, f, nnz, nnz_test, lambda, first_device, n_devices, solver, path, /*wait_uploads=*/true, nullptr,
+                             nullptr);
+}
+
+extern "C" int cumf_group_size(const cumf_als_group* g) { return g ? (int)g->s.size() : 0; }
+extern "C" cumf_als_solver* cumf_group_shard(cumf_als_group* g, int k) { return (g && k >= 0 && k < (int)g->s.size()) ? g->s[k] : nullptr; }
+
+extern "C" int cumf_group_set_factors(cumf_als_group* g, const float* thetaTHost, const float* XTHost) {
+    CUMF_REQUIRE(g, "null pointer");
+    for (auto* s : g->s) CUMF_TRY(cumf_als_set_factors(s, thetaTHost, XTHost));
+    return CUMF_OK;
+}
+// every replica holds both full factors after a half-step's barrier: one download
+extern "C" int cumf_group_get_factors(cumf_als_group* g, float* thetaTHost, float* XTHost) {
+    CUMF_REQUIRE(g && !g->s.empty(), "null pointer");
+    for (auto* s : g->s) { CUMF_CUDA_TRY(cudaSetDevice(s->device)); CUMF_CUDA_TRY(cudaDeviceSynchronize()); }
+    return cumf_als_get_factors(g->s[0], thetaTHost, XTHost);
+}
+
+// `iters` iterations on every shard (asynchronous launches device by device: the devices only meet in the barrier kernels);
+// ms_out = device time of the slowest shard
+extern "C" int cumf_group_iterate(cumf_als_group* g, int iters, float* ms_out) {
+    CUMF_REQUIRE(g && iters >= 0, "bad argument");
+    const int n = (int)g->s.size();
+    std::vector<float> ms(n, 0.f);
+    std::vector<int> rcs(n, CUMF_OK);
+    for_each_shard_parallel(n, [&](int k) {
+        cudaSetDevice(g->s[k]->device);
+        rcs[k] = cumf_als_iterate(g->s[k], iters, &ms[k], g->s[k]->run_stream);
+        if (rcs[k] != CUMF_OK) g->errors[k] = cumf_last_error();
+    });
+    for (int k = 0; k < n; ++k)
+        if (rcs[k] != CUMF_OK) { set_last_error("shard " + std::to_string(k) + ": " + g->errors[k]); return rcs[k]; }
+    if (ms_out) *ms_out = *std::max_element(ms.begin(), ms.end());
+    return CUMF_OK;
+}
+
+extern "C" int cumf_group_collect_train_sse(cumf_als_group* g, int on) {
+    CUMF_REQUIRE(g, "null pointer");
+    int all = 1;
+    for (auto* s : g->s) all &= cumf_als_collect_train_sse(s, on);
+    if (!all) for (auto* s : g->s) cumf_als_collect_train_sse(s, 0);       // all shards or none: they must count the same sample set
+    return all;
+}
+
+extern "C" int cumf_group_sse(cumf_als_group* g, double* train_sse, double* test_sse) {
+    CUMF_REQUIRE(g, "null pointer");
+    const int n = (int)g->s.size();
+    std::vector<double> tr(n, 0.0), te(n, 0.0);
+    std::vector<int> rcs(n, CUMF_OK);
+    for_each_shard_parallel(n, [&](int k) {
+        cudaSetDevice(g->s[k]->device);
+        rcs[k] = cumf_als_sse(g->s[k], train_sse ? &tr[k] : nullptr, test_sse ? &te[k] : nullptr, g->s[k]->run_stream);
+        if (rcs[k] != CUMF_OK) g->errors[k] = cumf_last_error();
+    });
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < n; ++k) {
+        if (rcs[k] != CUMF_OK) { set_last_error("shard " + std::to_string(k) + ": " + g->errors[k]); return rcs[k]; }
+        a += tr[k]; b += te[k];          // rank order: deterministic
+    }
+    if (train_sse) *train_sse = a;
+    if (test_sse) *test_sse = b;
+    return CUMF_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // b1: doALS.  Same signature and observable behaviour as als.cu:662-1035: blocking,
 // host pointers in, factors written back, last test RMSE returned, progress on stdout
@@ -1114,6 +1446,96 @@ extern "C" int cumf_als_timers(cumf_als_solver* s, double* out6, int reset) {
     fprintf(stderr, "cumf_als_b200 error in %s: %s\n", where, cumf_last_error());
     cudaDeviceReset();
     exit(EXIT_FAILURE);
+}
+
+// doALS over CUMF_GPUS devices of this node (DEVICEID = the first): one host thread per device runs the iteration loop of its
+// shard; the devices meet in the barrier kernels, the host threads only to add up the RMSE sums.  Same stdout contract.
+namespace cumf_multi {
+struct HostBarrier {
+    std::atomic<int> count{0}, sense{0};
+    int n = 1;
+    void wait() {
+        const int s = sense.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(s ^ 1, std::memory_order_release);
+        } else {
+            while (sense.load(std::memory_order_acquire) == s) std::this_thread::yield();
+        }
+    }
+};
+}  // namespace cumf_multi
+
+static float doALS_multi(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
+                         const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                         const int* cooRowIndexHostPtr, float* thetaTHost, float* XTHost, const int* cooRowIndexTestHostPtr,
+                         const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, const int m, const int n, const int f,
+                         const long nnz, const long nnz_test, const float lambda, const int ITERS, const int DEVICEID,
+                         const int gpus, const int solver, const int path, const bool quiet, const bool debug) {
+    cumf_als_group* g = nullptr;
+    const double t_setup = wall_seconds();
+    if (group_create_impl(&g, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr, cscColIndexHostPtr,
+                          cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr, cooColIndexTestHostPtr, cooValHostTestPtr, m, n,
+                          f, nnz, nnz_test, lambda, DEVICEID, gpus, solver, path, /*wait_uploads=*/false, thetaTHost, XTHost) != CUMF_OK)
+        die("cumf_group_create");
+    cumf_group_collect_train_sse(g, 1);
+    if (debug) printf("\tsetup of %d shards (work plans; uploads continue in the background) run %f seconds.\n", gpus, wall_seconds() - t_setup);
+    if (!quiet) printf("*******start iterations on %d GPUs (rows sharded by rating count)...\n", gpus);
+    cumf_multi::HostBarrier hb;
+    hb.n = gpus;
+    std::vector<double> tr(2 * (size_t)gpus, 0.0), te(2 * (size_t)gpus, 0.0);
+    std::vector<int> rcs(gpus, CUMF_OK);
+    std::vector<std::string> errs(gpus);
+    float final_rmse = 0.f;
+    auto run = [&](int k) {
+        cumf_als_solver* s = g->s[k];
+        cudaSetDevice(s->device);
+        auto step = [&](int rc) { if (rc != CUMF_OK && rcs[k] == CUMF_OK) { rcs[k] = rc; errs[k] = cumf_last_error(); } return rcs[k] == CUMF_OK; };
+        // nobody pushes rows into a replica whose initial upload is still in flight
+        void* st = s->run_stream;
+        cudaStreamWaitEvent(s->run_stream, s->ev_csr, 0);
+        step(cumf_als_peer_barrier(s, st));
+        for (int iter = 0; iter < ITERS; ++iter) {
+            double t0 = wall_seconds();
+            if (rcs[k] == CUMF_OK) {
+                step(cumf_als_update_x(s, st)) && step(cumf_als_peer_barrier(s, st));
+                if (debug && k == 0) {
+                    cudaStreamSynchronize(s->run_stream);
+                    printf("---------------------------ALS iteration %d, update X.----------------------------------\n", iter);
+                    printf("update X run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, m, f);
+                    t0 = wall_seconds();
+                }
+                step(cumf_als_update_theta(s, st)) && step(cumf_als_peer_barrier(s, st));
+                if (debug && k == 0) {
+                    cudaStreamSynchronize(s->run_stream);
+                    printf("---------------------------------- ALS iteration %d, update theta ----------------------------------\n", iter);
+                    printf("update theta run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, n, f);
+                    printf("Calculate RMSE.\n");
+                }
+                step(cumf_als_sse(s, cooRowIndexHostPtr ? &tr[(iter & 1) * gpus + k] : nullptr, &te[(iter & 1) * gpus + k], st));
+            }
+            hb.wait();          // every shard's sums of this iteration are in (a failed shard still takes part)
+            if (k == 0) {
+                double a = 0.0, b = 0.0;
+                for (int j = 0; j < gpus; ++j) { a += tr[(iter & 1) * gpus + j]; b += te[(iter & 1) * gpus + j]; }
+                const float rmse_train = sqrtf((float)a / (float)nnz);        // als.cu:991
+                final_rmse = sqrtf((float)b / (float)nnz_test);                // als.cu:1018
+                if (!quiet) {
+                    printf("--------- Train RMSE in iter %d: %f\n", iter, rmse_train);
+                    printf("--------- Test RMSE in iter %d: %f\n", iter, final_rmse);
+                }
+            }
+        }
+    };
+    for_each_shard_parallel(gpus, run);
+    for (int k = 0; k < gpus; ++k)
+        if (rcs[k] != CUMF_OK) { set_last_error("shard " + std::to_string(k) + ": " + errs[k]); die("multi-GPU iteration"); }
+    const double t_down = wall_seconds();
+    if (cumf_group_get_factors(g, thetaTHost, XTHost) != CUMF_OK) die("cumf_group_get_factors");
+    const double t_free = wall_seconds();
+    cumf_group_destroy(g);
+    if (debug) printf("\tfactor download run %f seconds, release of the device buffers %f seconds.\n", t_free - t_down, wall_seconds() - t_free);
+    return final_rmse;
 }
 
 float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
@@ -1133,6 +1555,12 @@ float doALS(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const 
                solver == CUMF_SOLVER_CG ? "CG" : "LU(cuBLAS oracle)",
                path == CUMF_PATH_SIMT ? "simt" : (path == CUMF_PATH_TC ? "tcgen05" : "auto"));
     }
+    // CUMF_GPUS=n: the X_BATCH / THETA_BATCH model-parallel split (als.cu:768-777) becomes a row sharding over n GPUs
+    const int gpus = (int)env_long("CUMF_GPUS", 1);
+    if (gpus > 1)
+        return doALS_multi(csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr, cscColIndexHostPtr,
+                           cscValHostPtr, cooRowIndexHostPtr, thetaTHost, XTHost, cooRowIndexTestHostPtr, cooColIndexTestHostPtr,
+                           cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, ITERS, DEVICEID, gpus, solver, path, quiet, debug);
     cumf_als_solver* s = nullptr;
     const double t_setup = wall_seconds();
     // the host arrays outlive this call, so the uploads may still be in flight when the iterations start

@@ -82,12 +82,30 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Replicas of the factor being updated on peer GPUs (peer-mapped pointers: cudaDeviceEnablePeerAccess in one process, CUDA
+// IPC across processes).  Every solved row is stored to all of them from the solver epilogue, so the row-block exchange of
+// the sharded half-step rides on the kernel instead of following it.
+struct PeerOut {
+    float* p[8];
+    int n;
+};
+
 // Small host -> device uploads of plan metadata that must not queue on the copy engine behind gigabytes of rating
 // uploads: the bytes go through a pinned staging arena (process-wide, grown on demand, kept) and are copied by a kernel
 // reading the arena over PCIe.  Asynchronous on `st`; the arena is recycled by staging_reset(), which the caller may
 // only invoke after `st` has been synchronised.  `bytes` must be a multiple of 4.   (als_api.cu)
 int upload_via_kernel(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
 void staging_reset();
+// The arena is one per process: a StagingSection owns it from construction (which recycles it) until finish() has
+// synchronised the stream its copies run on.  Host threads of a multi-GPU group build their plans in parallel and only
+// serialise in these short sections.
+struct StagingSection {
+    StagingSection();
+    ~StagingSection();
+    int finish(cudaStream_t st);      // stream synchronisation, then the arena is handed on
+    bool held = false;
+    cudaStream_t last = nullptr;
+};
 
 // Launch helpers implemented in the .cu files -------------------------------------
 // SIMT Gram (+RHS) over chunk range [c0,c1): direct rows go to tt/rhs at
@@ -105,7 +123,8 @@ int launch_split_reduce(const SplitRow* d_rows, int r0, int r1, int f, float lam
 // d_sys_rows (optional): system s reads/writes x at row d_sys_rows[s].row of d_x instead of row s
 // (used for the compact batch of split rows).
 int launch_cg(const float* d_A, float* d_x, const float* d_b, int batch, int f, float cg_iter,
-              const SplitRow* d_sys_rows, cudaStream_t st, float lambda = 0.f, double* d_sse_rows = nullptr);
+              const SplitRow* d_sys_rows, cudaStream_t st, float lambda = 0.f, double* d_sse_rows = nullptr,
+              const PeerOut* peers = nullptr, int x_row_offset = 0);
 // cuBLAS batched LU oracle.
 int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t st);
 // RMSE partial sums.
@@ -135,6 +154,11 @@ struct TcExtra {
     float* d_tt = nullptr; float* d_rhs = nullptr; int tt_row_base = 0;
     float* const* peer_out = nullptr; int n_peer_out = 0;
 };
+inline TcExtra tc_extra_from(const PeerOut* peers) {
+    TcExtra e;
+    if (peers) { e.peer_out = peers->p; e.n_peer_out = peers->n; }
+    return e;
+}
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,
                      const int* d_colidx, const float* d_val, const float* d_factor, float* d_out,
                      int f, float lambda, float cg_iter, float* d_scratchA, float* d_scratchB,

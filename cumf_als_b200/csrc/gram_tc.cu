@@ -463,7 +463,7 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                       const int* __restrict__ colidx, const float* __restrict__ val,
                       const __grid_constant__ CUtensorMap factor_map, float* __restrict__ out, float lambda, float cg_iter,
                       float* __restrict__ scratchA, float* __restrict__ scratchB, uint64_t desc_tmpl,
-                      double* __restrict__ sse_terms, int zero_row) {
+                      double* __restrict__ sse_terms, int zero_row, PeerOut peers) {
     // dynamic shared memory is used in place (no pointer arithmetic through integers, so the
     // compiler keeps the shared address space and emits LDS/STS)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -954,7 +954,10 @@ als_fused_f100_kernel(const Chunk* __restrict__ chunks, const int* __restrict__ 
                     rsold = rsnew;
                     p = fmaf(beta, p, r);
                 }
-                if (active) xrow[i] = xi;
+                if (active) {
+                    xrow[i] = xi;
+                    for (int k = 0; k < peers.n; ++k) peers.p[k][(size_t)ck.row * F + i] = xi;     // every peer replica gets the row
+                }
                 if (sse_terms != nullptr) {
                     // Squared error of the row's ratings under the x just computed, without touching them again:
                     //   sum_j (r_j - x.theta_j)^2 = sum r_j^2 - 2 x^T b + x^T G x,   G = A - reg I,   A x = b - r
@@ -1191,6 +1194,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     if (rc == CUMF_OK) rc = w->stage_tab.alloc(sizeof(StageDesc) * (size_t)std::max(1, stage_base[n]));
     if (rc == CUMF_OK) rc = d_base.alloc(sizeof(int) * (n + 1));
     if (rc == CUMF_OK) rc = w->chunk_meta.alloc(sizeof(int) * std::max(n, 1));
+    StagingSection sec;      // the process-wide pinned arena, until the fill kernel below has read it
     if (rc == CUMF_OK &&
         (upload_via_kernel(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), 0) != CUMF_OK ||
          upload_via_kernel(w->chunk_meta.p, chunk_meta.data(), sizeof(int) * std::max(n, 1), 0) != CUMF_OK ||
@@ -1206,10 +1210,10 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
             auto fill = kt == 64 ? fill_stage_table_kernel<64, 4> : (kt == 32 ? fill_stage_table_kernel<32, 8> : fill_stage_table_kernel<KT, SUB_STEPS>);
             fill<<<(n + 127) / 128, 128>>>(d_chunks, d_base.as<int>(), w->chunk_meta.as<int>(), n, w->stage_tab.as<StageDesc>());
         }
-        if (cudaStreamSynchronize(0) != cudaSuccess) {      // not the device: uploads may be running on another stream
-            set_last_error(std::string("tc_plan_create: stage table: ") + cudaGetErrorString(cudaGetLastError()));
-            rc = CUMF_ECUDA;
-        }
+    }
+    {   // (the stream, not the device: rating uploads may be running on another stream)
+        const int rc2 = sec.finish(0);
+        if (rc == CUMF_OK) rc = rc2;
     }
     if (rc != CUMF_OK) { tc_plan_destroy(w, false); return rc; }
     *out = w;
@@ -1241,13 +1245,15 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         return CUMF_EINVAL;
     }
     if (nchunks == 0) return CUMF_OK;
-    if (w->impl != 2 && extra && (extra->d_tt || extra->n_peer_out > 0)) {
-        set_last_error("tc_update_factor: direct stores / peer outputs need the generic-f kernel (CUMF_TC_IMPL=2)");
+    if (w->impl != 2 && extra && extra->d_tt) {
+        set_last_error("tc_update_factor: direct stores need the generic-f kernel (CUMF_TC_IMPL=2)");
         return CUMF_EUNSUPPORTED;
     }
     // kernel variant: (long rows -> symmetric single-MMA mode) x (staging, stage size)
     using KernelFn = void (*)(const Chunk*, const int*, const StageDesc*, const int*, const int*, const float*, const CUtensorMap, float*,
-                              float, float, float*, float*, uint64_t, double*, int);
+                              float, float, float*, float*, uint64_t, double*, int, PeerOut);
+    PeerOut peers{};
+    if (extra) for (int k = 0; k < extra->n_peer_out && k < 8; ++k) peers.p[peers.n++] = extra->peer_out[k];
     struct Variant { KernelFn fn; int threads; size_t smem; };
     auto variant = [&]() -> Variant {
 #define CUMF_VARIANT(SYM, DIRECT, ROWS) \
@@ -1331,7 +1337,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         const uint64_t desc_tmpl = smem_desc_template_direct(D_CHUNK_STRIDE, D_KG_STRIDE);
         v.fn<<<w->grid, v.threads, v.smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->split_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
-                                               desc_tmpl, d_sse_terms, w->factor_rows);
+                                               desc_tmpl, d_sse_terms, w->factor_rows, peers);
     } else {
         if (w->mapped_factor != d_factor) {
             CUMF_TRY(encode_factor_map(&w->factor_map, d_factor));
@@ -1341,7 +1347,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
         const uint64_t desc_tmpl = smem_desc_template(swap && *swap == '1');
         v.fn<<<w->grid, v.threads, v.smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->factor_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,
-                                               desc_tmpl, d_sse_terms, 0);
+                                               desc_tmpl, d_sse_terms, 0, peers);
     }
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;

@@ -188,13 +188,13 @@ int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const 
                     long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
                     int device, int solver, int path);
 int cumf_als_destroy(cumf_als_solver* s);
-/* cumf_als_destroy (and so cumf_doALS) keeps the large device buffers of the solver for the next
- * one instead of cudaFree-ing them (at most CUMF_CACHE_MB megabytes, default 16384; 0 disables);
- * this call returns them to the driver.  The reference frees everything (als.cu:1026-1033).
- * Call it before cudaDeviceReset(): the cached pointers do not survive the context.           */
+/* By default cumf_als_destroy (and so cumf_doALS) cudaFree's every device buffer, like the reference
+ * (als.cu:1026-1033).  With CUMF_CACHE_MB=<n> (opt-in) up to n MiB of them are kept for the next
+ * solver; this call returns those, and the pinned staging arena of the plan uploads, to the driver. */
 int cumf_release_cached_memory(void);
-/* Train RMSE as a by-product of the theta half-step: when on (returns 1 if the solver can do it: whole matrix on this
- * GPU, fused CG path, cooRowIndex == CSR rows), cumf_als_update_theta also accumulates, per row, x^T b + x^T r + reg x^T x
+/* Train RMSE as a by-product of the theta half-step: when on (returns 1 if the solver can do it:
+ * fused CG path, cooRowIndex == CSR rows; a row shard then reports the ratings of its theta rows, so every shard of a run
+ * must switch it on or none), cumf_als_update_theta also accumulates, per row, x^T b + x^T r + reg x^T x
  * from the CG state, and cumf_als_sse returns  sum r^2 - that  for the train set instead of streaming over the ratings
  * (als.cu:967-991) -- valid while X is unchanged since that half-step; otherwise, and whenever the subtraction would
  * keep fewer than three digits, the streaming kernel runs.  Off by default; cumf_doALS turns it on.                    */
@@ -217,6 +217,45 @@ int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, void* stream)
  * out[0] = X step, out[1] = theta step, out[2] = dominant Gram kernel X side,
  * out[3] = dominant Gram kernel theta side, out[4] = kernel launches, out[5] = iterations */
 int cumf_als_timers(cumf_als_solver* s, double* out6, int reset);
+
+/* ---- multi-GPU row sharding -----------------------------------
+ * Replaces the X_BATCH / THETA_BATCH model-parallel loop (als.cu:768-777, 881-890) and the
+ * peer-copy exchange of hugewiki.cu:2562-2572, 2744-2745: rank g owns rating-balanced row
+ * ranges of X and theta and full replicas of both factors; the solver epilogue of its half-step
+ * stores every updated row into ALL replicas (peer-mapped pointers over NVLink), so the
+ * exchange overlaps the kernel, and one tiny barrier kernel (epoch flags in peer memory) ends
+ * the half-step.  No NCCL call on this path.
+ *
+ * (a) one process per GPU (torchrun / MPI): create the solver with this rank's ranges, exchange
+ *     the blobs of cumf_als_ipc_export (CUDA IPC handles of the two replicas and the flag
+ *     words; cumf_als_ipc_blob_bytes() each) with any transport, hand all of them, in rank
+ *     order, to cumf_als_ipc_import on every rank, synchronise the ranks once on the host, then
+ *     cumf_als_iterate (which ends each half-step with cumf_als_peer_barrier) or
+ *     update_x / peer_barrier / update_theta / peer_barrier by hand.                          */
+int cumf_als_ipc_blob_bytes(void);
+int cumf_als_ipc_export(cumf_als_solver* s, void* blob);
+int cumf_als_ipc_import(cumf_als_solver* s, const void* blobs, int nranks, int my_rank);
+int cumf_als_peer_barrier(cumf_als_solver* s, void* stream);
+/* (b) one process, n devices [first_device, first_device + n): the group creates one shard per
+ *     device on its own host thread (plans, allocations and uploads in parallel), connects them
+ *     with cudaDeviceEnablePeerAccess and drives them.  cumf_doALS does this itself when
+ *     CUMF_GPUS=n is set, so the reference's main.cpp goes multi-GPU unmodified.               */
+typedef struct cumf_als_group cumf_als_group;
+int cumf_group_create(cumf_als_group** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                      const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                      const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                      const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                      const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                      long nnz, long nnz_test, float lambda, int first_device, int n_devices, int solver,
+                      int path);
+int cumf_group_destroy(cumf_als_group* g);
+int cumf_group_size(const cumf_als_group* g);
+cumf_als_solver* cumf_group_shard(cumf_als_group* g, int k);
+int cumf_group_set_factors(cumf_als_group* g, const float* thetaTHost, const float* XTHost);
+int cumf_group_get_factors(cumf_als_group* g, float* thetaTHost, float* XTHost);   /* one replica */
+int cumf_group_iterate(cumf_als_group* g, int iters, float* ms_out);   /* ms_out: slowest shard */
+int cumf_group_collect_train_sse(cumf_als_group* g, int on);
+int cumf_group_sse(cumf_als_group* g, double* train_sse, double* test_sse);   /* summed over shards */
 
 #ifdef __cplusplus
 }
