@@ -13,8 +13,13 @@ Prints ONE JSON line (rank 0):
              per orientation) exceed the 126 MB L2, so no flush is needed between iterations.
   e2e        the same metric through the reference-facing call doALS(host pointers): uploads,
              K iterations, per-iteration train/test RMSE, factor download -- wall clock / K.
-  roofline   Gram(+fused solve) kernel: algorithmic bytes / CUDA-event kernel time.
-  cpu_baseline  the CPU oracle (oracle/als_cpu.c port) timed on a bounded row sample, scaled.
+  roofline   Gram(+fused solve) kernel: algorithmic bytes / CUDA-event kernel time, for the iteration and per
+             launch (`launches.x_side`, `launches.theta_side`: each with its own bound -- the theta-side launch of the Netflix
+             shape gathers from an L2-resident 7 MB table and is bound on chip, not by HBM).
+  cpu_baseline  the CPU oracle (oracle/als_cpu.c port) timed on a bounded row sample, scaled: 1 thread (north_star) and all cores.
+N > 1 (torchrun, one process per GPU): rows sharded by rating count; every rank's solver epilogues store the updated rows into
+all ranks' factor replicas (CUDA IPC peer mappings) and a flag-barrier kernel ends each half-step -- no collective on the data
+path; e2e = cumf_doALS(host pointers) on rank 0 with CUMF_GPUS=N (one process driving the N GPUs).
 `--impl reference` runs the UNMODIFIED reference (oracle/_ref, its Kepler-era kernels recompiled
 for sm_100a + cuBLAS/cuSPARSE) through its own doALS on the same inputs.
 """
@@ -46,6 +51,18 @@ WORKLOADS = {
     "yahoo": dict(m=1000990, n=624961, nnz=252800275, nnz_test=4003960, f=100, lam=1.4, seed=1004, ref_batches=(6, 3)),
     "tiny": dict(m=2000, n=5000, nnz=400000, nnz_test=20000, f=100, lam=0.048, seed=1, ref_batches=(1, 1)),
 }
+
+
+DTYPE = "f32 (Gram: split-fp16 tcgen05 MMA, hi + lo, fp32 accumulate in TMEM; CG and RMSE in fp32)"
+
+
+def common_config(args, r, w):
+    """Identical keys and values in both arms (ours / --impl reference): the driver compares them."""
+    f = w["f"]
+    return {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f, "lambda": w["lam"],
+            "solver": "cg6",
+            "l2": f"inputs exceed L2 (factors {(r.m + r.n) * f * 4 / 1e6:.0f} MB, ratings {r.nnz * 12 / 1e9:.1f} GB per "
+                  f"orientation): no flush"}
 
 
 def dist_env():
@@ -119,6 +136,34 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def tensor_peak():
+    """Dense bf16/fp16 TFLOP/s, the sustained figure (the kernel is timed inside a long step)."""
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+
+
+def launch_roofline(rows, nnz, f, fused, ms, ncu):
+    """One half-step launch: algorithmic HBM rate and useful tensor rate, with the bound the committed ncu capture shows
+    (profiles/traffic.json: DRAM bytes, tensor-pipe %, L2 hit rate of that launch)."""
+    if not ms or ms <= 0:
+        return None
+    hbm, _ = measured_peaks()
+    tf, _ = tensor_peak()
+    b = gram_bytes(rows, nnz, f, fused)
+    flops = 2.0 * f * f * nnz
+    out = {"ms": ms, "algorithmic_bytes": b, "algorithmic_gbs": b / 1e9 / (ms / 1e3), "frac_hbm": b / 1e9 / (ms / 1e3) / hbm,
+           "useful_tflops": flops / 1e12 / (ms / 1e3), "frac_tensor": flops / 1e12 / (ms / 1e3) / tf}
+    if ncu:
+        out.update({k: ncu[k] for k in ("dram_bytes", "tensor_pipe_pct", "l2_hit_pct") if k in ncu})
+        if "dram_bytes" in ncu:
+            out["dram_gbs"] = ncu["dram_bytes"] / 1e9 / (ms / 1e3)
+            out["bound"] = "hbm" if ncu["dram_bytes"] > 0.25 * b else "tensor+l2 (gather source is L2-resident)"
+    return out
+
+
 def ncu_traffic(workload: str, path: str):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
@@ -135,11 +180,21 @@ def gram_bytes(rows, nnz, f, fused: bool):
     return nnz * (4 * f + 4) + (rows + 1) * 4 + rows * f * f * 4
 
 
-def cpu_baseline(r, theta0, X0, w, budget_s: float = 15.0):
+def _omp_set_threads(n: int) -> bool:
+    import ctypes
+    for name in ("libgomp.so.1", "libomp.so", "libiomp5.so"):
+        try:
+            ctypes.CDLL(name).omp_set_num_threads(int(n))
+            return True
+        except (OSError, AttributeError):
+            continue
+    return False
+
+
+def _cpu_sample(r, theta0, X0, w, budget_s):
     """CPU oracle on a bounded sample of rows of both half-steps, scaled by rating share."""
     from oracle import oracle as O
     f, lam = w["f"], w["lam"]
-    cores = os.cpu_count() or 1
     est = {}
     sample_desc = []
     for side, (ptr, idx, val, fac, out, rows) in {
@@ -147,8 +202,8 @@ def cpu_baseline(r, theta0, X0, w, budget_s: float = 15.0):
         "theta": (r.csc_indptr, r.csc_indices, r.csc_data, np.ascontiguousarray(
             np.random.default_rng(0).random((r.m, f), dtype=np.float32) * 0.2), theta0.copy(), r.n),
     }.items():
-        # grow the sample until it costs ~budget/2 seconds
-        share_rows = max(8, rows // 2000)
+        # grow the sample until it costs ~budget/4 seconds
+        share_rows = max(8, rows // 20000)
         t, k = 0.0, 0
         while True:
             lo = (rows // 3)
@@ -162,69 +217,77 @@ def cpu_baseline(r, theta0, X0, w, budget_s: float = 15.0):
             share_rows = int(share_rows * max(2.0, min(16.0, (budget_s / 2) / max(t, 1e-3))))
         est[side] = t * (int(ptr[-1]) / max(k, 1))
         sample_desc.append(f"{side}: rows [{lo},{hi}) = {k} ratings in {t:.2f} s")
-    per_iter = est["x"] + est["theta"]
-    return {"value": 1.0 / per_iter, "unit": "iterations/s", "cores": cores, "kind": "port",
-            "sample": "oracle/als_cpu.c (OpenMP) on " + "; ".join(sample_desc) + "; scaled by rating share"}
+    return 1.0 / (est["x"] + est["theta"]), "; ".join(sample_desc)
 
 
-def e2e_sharded(args, r, theta0, X0, f, lam, path, rank, local_rank, world, barrier):
-    """e2e at N > 1: cumf_als_b200.dist.ShardedAls over one AlsSolver per rank, from pinned HOST buffers -- every rank
-    uploads its CSR/CSC shard + the factors, runs K iterations with the row-block exchange and the per-iteration
-    all-reduced RMSE doALS prints (als.cu:991, 1018), and downloads the factors; max wall clock over ranks."""
+def cpu_baseline(r, theta0, X0, w, budget_s: float = 12.0):
+    """north_star: the CPU path on ONE thread (count stated); the all-core figure rides along."""
+    cores = os.cpu_count() or 1
+    out = {"unit": "iterations/s", "kind": "port"}
+    if _omp_set_threads(1):
+        v1, d1 = _cpu_sample(r, theta0, X0, w, budget_s)
+        out.update({"value": v1, "cores": 1, "sample": "oracle/als_cpu.c, 1 OpenMP thread, on " + d1 + "; scaled by rating share"})
+        _omp_set_threads(cores)
+        vn, dn = _cpu_sample(r, theta0, X0, w, budget_s)
+        out["all_cores"] = {"value": vn, "cores": cores, "sample": dn}
+    else:
+        vn, dn = _cpu_sample(r, theta0, X0, w, budget_s)
+        out.update({"value": vn, "cores": cores, "sample": "oracle/als_cpu.c (OpenMP, all cores: omp_set_num_threads unavailable) on " + dn})
+    return out
+
+
+def pin_inputs(r, theta0, X0):
+    """The reference's CLI keeps every input in pinned host memory (cudaMallocHost, main.cpp:50-69): same here."""
     import torch
-    import torch.distributed as dist
-    import cumf_als_b200 as c
-    from cumf_als_b200.data import nnz_balanced_ranges
-    from cumf_als_b200.dist import GpuEngine, ShardedAls
-
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row",
                  "test_row", "test_col", "test_val"):
         setattr(r, name, pin(getattr(r, name)))
-    th0, x0 = pin(theta0), pin(X0)
-    x_ranges = nnz_balanced_ranges(r.csr_indptr, world)
-    t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
+    return pin(theta0), pin(X0), pin
 
-    def call(iters):
-        s2 = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
-                         r.test_row, r.test_col, r.test_val, r.m, r.n, f, lam, x_range=x_ranges[rank],
-                         theta_range=t_ranges[rank], device=local_rank, path=path)
-        s2.set_factors(th0, x0)
-        sh = ShardedAls(GpuEngine(s2, local_rank), x_ranges, t_ranges, r.nnz, r.nnz_test)
-        fin = None
-        for _ in range(iters):
-            sh.step()
-            fin = sh.rmse()
-        out = s2.get_factors()
-        s2.close()
-        return fin, out
 
-    if args.warmup > 0:
-        call(1)
-    barrier()
+def e2e_doals(args, r, theta0, X0, f, lam, gpus: int, device: int):
+    """The reference-facing call with HOST buffers: cumf_doALS(host pointers, ITERS = steps) -- uploads, K iterations with the
+    per-iteration train/test RMSE doALS prints, factor download, release of every device buffer -- wall clock / K.  gpus > 1:
+    the same call with CUMF_GPUS=gpus (one process driving the GPUs, rows sharded inside the library)."""
+    import torch
+    import cumf_als_b200 as c
+    os.environ["CUMF_QUIET"] = "1"
+    os.environ["CUMF_PATH"] = args.path
+    os.environ["CUMF_GPUS"] = str(gpus)
+    th0, x0, pin = pin_inputs(r, theta0, X0)
+    # pinned host -> device copy rate of this box (the e2e number moves with it: 2.2 GB of ratings per call)
+    probe = torch.from_numpy(r.csr_data).cuda()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    src = torch.from_numpy(r.csr_data)
+    probe.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    e0.record()
+    probe.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = r.csr_data.nbytes / 1e9 / (e0.elapsed_time(e1) / 1e3)
+    del probe
+    torch.cuda.empty_cache()
+    call = lambda th, X, iters: c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz,
+                                         r.nnz_test, lam, iters, 1, 1, device)
+    if args.warmup > 0:   # context / allocator / driver warm-up outside the timed call, as in the reference arm
+        call(pin(theta0), pin(X0), 1)
+    th, X = pin(theta0), pin(X0)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    fin, _ = call(args.steps)
-    barrier()
+    fin = call(th, X, args.steps)
     wall = time.perf_counter() - t0
-    # bytes this rank moved: its rating shards + both full factors in, both full factors out; summed over ranks
-    xr0, xr1 = x_ranges[rank]
-    tr0, tr1 = t_ranges[rank]
-    xn = int(r.csr_indptr[xr1] - r.csr_indptr[xr0])      # CSR shard: column ids + values + COO rows (12 B per rating)
-    tn = int(r.csc_indptr[tr1] - r.csc_indptr[tr0])      # CSC shard: row ids + values (8 B per rating)
-    eff = ((r.nnz_test - 1) // 256) * 256                # test samples the reference's launch covers (als.cu:1006)
-    test_share = eff * xr1 // r.m - eff * xr0 // r.m
-    stats = [wall, float(xn * 12 + tn * 8 + test_share * 12 + th0.nbytes + x0.nbytes), float(th0.nbytes + x0.nbytes)]
-    if world > 1:
-        wt = torch.tensor([stats[0]], device="cuda", dtype=torch.float64)
-        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
-        bt = torch.tensor(stats[1:], device="cuda", dtype=torch.float64)
-        dist.all_reduce(bt)
-        stats = [float(wt.item()), float(bt[0].item()), float(bt[1].item())]
-    return {"value": args.steps / stats[0], "unit": "iterations/s", "h2d_bytes_per_step": int(stats[1]) // args.steps,
-            "d2h_bytes_per_step": int(stats[2]) // args.steps, "wall_s": stats[0],
-            "final_test_rmse": fin[1] if fin else None,
-            "what": "per rank: AlsSolver(host shard) + set_factors + K x (ShardedAls.step + all-reduced RMSE) + get_factors, "
-                    "pinned host buffers; max wall clock over ranks; one untimed 1-iteration call first"}
+    os.environ["CUMF_GPUS"] = "1"
+    ratings = (r.csr_indices.nbytes + r.csr_data.nbytes + r.csc_indices.nbytes + r.csc_data.nbytes + r.coo_row.nbytes +
+               r.test_row.nbytes + r.test_col.nbytes + r.test_val.nbytes)
+    return {"value": args.steps / wall, "unit": "iterations/s",
+            "h2d_bytes_per_step": (ratings + gpus * (th.nbytes + X.nbytes)) // args.steps,
+            "d2h_bytes_per_step": (th.nbytes + X.nbytes) // args.steps, "wall_s": wall, "pinned_h2d_gbs_this_box": h2d_gbs,
+            "final_test_rmse": fin, "gpus": gpus,
+            "what": "cumf_doALS(host pointers, ITERS=steps" + (f", CUMF_GPUS={gpus}" if gpus > 1 else "") + "): every rating "
+                    "slice uploaded once, both factors to every GPU, iterations with per-iteration train/test RMSE, ONE factor "
+                    "replica downloaded, all device buffers freed; one untimed 1-iteration call first (both arms)"}
 
 
 def run_ours(args, w):
@@ -235,49 +298,57 @@ def run_ours(args, w):
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    host_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_pg = dist.new_group(backend="gloo")        # host-side barriers that do not occupy the GPUs
     r, theta0, X0 = make_inputs(w, args.scale, "cuda")
     f, lam = w["f"], w["lam"]
     path = {"auto": c.PATH_AUTO, "simt": c.PATH_SIMT, "tc": c.PATH_TC}[args.path]
     os.environ["CUMF_TIME_KERNELS"] = "1"
 
-    if world == 1:
-        xr, tr_ = (0, r.m), (0, r.n)
-    else:
-        xr = nnz_balanced_ranges(r.csr_indptr, world)[rank]
-        tr_ = nnz_balanced_ranges(r.csc_indptr, world)[rank]
+    x_ranges = nnz_balanced_ranges(r.csr_indptr, world)
+    t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
+    xr, tr_ = x_ranges[rank], t_ranges[rank]
     solver = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
                          r.test_row, r.test_col, r.test_val, r.m, r.n, f, lam, x_range=xr, theta_range=tr_,
                          device=local_rank, path=path)
     solver.set_factors(theta0, X0)
-
-    if world > 1:
-        from cumf_als_b200.dist import GpuEngine, ShardedAls
-        x_ranges = nnz_balanced_ranges(r.csr_indptr, world)
-        t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
-        sharded = ShardedAls(GpuEngine(solver, local_rank), x_ranges, t_ranges, r.nnz, r.nnz_test)
-        step = sharded.iterate
-    else:
-        step = lambda k: solver.iterate(k)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    step(args.warmup)
+    if world > 1:
+        # connect the ranks' factor replicas (CUDA IPC): from here on every half-step stores its rows into all of them and
+        # ends with the device-side barrier -- the library's own multi-GPU path, no collective on the data path
+        blobs = [None] * world
+        dist.all_gather_object(blobs, solver.ipc_export())
+        solver.ipc_import(blobs, rank)
+        barrier()
+
+    def rmse():
+        tr, te = solver.sse()
+        if world > 1:
+            t = torch.tensor([tr, te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            tr, te = (float(v) for v in t.cpu())
+        f32 = np.float32
+        return float(np.sqrt(f32(tr) / f32(r.nnz))), float(np.sqrt(f32(te) / f32(r.nnz_test)))
+
+    solver.iterate(args.warmup)
     solver.timers(reset=True)
     barrier()
     with ClockSampler(local_rank) as clocks:
-        ms = step(args.steps)
+        ms = solver.iterate(args.steps)
         barrier()
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     tm = solver.timers()
-    train_rmse, test_rmse = (sharded.rmse() if world > 1 else solver.rmse())
+    train_rmse, test_rmse = rmse()
     iters_per_s = args.steps / (ms / 1e3)
 
     line = None
@@ -288,85 +359,52 @@ def run_ours(args, w):
         nnz_x = int(r.csr_indptr[xr[1]] - r.csr_indptr[xr[0]])
         nnz_t = int(r.csc_indptr[tr_[1]] - r.csc_indptr[tr_[0]])
         gb = (gram_bytes(xs, nnz_x, f, fused) + gram_bytes(ts, nnz_t, f, fused)) / 1e9   # per iteration, this rank
-        iters_done = tm["iterations"] if tm["iterations"] > 0 else args.steps      # sharded runs drive the half-steps directly
-        tm["iterations"] = iters_done
-        if world > 1:
-            tm["x_ms"], tm["theta_ms"] = tm["gram_x_ms"], tm["gram_theta_ms"]     # per-rank kernel time (rank 0)
-        gram_ms = (tm["gram_x_ms"] + tm["gram_theta_ms"]) / max(iters_done, 1)
+        iters_done = max(tm["iterations"], 1)
+        gx, gt = tm["gram_x_ms"] / iters_done, tm["gram_theta_ms"] / iters_done
+        gram_ms = gx + gt
         achieved = gb / (gram_ms / 1e3) if gram_ms > 0 else None
+        ncu = ncu_traffic(args.workload, "fused" if fused else "simt") if world == 1 and args.scale == 1.0 else None
+        impl = os.environ.get("CUMF_TC_IMPL", "")
         line = {
             "metric": METRIC.format(workload=args.workload, f=f), "value": iters_per_s,
             "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
-                       "lambda": lam, "solver": "cg6", "path": "tcgen05-fused" if fused else "simt-unfused",
-                       "sharding": "single GPU" if world == 1 else f"rows nnz-balanced over {world} ranks, all-gather",
-                       "l2": f"inputs exceed L2 (factors {(r.m + r.n) * f * 4 / 1e6:.0f} MB, ratings {r.nnz * 12 / 1e9:.1f} GB per "
-                             f"orientation): no flush"},
-            "x_ms": tm["x_ms"] / max(tm["iterations"], 1), "theta_ms": tm["theta_ms"] / max(tm["iterations"], 1),
+            "dtype": DTYPE if fused else "f32", "data": "synthetic",
+            "config": common_config(args, r, w),
+            "impl_detail": {"path": ("tcgen05-fused" + (f" (CUMF_TC_IMPL={impl})" if impl else "")) if fused else "simt-unfused",
+                            "sharding": "single GPU" if world == 1 else
+                            f"rows rating-balanced over {world} ranks; solver epilogues store rows into every rank's replica "
+                            f"(CUDA IPC peer pointers), flag-barrier kernel per half-step"},
+            "x_ms": tm["x_ms"] / iters_done, "theta_ms": tm["theta_ms"] / iters_done,
             "train_rmse": train_rmse, "test_rmse": test_rmse,
             "gpu_launches": int(tm["launches"]),
             "clocks": clocks.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": ncu_traffic(args.workload, "fused" if fused else "simt") if world == 1 and args.scale == 1.0 else None,
-                         "kernel": "gram (+rhs" + (" + fused CG)" if fused else ")") + " X side + theta side",
+                         "traffic": (sum(v.get("dram_bytes", 0) for v in ncu.values() if isinstance(v, dict)) or None) if ncu else None,
+                         "kernel": "gram (+rhs" + (" + fused CG)" if fused else ")") + ", X-side launch + theta-side launch (rank 0)",
                          "bytes_per_iteration_gb": gb, "kernel_ms_per_iteration": gram_ms,
-                         "gram_x_ms": tm["gram_x_ms"] / max(tm["iterations"], 1),
-                         "gram_theta_ms": tm["gram_theta_ms"] / max(tm["iterations"], 1),
-                         "formula": "B_gram_fused" if fused else "B_gram (materialised A)", "peak_source": peak_src},
+                         "formula": "B_gram_fused" if fused else "B_gram (materialised A)", "peak_source": peak_src,
+                         "traffic_source": (ncu or {}).get("source"),
+                         "launches": {"x_side": launch_roofline(xs, nnz_x, f, fused, gx, (ncu or {}).get("x_side")),
+                                      "theta_side": launch_roofline(ts, nnz_t, f, fused, gt, (ncu or {}).get("theta_side")),
+                                      "tensor_peak_source": tensor_peak()[1]}},
         }
     solver.close()
+    torch.cuda.empty_cache()
 
-    # e2e: the reference-facing call with host buffers (rank 0 of a single-GPU run; under
-    # torchrun every rank would repeat the same whole-job call, so it is only timed at N=1)
-    if rank == 0 and world == 1 and not args.no_e2e:
-        os.environ["CUMF_QUIET"] = "1"
-        os.environ["CUMF_PATH"] = args.path
-        # the reference's CLI keeps every input in pinned host memory (cudaMallocHost, main.cpp:50-69): same here
-        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row",
-                     "test_row", "test_col", "test_val"):
-            setattr(r, name, pin(getattr(r, name)))
-        # pinned host -> device copy rate of this box (the e2e number moves with it: 2.2 GB of ratings per call)
-        probe = torch.from_numpy(r.csr_data).cuda()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        src = torch.from_numpy(r.csr_data)
-        probe.copy_(src, non_blocking=True)
-        torch.cuda.synchronize()
-        e0.record()
-        probe.copy_(src, non_blocking=True)
-        e1.record()
-        torch.cuda.synchronize()
-        h2d_gbs = r.csr_data.nbytes / 1e9 / (e0.elapsed_time(e1) / 1e3)
-        del probe
-        if args.warmup > 0:   # allocator / driver warm-up outside the timed call, as in the reference arm
-            c.do_als(*r.doals_args(), pin(theta0), pin(X0), r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz,
-                     r.nnz_test, lam, 1, 1, 1, local_rank)
-        th, X = pin(theta0), pin(X0)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        fin = c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz, r.nnz_test, lam,
-                       args.steps, 1, 1, local_rank)
-        wall = time.perf_counter() - t0
-        h2d = (r.csr_indices.nbytes + r.csr_data.nbytes + r.csc_indices.nbytes + r.csc_data.nbytes + r.coo_row.nbytes +
-               r.test_row.nbytes + r.test_col.nbytes + r.test_val.nbytes + th.nbytes + X.nbytes)
-        line["e2e"] = {"value": args.steps / wall, "unit": "iterations/s", "h2d_bytes_per_step": h2d // args.steps,
-                       "d2h_bytes_per_step": (th.nbytes + X.nbytes) // args.steps, "wall_s": wall,
-                       "pinned_h2d_gbs_this_box": h2d_gbs,
-                       "final_test_rmse": fin,
-                       "what": "doALS(host pointers, ITERS=steps): upload + iterations + per-iteration RMSE + download; "
-                               "one untimed 1-iteration call first (both arms)"}
-    # e2e at N > 1: the sharded public API from pinned host buffers (CUMF_BENCH_SHARDED_E2E=1 exercises it on one GPU)
-    force_sharded = os.environ.get("CUMF_BENCH_SHARDED_E2E") == "1"
-    if (world > 1 or force_sharded) and not args.no_e2e:
-        try:
-            e2e = e2e_sharded(args, r, theta0, X0, f, lam, path, rank, local_rank, world, barrier)
-        except Exception as exc:        # the resident numbers above stay valid; every rank fails the same way
-            e2e = {"error": f"{type(exc).__name__}: {exc}"}
+    # e2e: the reference-facing call with host buffers.  N > 1: rank 0 alone calls cumf_doALS with CUMF_GPUS=N (the library
+    # shards inside the call); the other ranks have released their shards and wait on a host-side (gloo) barrier.
+    if not args.no_e2e:
+        if world > 1:
+            dist.barrier(group=host_pg)
         if rank == 0:
-            line["e2e_sharded" if world == 1 else "e2e"] = e2e
+            try:
+                line["e2e"] = e2e_doals(args, r, theta0, X0, f, lam, world, local_rank)
+            except Exception as exc:        # the resident numbers above stay valid
+                line["e2e"] = {"error": f"{type(exc).__name__}: {exc}"}
+        if world > 1:
+            dist.barrier(group=host_pg)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(r, theta0, X0, w)
     if rank == 0:
@@ -443,12 +481,11 @@ def run_ours_partial_gram(args, w):
             "metric": METRIC.format(workload=args.workload, f=f), "value": args.steps / (ms / 1e3),
             "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
-                       "lambda": lam, "solver": "cg6", "path": "tcgen05" if fused else "simt",
-                       "sharding": f"theta rows nnz-balanced over {world} ranks; X-step = partial [A|b] + NCCL all-reduce "
-                                   f"+ replicated CG; theta-step rank-local (no factor exchange)",
-                       "l2": "inputs exceed L2: no flush"},
+            "dtype": DTYPE if fused else "f32", "data": "synthetic",
+            "config": common_config(args, r, w),
+            "impl_detail": {"path": "tcgen05" if fused else "simt",
+                            "sharding": f"theta rows nnz-balanced over {world} ranks; X-step = partial [A|b] + NCCL all-reduce "
+                                        f"+ replicated CG; theta-step rank-local (no factor exchange)"},
             "phases_ms": phases, "allreduce_bytes_per_iteration": drv.allreduce_bytes // max(args.steps, 1),
             "train_rmse": train_rmse, "test_rmse": test_rmse, "gpu_launches": int(eng.launches),
             "clocks": clocks.summary(),
@@ -499,9 +536,9 @@ def run_reference(args, w):
                  "test_row", "test_col", "test_val"):
         setattr(r, name, pin(getattr(r, name)))
     theta0, X0 = pin(theta0), pin(X0)
-    if args.warmup > 0:   # context / cuBLAS / cuSPARSE initialisation outside the timed call
+    if args.warmup > 0:   # context / cuBLAS / cuSPARSE initialisation outside the timed call: W iterations, like the other arm
         with CaptureStdout():
-            O.ref_do_als(r, theta0.copy(), X0.copy(), f, lam, 1, xb, tb, variant, local_rank)
+            O.ref_do_als(r, theta0.copy(), X0.copy(), f, lam, args.warmup, xb, tb, variant, local_rank)
     th, X = pin(theta0), pin(X0)
     iters = args.steps
     with ClockSampler(local_rank) as clocks:
@@ -521,12 +558,13 @@ def run_reference(args, w):
     gram_s = (sum(kx) + sum(kt)) / iters if kx else None
     line = {
         "impl": "reference", "metric": METRIC.format(workload=args.workload, f=f), "value": value,
-        "unit": "iterations/s", "n_gpus": 1, "steps": iters, "warmup": 0, "ms_per_step": 1e3 * als_s / iters,
+        "unit": "iterations/s", "n_gpus": 1, "steps": iters, "warmup": args.warmup, "ms_per_step": 1e3 * als_s / iters,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "m": r.m, "n": r.n, "nnz": r.nnz, "nnz_test": r.nnz_test, "f": f,
-                   "lambda": lam, "solver": "cg6" if variant == "cg" else "cublas-lu", "X_BATCH": xb, "THETA_BATCH": tb,
-                   "what": "unmodified reference sources (oracle/_ref), Kepler-era kernels recompiled for sm_100a; value = "
-                           "iterations / sum of its own `update X run`+`update theta run` timers (als.cu:850, 963)"},
+        "config": common_config(args, r, w),
+        "impl_detail": {"solver": "cg6" if variant == "cg" else "cublas-lu (getrfBatched, no pivoting)", "X_BATCH": xb, "THETA_BATCH": tb,
+                        "what": "unmodified reference sources (oracle/_ref), Kepler-era kernels recompiled for sm_100a; value = "
+                                "iterations / sum of its own `update X run`+`update theta run` timers (als.cu:850, 963); "
+                                "one untimed call of `warmup` iterations first"},
         "e2e": {"value": iters / wall, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "wall_s": wall},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "reference",

@@ -562,7 +562,8 @@ def test_tc_half_step_both_stagings_vs_simt(cuda, monkeypatch, direct):
 
 
 def test_plan_factor_rows_hint_saves_the_index_scan(cuda, monkeypatch):
-    """cumf_plan_set_factor_rows: same result, one kernel launch less on the first call (no scan of the column ids)."""
+    """cumf_plan_set_factor_rows: same result and no stream synchronisation on the first call -- the scan of the column ids
+    still runs (it validates the hint) but asynchronously, its verdict is read by the plan's next launch."""
     monkeypatch.setenv("CUMF_TC_DIRECT", "1")
     rng = np.random.default_rng(13)
     n, f, lam = 3000, 100, 0.05
@@ -582,12 +583,50 @@ def test_plan_factor_rows_hint_saves_the_index_scan(cuda, monkeypatch):
         launches.append(plan.last_launches)
         plan.close()
     assert np.array_equal(res[0], res[1])
-    assert launches[1] == launches[0] - 1
+    assert launches[1] <= launches[0]
 
 
-def test_doals_twice_reuses_cached_buffers_and_matches(cuda):
-    """cumf_als_destroy keeps the device buffers for the next solver; a second doALS on the same inputs must give the
-    same factors and RMSE, and cumf_release_cached_memory must hand the memory back."""
+def test_plan_factor_rows_hint_too_small_is_reported(cuda, monkeypatch):
+    """A hint smaller than the largest column id + 1 would gather out-of-bounds rows as zeros: the asynchronous validation
+    turns that into CUMF_EINVAL on the plan's next launch instead of a silently wrong Gram."""
+    rng = np.random.default_rng(14)
+    n, f = 3000, 100
+    lengths = [int(x) for x in rng.integers(1, 300, 200)]
+    rowptr, colidx, val = random_csr(rng, lengths, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    plan = c.Plan(rowptr, 0, len(lengths), f, c.PATH_TC)
+    plan.set_factor_rows(int(colidx.max()))            # one too few
+    x = dev(cuda, np.zeros((len(lengths), f), np.float32))
+    args = (plan, dev(cuda, colidx), dev(cuda, val), dev(cuda, factor), x, 0.05)
+    c.update_factor(*args)
+    cuda.cuda.synchronize()
+    with pytest.raises(c.CumfError, match="exceeds"):
+        c.update_factor(*args)
+    plan.close()
+
+
+def test_doals_frees_its_device_memory_by_default(cuda, monkeypatch):
+    """Like the reference (als.cu:1026-1033), doALS returns with its device buffers released: the buffer cache is opt-in."""
+    monkeypatch.delenv("CUMF_CACHE_MB", raising=False)
+    monkeypatch.setenv("CUMF_QUIET", "1")
+    f, lam = 100, 0.048
+    r = synth_ratings(3000, 5000, 400000, 20000, seed=5)
+    theta0, X0 = init_factors(r.m, r.n, f, seed=2)
+    c.load_library().cumf_release_cached_memory()
+    call = lambda: c.do_als(*r.doals_args(), theta0.copy(), X0.copy(), r.test_row, r.test_col, r.test_val, r.m, r.n, f, r.nnz,
+                            r.nnz_test, lam, 1, 1, 1, 0)
+    call()                                  # context-level allocations (module load, cuBLAS-free path) happen once
+    cuda.cuda.synchronize()
+    free0 = cuda.cuda.mem_get_info()[0]
+    call()
+    cuda.cuda.synchronize()
+    assert cuda.cuda.mem_get_info()[0] >= free0 - (1 << 20), "doALS kept device memory after returning"
+
+
+def test_doals_twice_reuses_cached_buffers_and_matches(cuda, monkeypatch):
+    """CUMF_CACHE_MB=<n> (opt-in): cumf_als_destroy keeps the device buffers for the next solver; a second doALS on the same
+    inputs must give the same factors and RMSE, and cumf_release_cached_memory must hand the memory back."""
+    monkeypatch.setenv("CUMF_CACHE_MB", "4096")
     f, lam, iters = 100, 0.048, 2
     r = synth_ratings(300, 500, 20000, 2000, seed=5)
     theta0, X0 = init_factors(r.m, r.n, f, seed=2)

@@ -1,7 +1,7 @@
 """Workload for ncu captures of the hot kernels (GPU box):
     ncu --set full --import-source on -k regex:als_fused -s 2 -c 2 -o gpurun_out/prof python tools/profile_fused.py
 One warm-up iteration, then one profiled ALS iteration (X side launch, theta side launch) on
-the Netflix-shaped workload (optionally scaled: argv[1] = scale, argv[2] = path auto|simt|tc)."""
+the Netflix-shaped workload (optionally scaled: argv[1] = scale, argv[2] = path auto|simt|tc, argv[3] = bench workload)."""
 import sys
 from pathlib import Path
 
@@ -16,7 +16,7 @@ import cumf_als_b200 as c  # noqa: E402
 def main():
     scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
     path = {"auto": c.PATH_AUTO, "simt": c.PATH_SIMT, "tc": c.PATH_TC}[sys.argv[2] if len(sys.argv) > 2 else "auto"]
-    w = bench.WORKLOADS["netflix"]
+    w = bench.WORKLOADS[sys.argv[3] if len(sys.argv) > 3 else "netflix"]
     r, theta0, X0 = bench.make_inputs(w, scale, "cuda")
     s = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
                     r.test_row, r.test_col, r.test_val, r.m, r.n, w["f"], w["lam"], path=path)
