@@ -65,6 +65,13 @@ SIGNATURES = {
     "cumf_als_create": (C.c_int, [C.POINTER(_vp)] + [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_long, C.c_long,
                                                                    C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                                                    C.c_int, C.c_int, C.c_int]),
+    "cumf_als_create64": (C.c_int, [C.POINTER(_vp)] + [_vp] * 10 + [C.c_int, C.c_int, C.c_int, C.c_long, C.c_long,
+                                                                     C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                     C.c_int, C.c_int, C.c_int]),
+    "cumf_als_create_device": (C.c_int, [C.POINTER(_vp)] + [_vp] * 9 + [C.c_long, C.c_int, C.c_int, C.c_int, C.c_long, C.c_long,
+                                                                         C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                         C.c_int, C.c_int, C.c_int]),
+    "cumf_plan_create64": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "cumf_als_destroy": (C.c_int, [_vp]),
     "cumf_als_collect_train_sse": (C.c_int, [_vp, C.c_int]),
     "cumf_als_set_factors": (C.c_int, [_vp, _vp, _vp]),

@@ -77,16 +77,17 @@ int DevBuf::alloc(size_t n) {
     return CUMF_OK;
 }
 void DevBuf::release() {
-    if (p) cudaFree(p);
+    if (p && !borrowed) cudaFree(p);
     p = nullptr;
     bytes = 0;
+    borrowed = false;
 }
 // the caller guarantees that no work touching the buffer is in flight
 void DevBuf::release_to_cache() {
     const char* v = getenv("CUMF_CACHE_MB");
     const size_t cap = (size_t)((v && *v) ? std::max(0L, atol(v)) : 0) << 20;
     std::unique_lock<std::mutex> lock(g_buf_cache_mutex);
-    if (p && bytes >= kCacheMinBytes && g_buf_cache_bytes + bytes <= cap) {
+    if (p && !borrowed && bytes >= kCacheMinBytes && g_buf_cache_bytes + bytes <= cap) {
         int dev = 0;
         cudaGetDevice(&dev);
         g_buf_cache.push_back(CachedBuf{p, bytes, dev});
@@ -347,9 +348,13 @@ static void plan_free(cumf_plan* p, bool cache = false) {
 // to materialise A through the fused kernel.
 // The rating range of row r is [h_begin[r], h_end[r]) (absolute positions in colidx/val).  With a CSR row
 // pointer that is (rowptr[r], rowptr[r+1]); the partial-Gram scheme passes narrower per-row ranges.
-static int plan_create_core(cumf_plan** out, const long long* h_begin, const long long* h_end, int rows, int row_begin,
-                            int row_end, int f, int path, bool alloc_workspace, bool force_slots) {
-    CUMF_REQUIRE(out && h_begin && h_end, "null pointer");
+// h_begin / h_end are indexed by (row - index_base): callers that hold pointers for their own rows only (a shard of a
+// 50 M-row matrix) do not have to materialise arrays over all rows.
+static int plan_create_core(cumf_plan** out, const long long* h_begin_in, const long long* h_end_in, int rows, int row_begin,
+                            int row_end, int f, int path, bool alloc_workspace, bool force_slots, int index_base = 0) {
+    const long long* h_begin = h_begin_in ? h_begin_in - index_base : nullptr;
+    const long long* h_end = h_end_in ? h_end_in - index_base : nullptr;
+    CUMF_REQUIRE(out && h_begin_in && h_end_in, "null pointer");
     CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
     CUMF_TRY(check_f(f));
     CUMF_TRY(check_device());
@@ -471,14 +476,23 @@ static int plan_create_impl(cumf_plan** out, const int* h_rowptr, int rows, int 
                             int path, bool alloc_workspace, bool force_slots = false) {
     CUMF_REQUIRE(out && h_rowptr, "null pointer");
     CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
-    std::vector<long long> b(rows + 1), e(rows + 1);
-    for (int r = row_begin; r < row_end; ++r) { b[r] = h_rowptr[r]; e[r] = h_rowptr[r + 1]; }
-    return plan_create_core(out, b.data(), e.data(), rows, row_begin, row_end, f, path, alloc_workspace, force_slots);
+    std::vector<long long> ptr((size_t)(row_end - row_begin) + 1);
+    for (int r = row_begin; r <= row_end; ++r) ptr[r - row_begin] = h_rowptr[r];
+    return plan_create_core(out, ptr.data(), ptr.data() + 1, rows, row_begin, row_end, f, path, alloc_workspace, force_slots, row_begin);
 }
 
 extern "C" int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end, int f,
                                 int path) {
     return plan_create_impl(out, h_rowptr, rows, row_begin, row_end, f, path, true);
+}
+
+// 64-bit row pointers (hugewiki.cu:2266 squeezes its 3.1 G ratings through `unsigned int`; here the pointer array is int64
+// and only the ratings of ONE plan -- one shard -- must number < 2^31)
+extern "C" int cumf_plan_create64(cumf_plan** out, const long long* h_rowptr, int rows, int row_begin, int row_end, int f,
+                                  int path) {
+    CUMF_REQUIRE(out && h_rowptr, "null pointer");
+    CUMF_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= rows, "bad row range");
+    return plan_create_core(out, h_rowptr + row_begin, h_rowptr + row_begin + 1, rows, row_begin, row_end, f, path, true, false, row_begin);
 }
 
 // Partial-Gram plan: all `rows` rows, row r restricted to ratings [h_begin[r], h_end[r]).  On the fused path
@@ -826,21 +840,36 @@ static int upload(DevBuf& buf, const T* host, size_t count, cudaStream_t st) {
     return CUMF_OK;
 }
 
+// What one shard is built from: the row pointers of its OWN rows / columns, rebased to 0 (int64: a whole matrix may hold
+// more than 2^31 ratings, one shard may not), and its slices of the rating arrays -- in host memory (uploaded here) or
+// already on the device (borrowed: the caller keeps them alive; the sharded generator / loader path).
+struct ShardSource {
+    std::vector<long long> x_ptr, t_ptr;      // (x_end - x_begin + 1), (t_end - t_begin + 1) entries
+    bool on_device = false;
+    const int* csr_col = nullptr; const float* csr_val = nullptr;
+    const int* csc_row = nullptr; const float* csc_val = nullptr;
+    const int* coo_row = nullptr;             // host mode: this shard's slice of cooRowIndex, or null
+    bool coo_is_csr = false;                  // device mode: the train samples ARE the CSR entries (no cooRowIndex array)
+    const int* test_row = nullptr; const int* test_col = nullptr; const float* test_val = nullptr;
+    long test_cnt = 0;                        // this shard's share of the launched test samples
+};
+
+template <typename T>
+static int adopt(DevBuf& buf, const T* src, size_t count, bool on_device, cudaStream_t st) {
+    if (on_device) { buf.borrow(const_cast<T*>(src), sizeof(T) * count); return CUMF_OK; }
+    return upload(buf, src, count, st);
+}
+
 // wait_uploads = false leaves the rating uploads in flight when it returns (the half-steps and the RMSE wait on
 // their events): only for callers that keep the host arrays alive until the first RMSE, i.e. cumf_doALS.
-static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
-                           const float* csrValHostPtr, const int* cscRowIndexHostPtr,
-                           const int* cscColIndexHostPtr, const float* cscValHostPtr,
-                           const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
-                           const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
-                           long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
-                           int device, int solver, int path, bool wait_uploads,
-                           const float* thetaTHost = nullptr, const float* XTHost = nullptr) {
-    CUMF_REQUIRE(out && csrRowIndexHostPtr && csrColIndexHostPtr && csrValHostPtr && cscRowIndexHostPtr &&
-                     cscColIndexHostPtr && cscValHostPtr, "null pointer");
+static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m, int n, int f, long nnz, long nnz_test,
+                           float lambda, int x_begin, int x_end, int t_begin, int t_end, int device, int solver, int path,
+                           bool wait_uploads, const float* thetaTHost, const float* XTHost) {
+    CUMF_REQUIRE(out, "null pointer");
     CUMF_REQUIRE(m > 0 && n > 0 && nnz >= 0 && nnz_test >= 0, "bad sizes");
     CUMF_REQUIRE(0 <= x_begin && x_begin <= x_end && x_end <= m, "bad X row range");
     CUMF_REQUIRE(0 <= t_begin && t_begin <= t_end && t_end <= n, "bad theta row range");
+    CUMF_REQUIRE(src.x_ptr.size() == (size_t)(x_end - x_begin) + 1 && src.t_ptr.size() == (size_t)(t_end - t_begin) + 1, "row pointer slices");
     CUMF_TRY(check_f(f));
     CUMF_CUDA_TRY(cudaSetDevice(device));
     CUMF_TRY(check_device());
@@ -851,11 +880,9 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     s->device = device; s->solver = solver; s->path = path;
     int rc = CUMF_OK;
     auto fail = [&](int code) { cumf_als_destroy(s); return code; };
-
-    // note the reference's argument order for CSC (main.cpp:99-101, als.cu:867-869):
-    // cscColIndex is the pointer array (n+1), cscRowIndex the row ids (nnz).
-    const long long xo = csrRowIndexHostPtr[x_begin], xn = (long long)csrRowIndexHostPtr[x_end] - xo;
-    const long long to = cscColIndexHostPtr[t_begin], tn = (long long)cscColIndexHostPtr[t_end] - to;
+    const long long xn = src.x_ptr.back() - src.x_ptr.front(), tn = src.t_ptr.back() - src.t_ptr.front();
+    CUMF_REQUIRE(xn == 0 || (src.csr_col && src.csr_val), "CSR slice");
+    CUMF_REQUIRE(tn == 0 || (src.csc_row && src.csc_val), "CSC slice");
     // Order: what the first X half-step needs goes to the copy engine first (factors, CSR), the work plans are built on
     // the host while those 1 GB are in flight, then the CSC / COO / test uploads follow; each group has its event.
     const bool debug = env_long("CUMF_DEBUG", 0) != 0;
@@ -870,7 +897,8 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     cudaStream_t up = s->up_stream;
     // the plan of the first half-step before anything is on the copy engine (its small synchronous copies would queue
     // behind the uploads); the theta-side plan is built while factors + CSR are in flight
-    if ((rc = cumf_plan_create(&s->px, csrRowIndexHostPtr, m, x_begin, x_end, f, path)) != CUMF_OK) return fail(rc);
+    if ((rc = plan_create_core(&s->px, src.x_ptr.data(), src.x_ptr.data() + 1, m, x_begin, x_end, f, path, true, false, x_begin)) != CUMF_OK)
+        return fail(rc);
     if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
     if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
     // initial factors (optional here; cumf_als_set_factors otherwise) go first: the X half-step needs them
@@ -879,41 +907,41 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
         set_last_error("cumf_als_create: factor upload failed");
         return fail(CUMF_ECUDA);
     }
-    if ((rc = upload(s->csr_col, csrColIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
-    if ((rc = upload(s->csr_val, csrValHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
+    if ((rc = adopt(s->csr_col, src.csr_col, (size_t)xn, src.on_device, up)) != CUMF_OK) return fail(rc);
+    if ((rc = adopt(s->csr_val, src.csr_val, (size_t)xn, src.on_device, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csr, up);
-    if ((rc = upload(s->csc_row, cscRowIndexHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
-    if ((rc = upload(s->csc_val, cscValHostPtr + to, (size_t)tn, up)) != CUMF_OK) return fail(rc);
+    if ((rc = adopt(s->csc_row, src.csc_row, (size_t)tn, src.on_device, up)) != CUMF_OK) return fail(rc);
+    if ((rc = adopt(s->csc_val, src.csc_val, (size_t)tn, src.on_device, up)) != CUMF_OK) return fail(rc);
     cudaEventRecord(s->ev_csc, up);
     const double t_plans = wall_seconds();
-    if ((rc = cumf_plan_create(&s->pt, cscColIndexHostPtr, n, t_begin, t_end, f, path)) != CUMF_OK) return fail(rc);
+    if ((rc = plan_create_core(&s->pt, src.t_ptr.data(), src.t_ptr.data() + 1, n, t_begin, t_end, f, path, true, false, t_begin)) != CUMF_OK)
+        return fail(rc);
     const double t_plans_end = wall_seconds();
     s->px->time_kernel = s->pt->time_kernel = (env_long("CUMF_TIME_KERNELS", 0) != 0);
     cumf_plan_set_factor_rows(s->px, n);     // X rows gather theta rows, and vice versa
     cumf_plan_set_factor_rows(s->pt, m);
+    const bool have_train = src.coo_row != nullptr || src.coo_is_csr;
     // train RMSE as a by-product of the theta half-step (see cumf_als_sse); CUMF_SSE_DIRECT=1 keeps the streaming kernel
     // (a shard's by-product covers the ratings of its theta rows = its CSC slice; over all shards that is every rating once)
-    s->can_collect_sse = (s->pt->path == CUMF_PATH_TC && solver == CUMF_SOLVER_CG && cooRowIndexHostPtr != nullptr &&
-                          env_long("CUMF_SSE_DIRECT", 0) == 0);
+    s->can_collect_sse = (s->pt->path == CUMF_PATH_TC && solver == CUMF_SOLVER_CG && have_train && env_long("CUMF_SSE_DIRECT", 0) == 0);
     if ((rc = s->sse.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
     if ((rc = s->partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
     if ((rc = s->prep.alloc(sizeof(double) * 2)) != CUMF_OK) return fail(rc);
     if ((rc = s->prep_partials.alloc(sizeof(double) * sse_partial_capacity())) != CUMF_OK) return fail(rc);
     cudaMemsetAsync(s->prep.p, 0, sizeof(double) * 2, up);
-    if (cooRowIndexHostPtr) {
-        if ((rc = upload(s->coo_row, cooRowIndexHostPtr + xo, (size_t)xn, up)) != CUMF_OK) return fail(rc);
+    if (src.coo_row) {
+        if ((rc = upload(s->coo_row, src.coo_row, (size_t)xn, up)) != CUMF_OK) return fail(rc);
         s->train_cnt = (long)xn;
+    } else if (src.coo_is_csr) {
+        s->train_cnt = (long)xn;
+        s->train_mode = 2;                  // walk the CSR rows: the samples are the matrix entries by construction
     }
     s->csc_cnt = (long)tn;
-    if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
-        // samples the reference's launch covers: 256*((nnz_test-1)/256) (als.cu:1006); this
-        // shard's share is the contiguous slice proportional to its X row range.
-        const long long eff = ((long long)(nnz_test - 1) / 256) * 256;
-        const long long t0 = eff * x_begin / m, t1 = eff * x_end / m;
-        if ((rc = upload(s->test_row, cooRowIndexTestHostPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
-        if ((rc = upload(s->test_col, cooColIndexTestHostPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
-        if ((rc = upload(s->test_val, cooValHostTestPtr + t0, (size_t)(t1 - t0), up)) != CUMF_OK) return fail(rc);
-        s->test_cnt = (long)(t1 - t0);
+    if (src.test_row && src.test_col && src.test_val && src.test_cnt > 0) {
+        if ((rc = adopt(s->test_row, src.test_row, (size_t)src.test_cnt, src.on_device, up)) != CUMF_OK) return fail(rc);
+        if ((rc = adopt(s->test_col, src.test_col, (size_t)src.test_cnt, src.on_device, up)) != CUMF_OK) return fail(rc);
+        if ((rc = adopt(s->test_val, src.test_val, (size_t)src.test_cnt, src.on_device, up)) != CUMF_OK) return fail(rc);
+        s->test_cnt = src.test_cnt;
     }
     // One-time RMSE preparation behind the last upload (kernels on this stream queue behind the persistent half-step
     // kernel that owns every SM, so anything placed before an upload would hold that upload back):
@@ -923,7 +951,7 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
                                sse_partial_capacity(), up)) != CUMF_OK) return fail(rc);
         s->prep_r2 = true;
     }
-    if (cooRowIndexHostPtr && env_long("CUMF_SSE_LITERAL", 0) == 0 && xn > 0) {
+    if (src.coo_row && env_long("CUMF_SSE_LITERAL", 0) == 0 && xn > 0) {
         // is cooRowIndex the CSR row expansion?  (decides the train-RMSE walk, see cumf_als_sse)
         if ((rc = launch_coo_check(s->px->d_chunks.as<Chunk>(), (int)s->px->chunks.size(), s->coo_row.as<int>(),
                                    reinterpret_cast<int*>(s->prep.p), up)) != CUMF_OK) return fail(rc);
@@ -941,6 +969,56 @@ static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr,
     return CUMF_OK;
 }
 
+// host arrays over the WHOLE matrix (the reference's ten arrays), row pointers int32 or int64
+template <typename PtrT>
+static int als_create_host(cumf_als_solver** out, const PtrT* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                           const float* csrValHostPtr, const int* cscRowIndexHostPtr, const PtrT* cscColIndexHostPtr,
+                           const float* cscValHostPtr, const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                           const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f, long nnz,
+                           long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end, int device, int solver,
+                           int path, bool wait_uploads, const float* thetaTHost, const float* XTHost) {
+    CUMF_REQUIRE(out && csrRowIndexHostPtr && csrColIndexHostPtr && csrValHostPtr && cscRowIndexHostPtr &&
+                     cscColIndexHostPtr && cscValHostPtr, "null pointer");
+    CUMF_REQUIRE(m > 0 && n > 0, "bad sizes");
+    CUMF_REQUIRE(0 <= x_begin && x_begin <= x_end && x_end <= m, "bad X row range");
+    CUMF_REQUIRE(0 <= t_begin && t_begin <= t_end && t_end <= n, "bad theta row range");
+    // note the reference's argument order for CSC (main.cpp:99-101, als.cu:867-869):
+    // cscColIndex is the pointer array (n+1), cscRowIndex the row ids (nnz).
+    ShardSource src;
+    const long long xo = (long long)csrRowIndexHostPtr[x_begin], to = (long long)cscColIndexHostPtr[t_begin];
+    src.x_ptr.resize((size_t)(x_end - x_begin) + 1);
+    for (int r = x_begin; r <= x_end; ++r) src.x_ptr[r - x_begin] = (long long)csrRowIndexHostPtr[r] - xo;
+    src.t_ptr.resize((size_t)(t_end - t_begin) + 1);
+    for (int r = t_begin; r <= t_end; ++r) src.t_ptr[r - t_begin] = (long long)cscColIndexHostPtr[r] - to;
+    src.csr_col = csrColIndexHostPtr + xo; src.csr_val = csrValHostPtr + xo;
+    src.csc_row = cscRowIndexHostPtr + to; src.csc_val = cscValHostPtr + to;
+    src.coo_row = cooRowIndexHostPtr ? cooRowIndexHostPtr + xo : nullptr;
+    if (cooRowIndexTestHostPtr && cooColIndexTestHostPtr && cooValHostTestPtr && nnz_test > 0) {
+        // samples the reference's launch covers: 256*((nnz_test-1)/256) (als.cu:1006); this
+        // shard's share is the contiguous slice proportional to its X row range.
+        const long long eff = ((long long)(nnz_test - 1) / 256) * 256;
+        const long long t0 = eff * x_begin / m, t1 = eff * x_end / m;
+        src.test_row = cooRowIndexTestHostPtr + t0; src.test_col = cooColIndexTestHostPtr + t0; src.test_val = cooValHostTestPtr + t0;
+        src.test_cnt = (long)(t1 - t0);
+    }
+    return als_create_core(out, src, m, n, f, nnz, nnz_test, lambda, x_begin, x_end, t_begin, t_end, device, solver, path,
+                           wait_uploads, thetaTHost, XTHost);
+}
+
+static int als_create_impl(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                           const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                           const int* cscColIndexHostPtr, const float* cscValHostPtr,
+                           const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                           const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                           long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                           int device, int solver, int path, bool wait_uploads,
+                           const float* thetaTHost = nullptr, const float* XTHost = nullptr) {
+    return als_create_host<int>(out, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
+                                cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
+                                cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, x_begin, x_end,
+                                t_begin, t_end, device, solver, path, wait_uploads, thetaTHost, XTHost);
+}
+
 extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
                                const float* csrValHostPtr, const int* cscRowIndexHostPtr,
                                const int* cscColIndexHostPtr, const float* cscValHostPtr,
@@ -952,6 +1030,45 @@ extern "C" int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHost
                            cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
                            cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, x_begin, x_end,
                            t_begin, t_end, device, solver, path, /*wait_uploads=*/true);
+}
+
+// Same with int64 row / column pointer arrays: matrices beyond 2^31 ratings (hugewiki.cu:27-42: 3.1 G), of which this
+// shard's slices must hold < 2^31 each.
+extern "C" int cumf_als_create64(cumf_als_solver** out, const long long* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                                 const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                                 const long long* cscColIndexHostPtr, const float* cscValHostPtr,
+                                 const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                                 const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                                 long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                                 int device, int solver, int path) {
+    return als_create_host<long long>(out, csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
+                                      cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
+                                      cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, x_begin,
+                                      x_end, t_begin, t_end, device, solver, path, /*wait_uploads=*/true, nullptr, nullptr);
+}
+
+// A shard whose rating slices are ALREADY on `device` (generated there, or loaded there shard by shard: no pass through a
+// host copy of the whole matrix).  h_csr_ptr / h_csc_ptr: the shard's own row / column pointers, rebased to 0
+// (x_end - x_begin + 1 and t_end - t_begin + 1 entries, host).  The device arrays are borrowed: they must outlive the
+// solver.  The train samples are the CSR entries themselves; test samples (optional) are this shard's own list.
+extern "C" int cumf_als_create_device(cumf_als_solver** out, const long long* h_csr_ptr, const int* d_csr_col,
+                                      const float* d_csr_val, const long long* h_csc_ptr, const int* d_csc_row,
+                                      const float* d_csc_val, const int* d_test_row, const int* d_test_col,
+                                      const float* d_test_val, long test_cnt, int m, int n, int f, long nnz, long nnz_test,
+                                      float lambda, int x_begin, int x_end, int t_begin, int t_end, int device, int solver,
+                                      int path) {
+    CUMF_REQUIRE(out && h_csr_ptr && h_csc_ptr, "null pointer");
+    CUMF_REQUIRE(0 <= x_begin && x_begin <= x_end && 0 <= t_begin && t_begin <= t_end, "bad ranges");
+    ShardSource src;
+    src.on_device = true;
+    src.coo_is_csr = true;
+    src.x_ptr.assign(h_csr_ptr, h_csr_ptr + (size_t)(x_end - x_begin) + 1);
+    src.t_ptr.assign(h_csc_ptr, h_csc_ptr + (size_t)(t_end - t_begin) + 1);
+    CUMF_REQUIRE(src.x_ptr.front() == 0 && src.t_ptr.front() == 0, "shard pointers must be rebased to 0");
+    src.csr_col = d_csr_col; src.csr_val = d_csr_val; src.csc_row = d_csc_row; src.csc_val = d_csc_val;
+    src.test_row = d_test_row; src.test_col = d_test_col; src.test_val = d_test_val; src.test_cnt = test_cnt;
+    return als_create_core(out, src, m, n, f, nnz, nnz_test, lambda, x_begin, x_end, t_begin, t_end, device, solver, path,
+                           /*wait_uploads=*/true, nullptr, nullptr);
 }
 
 // Ask the theta half-steps to leave the train-SSE by-product (costs one more block reduction per row, about 4 % of

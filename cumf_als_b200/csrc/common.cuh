@@ -70,12 +70,14 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), borrowed(o.borrowed) { o.p = nullptr; o.bytes = 0; o.borrowed = false; }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; borrowed = o.borrowed; o.p = nullptr; o.bytes = 0; o.borrowed = false; }
         return *this;
     }
     ~DevBuf() { release(); }
+    bool borrowed = false;     // points into memory the caller owns (device-resident shards): never freed or cached here
+    void borrow(void* ptr, size_t n) { release(); p = ptr; bytes = n; borrowed = true; }
     int alloc(size_t n);
     void release();
     void release_to_cache();   // opt-in (CUMF_CACHE_MB > 0): keep the allocation for the next DevBuf::alloc of a similar size

@@ -111,9 +111,7 @@ template <bool kSym, bool kDirect, int kRows> struct Cfg {
     static_assert(kGroups >= 1 && kGroups <= 4, "k-groups per stage (2-bit fields in the stage flags)");
 };
 constexpr int MAX_WG = 3;
-#ifndef CUMF_TC_IMPL_DEFAULT_F100
-#define CUMF_TC_IMPL_DEFAULT_F100 1       // f = 100 without CUMF_TC_IMPL: the kernel of this file (1) or gram_tc2.cuh (2)
-#endif
+
 constexpr int SUB_STEPS = 16;             // k-steps (x16 ratings) accumulated in TMEM before the tile is drained
 // "direct" staging (kDirect): the opposing factor is pre-split once per half-step into an fp16 table
 //   row j = [ hi_j (100) | 0 (12) | r slots (2) | 0 (14) | lo'_j (100) | 0 (28) ]      256 halfs = 512 B
@@ -1091,10 +1089,13 @@ bool tc_path_supports(int f) {
 
 // which fused kernel serves rank f: gram_tc2.cuh (generic f, one accumulator) unless CUMF_TC_IMPL=1 asks for the round-1
 // f = 100 kernel of this file
-static int tc_impl_for(int f) {
+// f = 100 without CUMF_TC_IMPL: measured per side on the Netflix shape (profiles/README.md, round 2) -- long rows (the "sym"
+// variant, X side) are 10 % faster on this file's kernel (one N = 240 MMA per k-group instead of two N = 112 ones keeps the
+// single issuing warp ahead of the L2-bound gather), short rows (theta side) 3 % faster on the generic kernel.
+static int tc_impl_for(int f, bool long_rows) {
     const char* e = getenv("CUMF_TC_IMPL");
     if (f == F && e && *e == '1') return 1;
-    if (f == F && !(e && *e)) return CUMF_TC_IMPL_DEFAULT_F100;
+    if (f == F && !(e && *e)) return long_rows ? 1 : 2;
     return 2;
 }
 
@@ -1103,7 +1104,6 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
         set_last_error("the fused tcgen05 kernels handle f = 10, 20, ..., 200");
         return CUMF_EUNSUPPORTED;
     }
-    const int impl = tc_impl_for(f);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1121,8 +1121,9 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     {
         const char* m = getenv("CUMF_TC_SYM");
         sym = (m && *m) ? (*m == '1') : (n > 0 && total_ratings >= 1024LL * n);
-        if (impl == 2 && f > F) sym = false;          // the generic kernel's symmetric variant exists for f <= 100
     }
+    const int impl = tc_impl_for(f, sym);
+    if (impl == 2 && f > F) sym = false;              // the generic kernel's symmetric variant exists for f <= 100
     Tc2Info info2{};
     if (impl == 2 && !tc2_plan_info(f, sym, &info2)) {
         set_last_error("no generic-f kernel variant for f = " + std::to_string(f));

@@ -132,6 +132,10 @@ int cumf_rmse(const float* d_val, const int* d_row, const int* d_col, const floa
 typedef struct cumf_plan cumf_plan;
 int cumf_plan_create(cumf_plan** out, const int* h_rowptr, int rows, int row_begin, int row_end,
                      int f, int path);
+/* int64 row pointers: a matrix with more than 2^31 ratings (hugewiki.cu:27-42: 3.1 G; the reference squeezes them
+ * through `unsigned int`, hugewiki.cu:2266).  Only the ratings of ONE plan (one shard) must number < 2^31.   */
+int cumf_plan_create64(cumf_plan** out, const long long* h_rowptr, int rows, int row_begin, int row_end,
+                       int f, int path);
 int cumf_plan_destroy(cumf_plan* plan);
 /* number of kernels launched by the last cumf_update_factor on this plan */
 int cumf_plan_last_launches(const cumf_plan* plan);
@@ -187,6 +191,25 @@ int cumf_als_create(cumf_als_solver** out, const int* csrRowIndexHostPtr, const 
                     const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
                     long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
                     int device, int solver, int path);
+/* the same with int64 csrRowIndex / cscColIndex (whole-matrix host arrays beyond 2^31 ratings)                  */
+int cumf_als_create64(cumf_als_solver** out, const long long* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
+                      const float* csrValHostPtr, const int* cscRowIndexHostPtr,
+                      const long long* cscColIndexHostPtr, const float* cscValHostPtr,
+                      const int* cooRowIndexHostPtr, const int* cooRowIndexTestHostPtr,
+                      const int* cooColIndexTestHostPtr, const float* cooValHostTestPtr, int m, int n, int f,
+                      long nnz, long nnz_test, float lambda, int x_begin, int x_end, int t_begin, int t_end,
+                      int device, int solver, int path);
+/* A shard whose rating slices are ALREADY on the device -- generated there (cumf_synth_*) or loaded there shard by
+ * shard, the B200 form of hugewiki's per-GPU batch files (hugewiki.cu:2332-2340, 2508-2516): no host copy of the
+ * whole matrix.  h_csr_ptr / h_csc_ptr: this shard's own row / column pointers, rebased to 0 (host, int64,
+ * x_end - x_begin + 1 and t_end - t_begin + 1 entries); d_*: device arrays of the slices, borrowed (they must
+ * outlive the solver); the train samples are the CSR entries; d_test_* (optional): this shard's test samples.    */
+int cumf_als_create_device(cumf_als_solver** out, const long long* h_csr_ptr, const int* d_csr_col,
+                           const float* d_csr_val, const long long* h_csc_ptr, const int* d_csc_row,
+                           const float* d_csc_val, const int* d_test_row, const int* d_test_col,
+                           const float* d_test_val, long test_cnt, int m, int n, int f, long nnz, long nnz_test,
+                           float lambda, int x_begin, int x_end, int t_begin, int t_end, int device, int solver,
+                           int path);
 int cumf_als_destroy(cumf_als_solver* s);
 /* By default cumf_als_destroy (and so cumf_doALS) cudaFree's every device buffer, like the reference
  * (als.cu:1026-1033).  With CUMF_CACHE_MB=<n> (opt-in) up to n MiB of them are kept for the next
