@@ -8,6 +8,7 @@ library, or calling them without a B200, raises.
 """
 from .api import (  # noqa: F401
     AlsGroup,
+    SynthShard,
     AlsSolver,
     CumfError,
     PATH_AUTO,
@@ -27,6 +28,6 @@ from .api import (  # noqa: F401
 )
 
 __all__ = [
-    "AlsGroup", "AlsSolver", "CumfError", "Plan", "PATH_AUTO", "PATH_SIMT", "PATH_TC", "SOLVER_CG", "SOLVER_LU",
+    "AlsGroup", "SynthShard", "AlsSolver", "CumfError", "Plan", "PATH_AUTO", "PATH_SIMT", "PATH_TC", "SOLVER_CG", "SOLVER_LU",
     "cg", "do_als", "gram", "library_path", "load_library", "lu", "rmse", "update_factor",
 ]

@@ -97,6 +97,20 @@ SIGNATURES = {
     "cumf_group_iterate": (C.c_int, [_vp, C.c_int, _f32p]),
     "cumf_group_collect_train_sse": (C.c_int, [_vp, C.c_int]),
     "cumf_group_sse": (C.c_int, [_vp, _f64p, _f64p]),
+    "cumf_als_shape": (C.c_int, [_vp, _i32p, _i32p, _i32p]),
+    "cumf_synth_create": (C.c_int, [C.POINTER(_vp), C.c_longlong, C.c_int, C.c_float, C.c_ulonglong, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_long, C.c_int]),
+    "cumf_synth_destroy": (C.c_int, [_vp]),
+    "cumf_synth_slice": (C.c_longlong, [_vp, C.c_int, _vp]),
+    "cumf_synth_total_nnz": (C.c_longlong, [_vp]),
+    "cumf_synth_download": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "cumf_synth_download_test": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "cumf_synth_solver": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_float, C.c_long, C.c_int, C.c_int]),
+    "cumf_als_init_factors_device": (C.c_int, [_vp, C.c_ulonglong, C.c_float]),
+    "cumf_group_create_synth": (C.c_int, [C.POINTER(_vp), C.c_longlong, C.c_int, C.c_float, C.c_ulonglong, C.c_long, C.c_int,
+                                          C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cumf_group_nnz": (C.c_long, [_vp]),
+    "cumf_group_nnz_test": (C.c_long, [_vp]),
 }
 # C++-linkage symbols the reference's main.cpp / als_tf.cc bind (als.h:676-681, host_utilities.h:31-40)
 MANGLED_SYMBOLS = [
@@ -392,6 +406,45 @@ class AlsSolver:
             pass
 
 
+class SynthShard:
+    """cumf_synth_shard: CSR rows [x0,x1) and CSC columns [t0,t1) of the synthetic matrix (m, n, avg_deg, seed) on one device."""
+
+    def __init__(self, m: int, n: int, avg_deg: float, seed: int, x_range, t_range, test_cnt: int = 0, device: int = 0):
+        self._h = _vp()
+        self.m, self.n, self.x_range, self.t_range, self.test_cnt = m, n, tuple(x_range), tuple(t_range), test_cnt
+        _check(load_library().cumf_synth_create(C.byref(self._h), m, n, avg_deg, seed, x_range[0], x_range[1], t_range[0], t_range[1],
+                                                test_cnt, device), "cumf_synth_create")
+
+    @property
+    def total_nnz(self) -> int:
+        return int(load_library().cumf_synth_total_nnz(self._h))
+
+    def slice(self, what: int):
+        """(ptr int64 rebased, idx int32, val float32) of the CSR (0) / CSC (1) slice, on the host."""
+        rows = (self.x_range[1] - self.x_range[0]) if what == 0 else (self.t_range[1] - self.t_range[0])
+        ptr = np.empty(rows + 1, np.int64)
+        cnt = int(load_library().cumf_synth_slice(self._h, what, _hp(ptr)))
+        idx, val = np.empty(cnt, np.int32), np.empty(cnt, np.float32)
+        _check(load_library().cumf_synth_download(self._h, what, _hp(idx), _hp(val)), "cumf_synth_download")
+        return ptr, idx, val
+
+    def test_samples(self):
+        r, c_, v = np.empty(self.test_cnt, np.int32), np.empty(self.test_cnt, np.int32), np.empty(self.test_cnt, np.float32)
+        _check(load_library().cumf_synth_download_test(self._h, _hp(r), _hp(c_), _hp(v)), "cumf_synth_download_test")
+        return r, c_, v
+
+    def close(self) -> None:
+        if self._h:
+            load_library().cumf_synth_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class AlsGroup:
     """cumf_als_group: n row shards on n devices of this node, driven from one process (what cumf_doALS does under
     CUMF_GPUS=n).  Same host arrays as AlsSolver; factors are full replicas on every device."""
@@ -414,6 +467,19 @@ class AlsGroup:
         self._h = _vp()
         _check(lib.cumf_group_create(C.byref(self._h), *[_hp(a) for a in arrs], m, n, f, self.nnz, self.nnz_test, lam,
                                      first_device, n_devices, solver, path), "cumf_group_create")
+
+    @classmethod
+    def from_synth(cls, m: int, n: int, avg_deg: float, seed: int, test_per_shard: int, f: int, lam: float, n_devices: int,
+                   first_device: int = 0, solver: int = SOLVER_CG, path: int = PATH_AUTO) -> "AlsGroup":
+        """cumf_group_create_synth: the matrix is generated shard by shard on the devices (Hugewiki-scale configuration)."""
+        self = cls.__new__(cls)
+        self._h = _vp()
+        self.m, self.n, self.f, self.lam = m, n, f, lam
+        _check(load_library().cumf_group_create_synth(C.byref(self._h), m, n, avg_deg, seed, test_per_shard, f, lam, first_device,
+                                                      n_devices, solver, path), "cumf_group_create_synth")
+        self.nnz = int(load_library().cumf_group_nnz(self._h))
+        self.nnz_test = int(load_library().cumf_group_nnz_test(self._h))
+        return self
 
     def set_factors(self, thetaT, XT) -> None:
         t, x = _host(thetaT, np.float32), _host(XT, np.float32)

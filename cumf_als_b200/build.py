@@ -32,7 +32,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CXXFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
             "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets"]
 LIB_SOURCES = ["als_api.cu", "gram_simt.cu", "gram_tc.cu", "gram_tc2.cu", "gram_tc2_a.cu", "gram_tc2_b.cu", "gram_tc2_c.cu", "cg.cu",
-               "rmse.cu", "host_io.cpp"]
+               "rmse.cu", "synth.cu", "host_io.cpp"]
 
 
 def _run(cmd: list[str]) -> None:

@@ -1096,6 +1096,13 @@ extern "C" int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float
     if (XTHost) CUMF_CUDA_TRY(cudaMemcpy(XTHost, s->x.p, sizeof(float) * (size_t)s->m * s->f, cudaMemcpyDeviceToHost));
     return CUMF_OK;
 }
+extern "C" int cumf_als_shape(const cumf_als_solver* s, int* m, int* n, int* f) {
+    CUMF_REQUIRE(s, "null pointer");
+    if (m) *m = s->m;
+    if (n) *n = s->n;
+    if (f) *f = s->f;
+    return CUMF_OK;
+}
 extern "C" float* cumf_als_theta_ptr(cumf_als_solver* s) { return s ? s->theta.as<float>() : nullptr; }
 extern "C" float* cumf_als_x_ptr(cumf_als_solver* s) { return s ? s->x.as<float>() : nullptr; }
 
@@ -1375,8 +1382,17 @@ extern "C" int cumf_als_ipc_import(cumf_als_solver* s, const void* blobs, int nr
 }
 
 // ---- one process, n devices -------------------------------------------------------------------------------------------
+struct cumf_synth_shard;
+extern "C" int cumf_synth_create(cumf_synth_shard** out, long long m, int n, float avg_deg, unsigned long long seed, int x0, int x1,
+                                 int t0, int t1, long test_cnt, int device);
+extern "C" int cumf_synth_destroy(cumf_synth_shard* sh);
+extern "C" int cumf_synth_solver(cumf_synth_shard* sh, cumf_als_solver** out, int f, float lambda, long nnz_test_total, int solver, int path);
+extern "C" long long cumf_synth_total_nnz(const cumf_synth_shard* sh);
+extern "C" int cumf_als_init_factors_device(cumf_als_solver* s, unsigned long long seed, float scale);
+
 struct cumf_als_group {
     std::vector<cumf_als_solver*> s;
+    std::vector<cumf_synth_shard*> synth;     // device-resident shards the solvers borrow (cumf_group_create_synth)
     int m = 0, n = 0, f = 0;
     long nnz = 0, nnz_test = 0;
     std::vector<std::string> errors;        // per shard (g_last_error is thread-local)
@@ -1410,10 +1426,88 @@ extern "C" int cumf_group_destroy(cumf_als_group* g) {
     if (!g) return CUMF_OK;
     // every device must be idle before any replica goes away: the peers' epilogues write into it
     for (auto* s : g->s) if (s) { cudaSetDevice(s->device); cudaDeviceSynchronize(); }
-    for_each_shard_parallel((int)g->s.size(), [&](int k) { if (g->s[k]) cumf_als_destroy(g->s[k]); });
+    for_each_shard_parallel((int)g->s.size(), [&](int k) {
+        if (g->s[k]) cumf_als_destroy(g->s[k]);
+        if (k < (int)g->synth.size() && g->synth[k]) cumf_synth_destroy(g->synth[k]);
+    });
     delete g;
     return CUMF_OK;
 }
+
+// rank / peer tables of a fully created group (same process: plain device pointers, peer access enabled by the caller)
+static void group_connect(cumf_als_group* g) {
+    const int n = (int)g->s.size();
+    for (int k = 0; k < n; ++k) {
+        cumf_als_solver* s = g->s[k];
+        s->rank = k;
+        s->nranks = n;
+        s->peer_x.n = s->peer_theta.n = 0;
+        for (int j = 0; j < n; ++j) {
+            s->peer_flags[j] = g->s[j]->flags.as<unsigned long long>();
+            if (j == k) continue;
+            s->peer_x.p[s->peer_x.n++] = g->s[j]->x.as<float>();
+            s->peer_theta.p[s->peer_theta.n++] = g->s[j]->theta.as<float>();
+        }
+    }
+}
+static int shard_runtime_setup(cumf_als_solver* s, int first_device, int n_devices, bool same_device) {
+    CUMF_TRY(solver_alloc_flags(s));
+    if (cudaStreamCreateWithFlags(&s->run_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_last_error("cumf_group_create: cannot create a stream");
+        return CUMF_ECUDA;
+    }
+    if (!same_device)
+        for (int j = 0; j < n_devices; ++j) {
+            if (first_device + j == s->device) continue;
+            const cudaError_t e = cudaDeviceEnablePeerAccess(first_device + j, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { set_last_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return CUMF_ECUDA; }
+        }
+    return CUMF_OK;
+}
+
+// A group over a synthetic matrix generated shard by shard ON the devices (synth.cu): the Hugewiki-scale configuration of
+// BASELINE.json (m ~ 50 M, n ~ 40 K, 3.1 G ratings over 8 GPUs) never exists as one host copy.  Rows and columns are split
+// evenly (the generator's degrees are i.i.d., so equal row counts are rating-balanced); theta0 = 0.2 * uniform, X0 = 0.
+extern "C" int cumf_group_create_synth(cumf_als_group** out, long long m, int n, float avg_deg, unsigned long long seed,
+                                       long test_per_shard, int f, float lambda, int first_device, int n_devices, int solver,
+                                       int path) {
+    CUMF_REQUIRE(out && m > 0 && m < (1ll << 31) && n > 0, "bad matrix spec");
+    CUMF_REQUIRE(n_devices >= 1 && n_devices <= 8, "1 .. 8 devices");
+    int have = 0;
+    CUMF_CUDA_TRY(cudaGetDeviceCount(&have));
+    const bool same_device = env_long("CUMF_GROUP_SAME_DEVICE", 0) != 0;
+    CUMF_REQUIRE(first_device >= 0 && first_device + (same_device ? 1 : n_devices) <= have, "not that many devices on this node");
+    cumf_als_group* g = new cumf_als_group();
+    g->m = (int)m; g->n = n; g->f = f; g->nnz_test = test_per_shard * n_devices;
+    g->s.assign(n_devices, nullptr);
+    g->synth.assign(n_devices, nullptr);
+    g->errors.assign(n_devices, std::string());
+    std::vector<int> rcs(n_devices, CUMF_OK);
+    for_each_shard_parallel(n_devices, [&](int k) {
+        const int dev = same_device ? first_device : first_device + k;
+        const int x0 = (int)(m * k / n_devices), x1 = (int)(m * (k + 1) / n_devices);
+        const int t0 = (int)((long long)n * k / n_devices), t1 = (int)((long long)n * (k + 1) / n_devices);
+        rcs[k] = cumf_synth_create(&g->synth[k], m, n, avg_deg, seed, x0, x1, t0, t1, test_per_shard, dev);
+        if (rcs[k] == CUMF_OK) rcs[k] = cumf_synth_solver(g->synth[k], &g->s[k], f, lambda, (long)g->nnz_test, solver, path);
+        if (rcs[k] == CUMF_OK) rcs[k] = shard_runtime_setup(g->s[k], first_device, n_devices, same_device);
+        if (rcs[k] == CUMF_OK) rcs[k] = cumf_als_init_factors_device(g->s[k], seed ^ 0xFAC70125ull, 0.2f);
+        if (rcs[k] != CUMF_OK) g->errors[k] = cumf_last_error();
+    });
+    for (int k = 0; k < n_devices; ++k)
+        if (rcs[k] != CUMF_OK) {
+            set_last_error("shard " + std::to_string(k) + ": " + g->errors[k]);
+            const int rc = rcs[k];
+            cumf_group_destroy(g);
+            return rc;
+        }
+    g->nnz = (long)cumf_synth_total_nnz(g->synth[0]);
+    group_connect(g);
+    *out = g;
+    return CUMF_OK;
+}
+extern "C" long cumf_group_nnz(const cumf_als_group* g) { return g ? g->nnz : -1; }
+extern "C" long cumf_group_nnz_test(const cumf_als_group* g) { return g ? g->nnz_test : -1; }
 
 static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr,
                              const float* csrValHostPtr, const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr,
@@ -1444,19 +1538,7 @@ static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr
                                  cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, xr[k].first,
                                  xr[k].second, tr[k].first, tr[k].second, device_of(k), solver, path, wait_uploads,
                                  thetaTHost, XTHost);
-        if (rcs[k] == CUMF_OK) rcs[k] = solver_alloc_flags(g->s[k]);
-        if (rcs[k] == CUMF_OK && cudaStreamCreateWithFlags(&g->s[k]->run_stream, cudaStreamNonBlocking) != cudaSuccess) {
-            set_last_error("cumf_group_create: cannot create a stream");
-            rcs[k] = CUMF_ECUDA;
-        }
-        if (rcs[k] == CUMF_OK && !same_device) {
-            for (int j = 0; j < n_devices; ++j) {
-                if (j == k) continue;
-                const cudaError_t e = cudaDeviceEnablePeerAccess(first_device + j, 0);
-                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-                else if (e != cudaSuccess) { set_last_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); rcs[k] = CUMF_ECUDA; }
-            }
-        }
+        if (rcs[k] == CUMF_OK) rcs[k] = shard_runtime_setup(g->s[k], first_device, n_devices, same_device);
         if (rcs[k] != CUMF_OK) g->errors[k] = cumf_last_error();
     });
     for (int k = 0; k < n_devices; ++k)
@@ -1466,17 +1548,7 @@ static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr
             cumf_group_destroy(g);
             return rc;
         }
-    for (int k = 0; k < n_devices; ++k) {
-        cumf_als_solver* s = g->s[k];
-        s->rank = k;
-        s->nranks = n_devices;
-        for (int j = 0; j < n_devices; ++j) {
-            s->peer_flags[j] = g->s[j]->flags.as<unsigned long long>();
-            if (j == k) continue;
-            s->peer_x.p[s->peer_x.n++] = g->s[j]->x.as<float>();
-            s->peer_theta.p[s->peer_theta.n++] = g->s[j]->theta.as<float>();
-        }
-    }
+    group_connect(g);
     *out = g;
     return CUMF_OK;
 }

@@ -1007,6 +1007,7 @@ struct TcWork {
     int impl = 1, f = F;
     Tc2Info info2{};
     DevBuf absmax, scales;              // per-launch scale state of the generic-f kernel
+    const float* scaled_val = nullptr;  // rating array whose largest |r| the plan already holds (CUMF_TC_RESCAN_RATINGS=1: never)
     int* h_max_idx = nullptr;           // pinned
     cudaEvent_t max_idx_ready = nullptr;
     bool max_idx_pending = false;
@@ -1077,7 +1078,7 @@ int tc_plan_impl(const TcWork* w) { return w ? w->impl : 0; }
 // the first direct-staging launch
 // (also invalidates the cached scan: the next launch validates the index buffer it is given against `rows`)
 void tc_plan_set_factor_rows(TcWork* w, int rows) {
-    if (w && rows > 0) { w->hint_rows = rows; w->scanned_colidx = nullptr; }
+    if (w && rows > 0) { w->hint_rows = rows; w->scanned_colidx = nullptr; w->scaled_val = nullptr; }
 }
 int tc_sse_terms_per_cta() { return MAX_WG; }
 
@@ -1320,6 +1321,11 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
             a.d_chunks = d_chunks; a.d_chunk_meta = w->chunk_meta.as<int>(); a.d_cta_ptr = w->cta_ptr.as<int>();
             a.d_stage_tab = w->stage_tab.p; a.d_cta_stage_ptr = w->cta_stage_ptr.as<int>();
             a.d_colidx = d_colidx; a.d_val = d_val; a.val_span = w->idx_span;
+            {
+                const char* rs = getenv("CUMF_TC_RESCAN_RATINGS");
+                a.scan_ratings = (w->scaled_val != d_val) || (rs && *rs == '1');
+                w->scaled_val = d_val;
+            }
             a.d_factor = d_factor; a.factor_rows = w->factor_rows;
             a.d_table = w->split_tab.p; a.tensor_map = &w->split_map;
             a.d_absmax = w->absmax.as<unsigned>(); a.d_scales = w->scales.as<float>();

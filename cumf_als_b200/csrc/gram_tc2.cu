@@ -134,17 +134,20 @@ int tc2_update(const Tc2Launch& a, cudaStream_t st, int* launches) {
         return CUMF_EUNSUPPORTED;
     }
     // scale of the half-step: largest finite |v| of the opposing factor and of the ratings (asynchronous, no host round trip)
-    CUMF_CUDA_TRY(cudaMemsetAsync(a.d_absmax, 0, 2 * sizeof(unsigned), st));
+    CUMF_CUDA_TRY(cudaMemsetAsync(a.d_absmax, 0, (a.scan_ratings ? 2 : 1) * sizeof(unsigned), st));
     const size_t nfac = (size_t)a.factor_rows * a.f;
     tc2::absmax_kernel<<<(unsigned)std::min<size_t>((nfac + 255) / 256, 1184), 256, 0, st>>>(a.d_factor, nfac, a.d_absmax);
-    tc2::absmax_kernel<<<(unsigned)std::min<size_t>(((size_t)a.val_span + 255) / 256, 1184), 256, 0, st>>>(a.d_val, (size_t)a.val_span,
-                                                                                                           a.d_absmax + 1);
+    if (a.scan_ratings) {       // the ratings are data, not state: their scale is kept per plan and rating array
+        tc2::absmax_kernel<<<(unsigned)std::min<size_t>(((size_t)a.val_span + 255) / 256, 1184), 256, 0, st>>>(a.d_val, (size_t)a.val_span,
+                                                                                                               a.d_absmax + 1);
+        *launches += 1;
+    }
     const size_t pieces = (size_t)(a.factor_rows + 1) * (v.tab_cols / 8);
     tc2::split_factor2_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a.d_factor, a.factor_rows, a.f, (a.f + 1 + 15) / 16 * 16,
                                                                                v.tab_cols, a.sym ? 1 : 0, a.d_absmax,
                                                                                reinterpret_cast<uint4*>(a.d_table), a.d_scales);
     CUMF_CUDA_TRY(cudaGetLastError());
-    *launches += 3;
+    *launches += 2;
     tc2::Params p;
     p.chunks = a.d_chunks; p.chunk_meta = a.d_chunk_meta; p.cta_chunk_ptr = a.d_cta_ptr;
     p.stage_tab = reinterpret_cast<const tc2::StageDesc*>(a.d_stage_tab); p.cta_stage_ptr = a.d_cta_stage_ptr;

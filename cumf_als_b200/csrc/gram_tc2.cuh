@@ -84,7 +84,11 @@ template <int F_> struct Geo {
     static constexpr int RB = (F + 1 > 128) ? 2 : 1;               // 128-lane row blocks of the accumulator
     static constexpr int TILE_COLS = RB * NB;
     static constexpr int NBUF = (TMEM_COLS / TILE_COLS >= 4) ? 4 : (TMEM_COLS / TILE_COLS >= 2 ? 2 : 1);
+#ifdef CUMF_TC2_KROWS32
+    static constexpr int KROWS = 32;                               // experiment: 32-rating stages everywhere (twice the slots)
+#else
     static constexpr int KROWS = (RB == 2) ? 32 : 64;              // ratings per stage
+#endif
     static constexpr int KGROUPS = KROWS / KT;
     static constexpr int SUB = 256 / KROWS;                        // stages per TMEM tile: chains are cut every 256 ratings
     static constexpr int KG_BYTES = KT * ROW_BYTES;
@@ -104,7 +108,11 @@ template <int F, int MODE> struct Cfg {
     static constexpr int kSys = kWG / kSysWG;                                     // systems in flight
     static constexpr int kFirstWorker = kSym ? 4 : 0;
     static constexpr int kWorkers = kSym ? 5 : 3;
+#ifdef CUMF_TC2_KROWS32
+    static constexpr int kSlotsPerWorker = kSym ? 2 : (G::RB == 2 ? 2 : 4);
+#else
     static constexpr int kSlotsPerWorker = kSym ? 1 : 2;
+#endif
     static constexpr int kSlots = kWorkers * kSlotsPerWorker;
     static constexpr int kFirstEpiWarp = kSym ? 12 : 4;
     static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;               // 640 / 512 / 384

@@ -224,6 +224,7 @@ int cumf_release_cached_memory(void);
 int cumf_als_collect_train_sse(cumf_als_solver* s, int on);
 int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost, const float* XTHost);
 int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float* XTHost);
+int cumf_als_shape(const cumf_als_solver* s, int* m, int* n, int* f);
 /* device pointers of the resident full factor replicas (for NCCL all-gather by the caller) */
 float* cumf_als_theta_ptr(cumf_als_solver* s);
 float* cumf_als_x_ptr(cumf_als_solver* s);
@@ -279,6 +280,31 @@ int cumf_group_get_factors(cumf_als_group* g, float* thetaTHost, float* XTHost);
 int cumf_group_iterate(cumf_als_group* g, int iters, float* ms_out);   /* ms_out: slowest shard */
 int cumf_group_collect_train_sse(cumf_als_group* g, int on);
 int cumf_group_sse(cumf_als_group* g, double* train_sse, double* test_sse);   /* summed over shards */
+
+
+/* ---- synthetic matrices generated shard by shard ON the device (bench / test tooling) ----------
+ * BASELINE.json's Hugewiki-scale configuration (m ~ 50 M, n ~ 40 K, 3.1 G ratings over 8 GPUs, hugewiki.cu:27-42)
+ * never exists as one host copy: every GPU derives its CSR slice (rows [x0,x1)) and CSC slice (columns [t0,t1)) of
+ * one global matrix -- a pure function of (seed, row, column) -- in device memory, without communication
+ * (cumf_als_b200/csrc/synth.cu).  cumf_synth_solver builds the shard's solver on those slices where they lie
+ * (cumf_als_create_device); cumf_group_create_synth does it for n devices and connects them (row sharding, above).   */
+typedef struct cumf_synth_shard cumf_synth_shard;
+int cumf_synth_create(cumf_synth_shard** out, long long m, int n, float avg_deg, unsigned long long seed,
+                      int x0, int x1, int t0, int t1, long test_cnt, int device);
+int cumf_synth_destroy(cumf_synth_shard* sh);
+long long cumf_synth_slice(const cumf_synth_shard* sh, int what /* 0 CSR, 1 CSC */, long long* ptr_out);
+long long cumf_synth_total_nnz(const cumf_synth_shard* sh);
+int cumf_synth_download(const cumf_synth_shard* sh, int what, int* idx_out, float* val_out);
+int cumf_synth_download_test(const cumf_synth_shard* sh, int* row_out, int* col_out, float* val_out);
+int cumf_synth_solver(cumf_synth_shard* sh, cumf_als_solver** out, int f, float lambda, long nnz_test_total,
+                      int solver, int path);
+/* theta <- scale * uniform[0,1) (same values on every replica), X <- 0, on the device (main.cpp:72-78's shape) */
+int cumf_als_init_factors_device(cumf_als_solver* s, unsigned long long seed, float scale);
+int cumf_group_create_synth(cumf_als_group** out, long long m, int n, float avg_deg, unsigned long long seed,
+                            long test_per_shard, int f, float lambda, int first_device, int n_devices,
+                            int solver, int path);
+long cumf_group_nnz(const cumf_als_group* g);
+long cumf_group_nnz_test(const cumf_als_group* g);
 
 #ifdef __cplusplus
 }
