@@ -431,8 +431,11 @@ def run_ours_partial_gram(args, w):
     f, lam = w["f"], w["lam"]
     path = {"auto": c.PATH_AUTO, "simt": c.PATH_SIMT, "tc": c.PATH_TC}[args.path]
     t_ranges = nnz_balanced_ranges(r.csc_indptr, world)
-    eng = GpuPartialGramEngine(r, f, lam, theta0, X0, t_ranges[rank], local_rank, path=path)
+    if args.free_sms > 0:      # leave SMs to the collective's kernels: the persistent Gram kernel otherwise owns every SM
+        os.environ["CUMF_TC_CTAS"] = str(max(1, torch.cuda.get_device_properties(local_rank).multi_processor_count - args.free_sms))
+    eng = GpuPartialGramEngine(r, f, lam, theta0, X0, t_ranges[rank], local_rank, path=path, cap_bytes=args.e2_batch_mb << 20)
     drv = PartialGramAls(eng, r.nnz, r.nnz_test)
+    drv.overlap = args.e2_overlap
 
     def barrier():
         if world > 1:
@@ -485,7 +488,9 @@ def run_ours_partial_gram(args, w):
             "config": common_config(args, r, w),
             "impl_detail": {"path": "tcgen05" if fused else "simt",
                             "sharding": f"theta rows nnz-balanced over {world} ranks; X-step = partial [A|b] + NCCL all-reduce "
-                                        f"+ replicated CG; theta-step rank-local (no factor exchange)"},
+                                        f"+ replicated CG; theta-step rank-local (no factor exchange)",
+                            "x_batches": len(eng.batches), "overlap": bool(args.e2_overlap and len(eng.batches) > 1),
+                            "free_sms_for_the_collective": args.free_sms},
             "phases_ms": phases, "allreduce_bytes_per_iteration": drv.allreduce_bytes // max(args.steps, 1),
             "train_rmse": train_rmse, "test_rmse": test_rmse, "gpu_launches": int(eng.launches),
             "clocks": clocks.summary(),
@@ -592,6 +597,9 @@ def main():
     ap.add_argument("--sharding", default="rows", choices=["rows", "partial-gram"],
                     help="N>1: 'rows' = each rank updates its rows from full factors and broadcasts them (E1); "
                          "'partial-gram' = theta sharded, partial [A|b] all-reduced (E2, hugewiki.cu:2629-2827)")
+    ap.add_argument("--e2-overlap", action="store_true", help="partial-gram: all-reduce of batch k under the Gram of batch k+1")
+    ap.add_argument("--e2-batch-mb", type=int, default=8192, help="partial-gram: workspace per X-row batch (MiB)")
+    ap.add_argument("--free-sms", type=int, default=0, help="partial-gram: SMs the Gram kernel leaves to the collective")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -178,6 +178,7 @@ struct Tc2Launch {
     const void* d_stage_tab = nullptr; const int* d_cta_stage_ptr = nullptr;
     const int* d_colidx = nullptr; const float* d_val = nullptr; long long val_span = 0;
     bool scan_ratings = true;                                       // (re)compute the rating scale from d_val[0, val_span)
+    bool hi_only = false;                                           // CUMF_TT_FP16=1: fp16 Gram operands without the lo halves
     const float* d_factor = nullptr; int factor_rows = 0;
     void* d_table = nullptr; const void* tensor_map = nullptr;      // fp16 split table [factor_rows + 1][tab_cols] and its CUtensorMap
     unsigned* d_absmax = nullptr; float* d_scales = nullptr;        // 2 words / 4 floats of per-launch scale state

@@ -1095,6 +1095,8 @@ bool tc_path_supports(int f) {
 // single issuing warp ahead of the L2-bound gather), short rows (theta side) 3 % faster on the generic kernel.
 static int tc_impl_for(int f, bool long_rows) {
     const char* e = getenv("CUMF_TC_IMPL");
+    const char* h = getenv("CUMF_TT_FP16");
+    if (h && *h == '1') return 2;                  // the reduced-precision mode lives in the generic kernel
     if (f == F && e && *e == '1') return 1;
     if (f == F && !(e && *e)) return long_rows ? 1 : 2;
     return 2;
@@ -1329,6 +1331,12 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
             a.d_factor = d_factor; a.factor_rows = w->factor_rows;
             a.d_table = w->split_tab.p; a.tensor_map = &w->split_map;
             a.d_absmax = w->absmax.as<unsigned>(); a.d_scales = w->scales.as<float>();
+            {   // the reference's CUMF_TT_FP16 / CUMF_XX_FP16 build flags (als.cu:30-31, 335-441: fp16 storage of the gathered
+                // factor) as a run-time switch: only the 11-bit hi halves are gathered and multiplied (half the bytes, a third
+                // of the MMAs; A is then accurate to ~5e-4 relative -- its own tolerance, tests/test_gpu_generic_f.py)
+                const char* h = getenv("CUMF_TT_FP16");
+                a.hi_only = h && *h == '1';
+            }
             a.d_out = d_out; a.lambda = lambda; a.cg_iter = cg_iter;
             a.d_scratchA = d_scratchA; a.d_scratchB = d_scratchB; a.d_sse_terms = d_sse_terms;
             if (extra) {

@@ -161,6 +161,7 @@ int tc2_update(const Tc2Launch& a, cudaStream_t st, int* launches) {
     p.scratchA = a.d_scratchA; p.scratchB = a.d_scratchB;
     p.tt = a.d_tt; p.rhs = a.d_rhs; p.tt_row_base = a.tt_row_base;
     p.scales = a.d_scales; p.sse_terms = a.d_sse_terms; p.zero_row = a.factor_rows;
+    p.hi_only = a.hi_only ? 1 : 0;
     CUMF_CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     v.fn<<<a.grid, v.threads, v.smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tensor_map), p);
     CUMF_CUDA_TRY(cudaGetLastError());

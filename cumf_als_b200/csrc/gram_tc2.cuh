@@ -173,6 +173,7 @@ struct Params {
     const float* scales;          // [0] 2^-2c (A), [1] 2^-(c+cr) (b), [2] 2^cr (ratings)
     double* sse_terms;
     int zero_row;
+    int hi_only;                  // reduced-precision mode: gather and multiply only the fp16 hi halves
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -417,8 +418,10 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                                     const uint64_t a_lo = d_g + (uint64_t)(((CR + 2 * rb) * ATOM_BYTES) >> 4);
                                     const uint32_t dt = d_tmem + (uint32_t)(rb * NB);
                                     umma_f16(dt, a_hi, b_hi, idesc, (g == 0 && st == 0u) ? 0u : 1u);    // hi^T hi
-                                    umma_f16(dt, a_hi, b_lo, idesc, 1u);                                // hi^T lo   (kSym: hi^T 2 lo)
-                                    if (!kSym) umma_f16(dt, a_lo, b_hi, idesc, 1u);                     // lo^T hi
+                                    if (!P.hi_only) {
+                                        umma_f16(dt, a_hi, b_lo, idesc, 1u);                            // hi^T lo   (kSym: hi^T 2 lo)
+                                        if (!kSym) umma_f16(dt, a_lo, b_hi, idesc, 1u);                 // lo^T hi
+                                    }
                                 }
                             }
                         }
@@ -464,7 +467,7 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 if (lane == 0) sm.meta_op[slot] = flags;
                 __syncwarp();
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&sm.full_tma[slot], groups * (uint32_t)G::KG_BYTES);
+                    mbar_arrive_expect_tx(&sm.full_tma[slot], groups * (uint32_t)(P.hi_only ? G::KG_BYTES / 2 : G::KG_BYTES));
 #pragma unroll
                     for (int g = 0; g < KGROUPS; ++g) {
                         if ((uint32_t)g < groups) {
@@ -473,7 +476,8 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                                 const int4 ix = *reinterpret_cast<const int4*>(&sm.stage_idx[slot][g * KT + q * 4]);
 #pragma unroll
                                 for (int c = 0; c < NC; ++c)
-                                    tma_gather4_col(sbase + g * G::KG_BYTES + (q >> 1) * G::SBO + c * ATOM_BYTES + (q & 1) * 512, &factor_map,
+                                    if (c < CR || !P.hi_only)
+                                        tma_gather4_col(sbase + g * G::KG_BYTES + (q >> 1) * G::SBO + c * ATOM_BYTES + (q & 1) * 512, &factor_map,
                                                     (c < CR ? c * CHUNK : NB + (c - CR) * CHUNK), ix.x, ix.y, ix.z, ix.w, &sm.full_tma[slot]);
                             }
                         }

@@ -210,6 +210,7 @@ class GpuPartialGramEngine:
         rows_max = max((b1 - b0 for b0, b1 in self.batches), default=1)
         self.tt = torch.empty((rows_max, f * f), dtype=torch.float32, device=dev)
         self.rhs = torch.empty((rows_max, f), dtype=torch.float32, device=dev)
+        self.tt2 = self.rhs2 = None         # second workspace, allocated by the overlapped driver
         # theta-step data: the owned CSC columns, rebased
         cp = np.asarray(r.csc_indptr, dtype=np.int64)
         lo, hi = int(cp[t0]), int(cp[t1])
@@ -230,17 +231,22 @@ class GpuPartialGramEngine:
         self.theta = torch.from_numpy(np.ascontiguousarray(theta0, dtype=np.float32)).to(dev)
         self.launches = 0
 
-    def partial_gram(self, batch: int):
+    def partial_gram(self, batch: int, buf: int = 0, stream=None):
+        """Partial [A|b] of the batch's rows over this rank's ratings into workspace `buf` (two workspaces when the
+        all-reduce of one batch overlaps the Gram of the next)."""
         b0, b1 = self.batches[batch]
-        tt, rhs = self.tt[: b1 - b0], self.rhs[: b1 - b0]
+        if buf == 1 and self.tt2 is None:
+            self.tt2, self.rhs2 = torch.empty_like(self.tt), torch.empty_like(self.rhs)
+        tt, rhs = (self.tt, self.rhs) if buf == 0 else (self.tt2, self.rhs2)
+        tt, rhs = tt[: b1 - b0], rhs[: b1 - b0]
         p = self.x_plans[batch]
-        p.gram(self.x_col, self.x_val, self.theta, self.lam, tt, rhs)
+        p.gram(self.x_col, self.x_val, self.theta, self.lam, tt, rhs, stream=stream)
         self.launches += p.last_launches
         return tt, rhs
 
-    def solve_x(self, batch: int, tt, rhs):
+    def solve_x(self, batch: int, tt, rhs, stream=None):
         b0, b1 = self.batches[batch]
-        self.api.cg(tt, self.x[b0:b1], rhs, b1 - b0, self.f, self.cg_iter)
+        self.api.cg(tt, self.x[b0:b1], rhs, b1 - b0, self.f, self.cg_iter, stream=stream)
         self.launches += 1
 
     def update_theta(self):
@@ -267,8 +273,12 @@ class PartialGramAls:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.allreduce_bytes = 0
+        self.overlap = False            # double-buffered batches: all-reduce(k) under Gram(k+1)
+        self._comm = None
 
     def step(self):
+        if self.overlap and self.world > 1 and len(self.e.batches) > 1 and self.e.x.is_cuda:
+            return self._step_overlapped()
         e = self.e
         for b in range(len(e.batches)):
             tt, rhs = e.partial_gram(b)
@@ -277,6 +287,42 @@ class PartialGramAls:
                 dist.all_reduce(rhs, group=self.group)
                 self.allreduce_bytes += 4 * (tt.numel() + rhs.numel())
             e.solve_x(b, tt, rhs)
+        e.update_theta()
+
+    def _step_overlapped(self):
+        """Batches double-buffered over two streams: the all-reduce of batch k (communication stream) runs while the compute
+        stream forms the partial Gram of batch k+1; the replicated CG of batch k follows on the compute stream once its sum
+        has arrived.  compute: G0 G1 S0 G2 S1 ...   comm: A0 A1 A2 ...   (hugewiki.cu:2703-2745 does reduce + broadcast
+        serially after each batch).  The Gram kernel must leave a few SMs free for the collective (CUMF_TC_CTAS)."""
+        e = self.e
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=e.x.device)
+        comp = torch.cuda.current_stream(e.x.device)
+        nb = len(e.batches)
+        done = [None] * nb          # all-reduce of batch b finished
+        bufs = [None] * nb
+
+        def gram(b):
+            bufs[b] = e.partial_gram(b, buf=b % 2)
+            ev = torch.cuda.Event()
+            ev.record(comp)
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(ev)
+                dist.all_reduce(bufs[b][0], group=self.group)
+                dist.all_reduce(bufs[b][1], group=self.group)
+                done[b] = torch.cuda.Event()
+                done[b].record(self._comm)
+            self.allreduce_bytes += 4 * (bufs[b][0].numel() + bufs[b][1].numel())
+
+        def solve(b):
+            comp.wait_event(done[b])
+            e.solve_x(b, *bufs[b])
+
+        gram(0)
+        for b in range(1, nb):
+            gram(b)             # workspace b % 2 was released by solve(b - 2), issued earlier on the compute stream
+            solve(b - 1)
+        solve(nb - 1)
         e.update_theta()
 
     iterate = ShardedAls.iterate

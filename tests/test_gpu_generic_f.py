@@ -187,3 +187,38 @@ def test_tc2_plan_gram_ranges_vs_oracle(cuda):
             assert np.abs(tt[u] - ref[u]).max() / scale < 6e-6, (f, u, lengths[u])
         assert np.allclose(rhs, ref_b, rtol=2e-5, atol=1e-4)
         plan.close()
+
+
+def test_tc2_reduced_precision_mode(cuda, monkeypatch):
+    """CUMF_TT_FP16=1, the run-time form of the reference's CUMF_TT_FP16 / CUMF_XX_FP16 storage flags (als.cu:30-31, 335-441;
+    SURVEY.md 8f f3): only the 11-bit hi halves of the factor are gathered and multiplied.  Own tolerance: the Gram is
+    accurate to 2^-11 per operand (measured ~3e-4 relative here), the per-iteration RMSE to 1e-3; off by default."""
+    rng = np.random.default_rng(8)
+    n, f, lam = 5000, 100, 0.05
+    rowptr, colidx, val = random_csr(rng, LENGTHS, n)
+    factor = (0.3 * rng.standard_normal((n, f))).astype(np.float32)
+    ref = O.gram(rowptr, colidx, factor, f, lam)
+    exact, _ = run_gram(cuda, rowptr, colidx, val, factor, f, lam, path=c.PATH_TC)
+    monkeypatch.setenv("CUMF_TT_FP16", "1")
+    lossy, rhs = run_gram(cuda, rowptr, colidx, val, factor, f, lam, path=c.PATH_TC)
+    e_exact, e_lossy = rel_fro(exact, ref), rel_fro(lossy, ref)
+    print(f"Gram rel error: split-fp16 {e_exact:.2e}, hi only {e_lossy:.2e}")
+    assert e_exact < 4e-6 and 2e-5 < e_lossy < 2e-3             # the switch is live, and as lossy as 11 bits say
+    assert rel_fro(rhs, O.rhs(rowptr, colidx, val, factor, f)) < 2e-3
+    r = synth_ratings(700, 4000, 160000, 8000, seed=31)
+    theta0, X0 = init_factors(r.m, r.n, f, seed=3)
+    hist = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CUMF_TT_FP16", mode)
+        s = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
+                        r.test_row, r.test_col, r.test_val, r.m, r.n, f, 0.048, path=c.PATH_TC)
+        s.set_factors(theta0, X0)
+        h = []
+        for _ in range(3):
+            s.iterate(1)
+            h.append(s.rmse())
+        hist[mode] = np.array(h)
+        s.close()
+    d = np.abs(hist["1"] - hist["0"]).max() / hist["0"].min()
+    print(f"per-iteration RMSE, hi only vs split-fp16: max rel diff {d:.2e}")
+    assert d < 3e-3
