@@ -1434,6 +1434,15 @@ extern "C" int cumf_group_destroy(cumf_als_group* g) {
     return CUMF_OK;
 }
 
+// Test mode CUMF_GROUP_SAME_DEVICE=1 puts every shard on one GPU.  There a spinning barrier CTA of one shard holds a few
+// registers of an SM, and the persistent half-step kernel of another shard (one CTA per SM, the whole register file) could
+// wait for that SM for ever: the plans of such a group leave one SM per shard free.  One shard per device needs none of this.
+static void same_device_leave_sms(int device, int shards) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    setenv("CUMF_TC_CTAS", std::to_string(std::max(1, sms - shards)).c_str(), 1);
+}
+
 // rank / peer tables of a fully created group (same process: plain device pointers, peer access enabled by the caller)
 static void group_connect(cumf_als_group* g) {
     const int n = (int)g->s.size();
@@ -1478,6 +1487,7 @@ extern "C" int cumf_group_create_synth(cumf_als_group** out, long long m, int n,
     CUMF_CUDA_TRY(cudaGetDeviceCount(&have));
     const bool same_device = env_long("CUMF_GROUP_SAME_DEVICE", 0) != 0;
     CUMF_REQUIRE(first_device >= 0 && first_device + (same_device ? 1 : n_devices) <= have, "not that many devices on this node");
+    if (same_device) same_device_leave_sms(first_device, n_devices);
     cumf_als_group* g = new cumf_als_group();
     g->m = (int)m; g->n = n; g->f = f; g->nnz_test = test_per_shard * n_devices;
     g->s.assign(n_devices, nullptr);
@@ -1523,6 +1533,7 @@ static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr
     const bool same_device = env_long("CUMF_GROUP_SAME_DEVICE", 0) != 0;
     CUMF_REQUIRE(first_device >= 0 && first_device + (same_device ? 1 : n_devices) <= have, "not that many devices on this node");
     auto device_of = [=](int k) { return same_device ? first_device : first_device + k; };
+    if (same_device) same_device_leave_sms(first_device, n_devices);
     cumf_als_group* g = new cumf_als_group();
     g->m = m; g->n = n; g->f = f; g->nnz = nnz; g->nnz_test = nnz_test;
     g->s.assign(n_devices, nullptr);

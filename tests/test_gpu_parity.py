@@ -281,9 +281,10 @@ def test_doals_vs_live_reference(cuda, f, theta_batch):
 TC_LENGTHS = [16, 1, 2, 15, 17, 31, 32, 33, 0, 100, 250, 1000, 3000, 48, 5]
 
 
-def test_tc_gram_vs_oracle(cuda):
+def test_tc_gram_vs_oracle(cuda, monkeypatch):
     """A materialised through the fused TMA + tcgen05 kernel (split-fp16 operands, fp32 TMEM
     accumulation) against the exact-fp32 restatement: error far below the 1e-4 parity bar."""
+    monkeypatch.setenv("CUMF_TC_IMPL", "1")          # the round-1 f = 100 kernel (gram_tc.cu); the generic one: test_gpu_generic_f.py
     rng = np.random.default_rng(1)
     n, f, lam = 5000, 100, 0.05
     rowptr, colidx, val = random_csr(rng, TC_LENGTHS, n)
@@ -296,8 +297,9 @@ def test_tc_gram_vs_oracle(cuda):
     assert np.allclose(rhs, O.rhs(rowptr, colidx, val, factor, f), rtol=1e-5, atol=1e-4)     # fp32 FMAs, two partial sums
 
 
-def test_tc_gram_small_and_large_values(cuda):
+def test_tc_gram_small_and_large_values(cuda, monkeypatch):
     """The hi/lo split keeps ~22 mantissa bits across magnitudes (values from 1e-3 to 30)."""
+    monkeypatch.setenv("CUMF_TC_IMPL", "1")
     rng = np.random.default_rng(2)
     n, f = 800, 100
     rowptr, colidx, val = random_csr(rng, [200, 40, 333], n)
@@ -311,6 +313,7 @@ def test_tc_gram_small_and_large_values(cuda):
 @pytest.mark.parametrize("split", [None, "64"])
 def test_tc_half_step_vs_simt(cuda, monkeypatch, split):
     """One half-step (Gram + RHS + CG) fused vs unfused, including rows split across CTAs."""
+    monkeypatch.setenv("CUMF_TC_IMPL", "1")
     if split:
         monkeypatch.setenv("CUMF_SPLIT_NNZ", split)
     rng = np.random.default_rng(3)
@@ -386,8 +389,9 @@ def test_doals_fused_midsize_vs_simt(cuda):
 
 # ---- partial Gram over per-row rating ranges (multi-GPU form, hugewiki.cu:1675-1678, 2629-2696) -----------------
 @pytest.mark.parametrize("f,path", [(20, c.PATH_SIMT), (100, c.PATH_SIMT), (100, c.PATH_TC)])
-def test_plan_gram_ranges_vs_oracle(cuda, f, path):
+def test_plan_gram_ranges_vs_oracle(cuda, monkeypatch, f, path):
     """cumf_plan_create_ranges + cumf_plan_gram: [A|b] over a sub-range of every row, lambda * local count."""
+    monkeypatch.setenv("CUMF_TC_IMPL", "1")
     rng = np.random.default_rng(11)
     n, lam = 3000, 0.05
     lengths = [0, 1, 16, 17, 40, 333, 5, 64, 1200, 2, 90, 31] * 14
@@ -525,6 +529,7 @@ def test_tc_direct_staging_bit_identical_to_fp32_staging(cuda, monkeypatch):
     """Both stagings hand the tensor core the same operands in the same order (16-rating k-groups, accumulation
     chains cut every 256 ratings), so the materialised [A|b] must agree bit for bit -- including ragged stages,
     empty rows and multi-tile rows."""
+    monkeypatch.setenv("CUMF_TC_IMPL", "1")          # both stagings belong to the round-1 kernel
     rng = np.random.default_rng(11)
     n, f, lam = 6000, 100, 0.05
     lengths = TC_LENGTHS + [64, 65, 255, 256, 257, 511, 513]
@@ -541,6 +546,7 @@ def test_tc_direct_staging_bit_identical_to_fp32_staging(cuda, monkeypatch):
 def test_tc_half_step_both_stagings_vs_simt(cuda, monkeypatch, direct):
     """Fused half-step (long-row and short-row kernel variants of either staging) against the exact-fp32 unfused path."""
     monkeypatch.setenv("CUMF_TC_DIRECT", direct)
+    monkeypatch.setenv("CUMF_TC_IMPL", "1")
     rng = np.random.default_rng(12)
     n, f, lam = 9000, 100, 0.048
     for lengths in ([int(x) for x in rng.integers(1, 120, 600)],            # short rows: two-MMA variant (three solver warpgroups)
