@@ -134,12 +134,11 @@ template <int F, int MODE> struct __align__(1024) Smem {
     unsigned char ring[C::kRing];                 // kSlots stages, TMA destination == UMMA operand
     unsigned char ring_guard[2 * ATOM_BYTES];     // A-operand windows of the last stage may read one atom past the ring
     float stage_vals[NBAR][MAX_ROWS];
-    uint32_t meta_op[NBAR];
     __align__(16) int stage_idx[NBAR][MAX_ROWS];
     float solver_scratch[C::kScratch];
     __align__(16) float sp[C::kSys][2][C::kSpN];  // CG direction vector per system, double buffered
     float red[C::kSys][3][8];                     // cross-warp partial sums
-    unsigned long long full_tma[NBAR], full_op[NBAR], empty_op[NBAR];
+    unsigned long long full_tma[NBAR], empty_op[NBAR];
     unsigned long long acc_full[MAX_SYS][MAX_BUF], acc_empty[MAX_BUF];
     uint32_t tmem_base;
     __device__ __forceinline__ unsigned char* dstage(int slot) { return ring + slot * C::G::STAGE_BYTES; }
@@ -358,7 +357,7 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
 
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();      // SWIZZLE_128B atoms need 1024-byte alignment
     if (tid == 0) {
-        for (int s = 0; s < NBAR; ++s) { mbar_init(&sm.full_tma[s], 1); mbar_init(&sm.full_op[s], 1); mbar_init(&sm.empty_op[s], 1); }
+        for (int s = 0; s < NBAR; ++s) { mbar_init(&sm.full_tma[s], 1); mbar_init(&sm.empty_op[s], 1); }
         for (int b = 0; b < MAX_BUF; ++b) {
             for (int g = 0; g < MAX_SYS; ++g) mbar_init(&sm.acc_full[g][b], 1);
             mbar_init(&sm.acc_empty[b], 4 * RB);
@@ -385,6 +384,7 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(&sm.tmem_base);
             const uint32_t empty_bar0 = smem_u32(&sm.empty_op[0]);
             const uint32_t acc_full_bar0 = smem_u32(&sm.acc_full[0][0]);      // [sys][buf], 8 bytes each
+            const float rscale = __ldg(P.scales + 2);
             uint32_t slot = 0, ph = 0;
             int S = s_begin;
             const int s_end = s_begin + total_stages;
@@ -402,11 +402,36 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 const uint32_t last_groups = ((info >> TILE_LAST_GROUPS_SHIFT) & 3u) + 1u;
                 mbar_wait(&sm.acc_empty[buf], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
                 for (uint32_t st = 0; st < stages; ++st) {
-                    mbar_wait(&sm.full_op[slot], ph);
+                    const uint32_t groups = (st + 1u < stages) ? (uint32_t)KGROUPS : last_groups;
+                    mbar_wait(&sm.full_tma[slot], ph);          // the gathered rows have landed (TMA complete_tx)
+                    {
+                        // The rating rides along as feature F of gathered row kk: hi part in the hi region, lo part in the lo region.
+                        // This warp drops them in itself -- the slot's worker is free to refill other slots, and a landed stage
+                        // never waits for a worker that is busy issuing gathers (round 2: 40 % of the workers' time was spent
+                        // blocked between these two duties while landed stages sat unprocessed).
+                        unsigned char* sbase = sm.dstage((int)slot);
+                        constexpr int LPR = KROWS / 32;
+#pragma unroll
+                        for (int e = 0; e < LPR; ++e) {
+                            const uint32_t kk = (uint32_t)lane + 32u * e;
+                            if ((kk >> 4) < groups) {
+                                const float r0 = sm.stage_vals[slot][kk] * rscale;
+                                const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
+                                const float l0 = kSym ? 2.f * (r0 - h0) : (r0 - h0);
+                                const uint32_t k = kk & 15u;
+                                constexpr uint32_t cF = F / CHUNK, eF = F % CHUNK;
+                                unsigned char* row = sbase + (kk >> 4) * G::KG_BYTES + (k >> 3) * G::SBO + (k & 7u) * 128u +
+                                                     (((eF >> 3) ^ (k & 7u)) << 4) + (eF & 7u) * 2u;
+                                *reinterpret_cast<__half*>(row + cF * ATOM_BYTES) = __float2half_rn(h0);
+                                *reinterpret_cast<__half*>(row + (CR + cF) * ATOM_BYTES) = __float2half_rn(l0);
+                            }
+                        }
+                        fence_proxy_async();                    // generic-proxy writes ordered before the tensor core's reads
+                        __syncwarp();
+                    }
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t d_stage = dbase + (uint64_t)(slot * (uint32_t)(G::STAGE_BYTES >> 4));
-                        const uint32_t groups = (st + 1u < stages) ? (uint32_t)KGROUPS : last_groups;
 #pragma unroll
                         for (int g = 0; g < KGROUPS; ++g) {
                             if ((uint32_t)g < groups) {
@@ -440,7 +465,6 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             constexpr int LPR = KROWS / 32;       // ratings per lane of a stage
             const int sw = warp - C::kFirstWorker;
             const int own = (total_stages > sw) ? (total_stages - sw + W - 1) / W : 0;
-            const float rscale = __ldg(P.scales + 2);
             auto load_desc = [&](int t) -> StageDesc {
                 return (t < own) ? P.stage_tab[s_begin + sw + W * t] : StageDesc{0, 0u};
             };
@@ -464,7 +488,6 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                     sm.stage_vals[slot][lane + 32 * e] = rat.val[e];
                     sm.stage_idx[slot][lane + 32 * e] = rat.idx[e];
                 }
-                if (lane == 0) sm.meta_op[slot] = flags;
                 __syncwarp();
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&sm.full_tma[slot], groups * (uint32_t)(P.hi_only ? G::KG_BYTES / 2 : G::KG_BYTES));
@@ -493,40 +516,20 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                     issue(sw + W * j, d.info >> 8, rat);
                 }
             }
-            StageDesc dn = load_desc(R);
+            // refills: own-stage t goes into slot sw + W (t mod R) once the MMAs of own-stage t - R (use number t / R - 1 of that
+            // slot) have retired (tcgen05.commit -> empty_op); descriptor and ratings of the next refill are prefetched
+            StageDesc dcur = load_desc(R);
+            Rat rat = load_rat(dcur);
             int slot_j = 0;
             uint32_t par = 0;
-            for (int t = 0; t < own; ++t) {
-                const StageDesc dcur = dn;
-                dn = load_desc(t + R + 1);
-                const Rat nrat = load_rat(dcur);
+            for (int t = R; t < own; ++t) {
+                const StageDesc dnext = load_desc(t + 1);
+                const Rat nrat = load_rat(dnext);
                 const int slot = sw + W * slot_j;
-                unsigned char* sbase = sm.dstage(slot);
-                mbar_wait(&sm.full_tma[slot], par);
-                const uint32_t groups = ((sm.meta_op[slot] >> FLAG_GROUPS_SHIFT) & 3u) + 1u;
-#pragma unroll
-                for (int e = 0; e < LPR; ++e) {
-                    const uint32_t kk = (uint32_t)lane + 32u * e;
-                    if ((kk >> 4) < groups) {
-                        // the rating rides along as feature F of gathered row kk: hi part in the hi region, lo part in the lo region
-                        const float r0 = sm.stage_vals[slot][kk] * rscale;
-                        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
-                        const float l0 = kSym ? 2.f * (r0 - h0) : (r0 - h0);
-                        const uint32_t k = kk & 15u;
-                        constexpr uint32_t cF = F / CHUNK, eF = F % CHUNK;
-                        unsigned char* row = sbase + (kk >> 4) * G::KG_BYTES + (k >> 3) * G::SBO + (k & 7u) * 128u +
-                                             (((eF >> 3) ^ (k & 7u)) << 4) + (eF & 7u) * 2u;
-                        *reinterpret_cast<__half*>(row + cF * ATOM_BYTES) = __float2half_rn(h0);
-                        *reinterpret_cast<__half*>(row + (CR + cF) * ATOM_BYTES) = __float2half_rn(l0);
-                    }
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.full_op[slot]);
-                if (t + R < own) {
-                    mbar_wait(&sm.empty_op[slot], par);
-                    issue(slot, dcur.info >> 8, nrat);
-                }
+                mbar_wait(&sm.empty_op[slot], par);
+                issue(slot, dcur.info >> 8, rat);
+                dcur = dnext;
+                rat = nrat;
                 if (++slot_j == R) { slot_j = 0; par ^= 1u; }
             }
         }
