@@ -1077,6 +1077,16 @@ extern "C" int cumf_als_create_device(cumf_als_solver** out, const long long* h_
 extern "C" int cumf_als_collect_train_sse(cumf_als_solver* s, int on) {
     CUMF_REQUIRE(s && s->pt, "null pointer");
     s->pt->collect_sse = (on != 0) && s->can_collect_sse;
+    if (s->pt->collect_sse && s->pt->tc) {
+        // the per-CTA / per-split-row terms are allocated now: the half-steps themselves must not allocate (a device
+        // allocation synchronises the device, see tc_plan_set_factor_rows)
+        cudaSetDevice(s->device);
+        const int want = tc_sse_terms_per_cta() * tc_plan_grid(s->pt->tc) + (int)s->pt->splits.size();
+        if (s->pt->sse_terms_count != want) {
+            s->pt->sse_terms.release();
+            if (s->pt->sse_terms.alloc(sizeof(double) * std::max(1, want)) == CUMF_OK) s->pt->sse_terms_count = want;
+        }
+    }
     if (!s->pt->collect_sse) { s->pt->sse_terms_valid = false; s->theta_fresh = false; }
     return s->pt->collect_sse ? 1 : 0;
 }

@@ -1034,7 +1034,7 @@ static EncodeFn tensor_map_encoder() {
 
 // pre-split fp16 table [rows][256]: tile::gather4 fetches four {64, 1} boxes (one 128-byte swizzle line per row);
 // coordinates beyond `rows` are out of bounds and read as zero
-static int encode_split_map(CUtensorMap* map, const void* d_table, long long rows, int cols = SPLIT_COLS) {
+static int encode_split_map(CUtensorMap* map, const void* d_table, long long rows, int cols) {
     EncodeFn encode = tensor_map_encoder();
     if (!encode) return CUMF_ECUDA;
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -1077,8 +1077,31 @@ int tc_plan_impl(const TcWork* w) { return w ? w->impl : 0; }
 // rows of the opposing factor, when the caller knows them: saves the index scan (and its stream synchronisation) of
 // the first direct-staging launch
 // (also invalidates the cached scan: the next launch validates the index buffer it is given against `rows`)
+static int encode_split_map(CUtensorMap* map, const void* d_table, long long rows, int cols);
+// Everything the launches need is allocated HERE, not by the first launch: a device allocation synchronises the device, and in
+// a multi-GPU run the first half-step of one rank must not wait for a barrier kernel that is spinning for its peers.
 void tc_plan_set_factor_rows(TcWork* w, int rows) {
-    if (w && rows > 0) { w->hint_rows = rows; w->scanned_colidx = nullptr; w->scaled_val = nullptr; }
+    if (!w || rows <= 0) return;
+    w->hint_rows = rows;
+    w->scanned_colidx = nullptr;
+    w->scaled_val = nullptr;
+    if (!w->direct) return;
+    if (rows != w->factor_rows || !w->split_tab.p) {
+        const int cols = w->impl == 2 ? w->info2.tab_cols : SPLIT_COLS;
+        w->split_tab.release();
+        if (w->split_tab.alloc((size_t)(rows + 1) * cols * 2) == CUMF_OK &&
+            encode_split_map(&w->split_map, w->split_tab.p, (long long)rows + 1, cols) == CUMF_OK)
+            w->factor_rows = rows;
+        else
+            w->split_tab.release();          // the launch path reports the failure
+    }
+    if (!w->max_idx.p) w->max_idx.alloc(sizeof(int));
+    if (!w->h_max_idx) cudaHostAlloc(reinterpret_cast<void**>(&w->h_max_idx), sizeof(int), cudaHostAllocDefault);
+    if (!w->max_idx_ready) cudaEventCreateWithFlags(&w->max_idx_ready, cudaEventDisableTiming);
+    if (w->impl == 2) {
+        if (!w->absmax.p) w->absmax.alloc(4 * sizeof(unsigned));
+        if (!w->scales.p) w->scales.alloc(4 * sizeof(float));
+    }
 }
 int tc_sse_terms_per_cta() { return MAX_WG; }
 

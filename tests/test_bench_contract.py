@@ -57,3 +57,33 @@ def test_two_gpu_line_is_whole_job_throughput():
     assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["nnz"] == one["config"]["nnz"]
     assert one["value"] < d["value"] < 2.2 * one["value"]
     assert "e2e" in d and d["e2e"]["h2d_bytes_per_step"] > 0
+
+
+# ---- round 2: both arms print the same `config`, the true warm-up count, per-launch roofline entries --------------------
+def test_round2_lines_same_config_in_both_arms():
+    ours, ref = _line("r2_bench_ours.json"), _line("r2_bench_reference.json")
+    assert ref["impl"] == "reference" and "impl" not in ours
+    assert ours["config"] == ref["config"]                                   # the driver's same_config check
+    assert ours["steps"] == ref["steps"] and ours["warmup"] == ref["warmup"] >= 3
+    for k in ("metric", "unit", "higher_is_better", "scaling", "data"):
+        assert ours[k] == ref[k]
+    assert ours["dtype"].startswith("f32") and "split-fp16" in ours["dtype"]
+    r = ours["roofline"]
+    assert r["bound"] == "hbm" and r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and r["traffic"]
+    for side in ("x_side", "theta_side"):
+        l = r["launches"][side]
+        assert {"ms", "algorithmic_gbs", "frac_hbm", "useful_tflops", "frac_tensor", "dram_bytes", "tensor_pipe_pct", "bound"} <= set(l)
+    assert r["launches"]["theta_side"]["bound"].startswith("tensor+l2") and r["launches"]["x_side"]["bound"] == "hbm"
+    c = ours["cpu_baseline"]
+    assert c["cores"] == 1 and c["kind"] == "port" and c["all_cores"]["cores"] >= 1 and c["all_cores"]["value"] > c["value"]
+    e = ours["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < ours["value"]
+    assert ours["gpu_launches"] > 0 and ref["gpu_launches"] == 0
+    assert ours["value"] > 20 * ref["value"]
+
+
+def test_round2_two_gpu_line():
+    d, one = _line("r2e_bench_2gpu_rows.json"), _line("r2_bench_ours.json")
+    assert d["n_gpus"] == 2 and d["config"] == one["config"] and d["scaling"] == "strong"
+    assert 1.8 * one["value"] < d["value"] < 2.2 * one["value"]
+    assert d["e2e"]["gpus"] == 2 and d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] * d["steps"] == (d["config"]["m"] + d["config"]["n"]) * d["config"]["f"] * 4
