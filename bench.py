@@ -449,24 +449,31 @@ def run_ours_partial_gram(args, w):
     with ClockSampler(local_rank) as clocks:
         ms = drv.iterate(args.steps)
         barrier()
-    # one more, instrumented, iteration for the phase split (outside the timed region)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    phases = None
-    if len(eng.batches) == 1:
-        barrier()
+    # one more, instrumented and serial, iteration for the phase split (outside the timed region): per phase summed over the
+    # row batches
+    phases = {"partial_gram_ms": 0.0, "allreduce_ms": 0.0, "cg_x_ms": 0.0, "theta_ms": 0.0}
+    barrier()
+    for b in range(len(eng.batches)):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        tt, rhs = eng.partial_gram(0)
+        tt, rhs = eng.partial_gram(b)
         ev[1].record()
         if world > 1:
             dist.all_reduce(tt)
             dist.all_reduce(rhs)
         ev[2].record()
-        eng.solve_x(0, tt, rhs)
+        eng.solve_x(b, tt, rhs)
         ev[3].record()
-        eng.update_theta()
-        ev[4].record()
         torch.cuda.synchronize()
-        phases = {k: ev[i].elapsed_time(ev[i + 1]) for i, k in enumerate(["partial_gram_ms", "allreduce_ms", "cg_x_ms", "theta_ms"])}
+        for i, k in enumerate(["partial_gram_ms", "allreduce_ms", "cg_x_ms"]):
+            phases[k] += ev[i].elapsed_time(ev[i + 1])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.update_theta()
+    e1.record()
+    torch.cuda.synchronize()
+    phases["theta_ms"] = e0.elapsed_time(e1)
+    phases["serial_sum_ms"] = sum(phases.values())
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -479,6 +486,9 @@ def run_ours_partial_gram(args, w):
         nnz_t = int(r.csc_indptr[t1] - r.csc_indptr[t0])
         gb = (gram_bytes(r.m, eng.local_nnz, f, False) + gram_bytes(t1 - t0, nnz_t, f, fused)) / 1e9
         kernel_ms = (phases["partial_gram_ms"] + phases["theta_ms"]) if phases else None
+        # how much of the all-reduce the timed (possibly overlapped) iteration hides: serial phase sum vs measured step
+        if phases and phases["allreduce_ms"] > 0:
+            phases["allreduce_hidden_frac"] = max(0.0, min(1.0, (phases["serial_sum_ms"] - ms / args.steps) / phases["allreduce_ms"]))
         achieved = gb / (kernel_ms / 1e3) if kernel_ms else None
         print(json.dumps({
             "metric": METRIC.format(workload=args.workload, f=f), "value": args.steps / (ms / 1e3),
