@@ -109,6 +109,10 @@ SIGNATURES = {
     "cumf_als_init_factors_device": (C.c_int, [_vp, C.c_ulonglong, C.c_float]),
     "cumf_group_create_synth": (C.c_int, [C.POINTER(_vp), C.c_longlong, C.c_int, C.c_float, C.c_ulonglong, C.c_long, C.c_int,
                                           C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "cumf_csr_to_csc_device": (C.c_int, [C.c_int, C.c_int, C.c_longlong, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cumf_bin_shard_extent": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "cumf_load_bin_slice": (C.c_int, [C.c_char_p, C.c_int, C.c_longlong, C.c_longlong, _vp]),
+    "cumf_load_csr_shard_bin": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "cumf_group_nnz": (C.c_long, [_vp]),
     "cumf_group_nnz_test": (C.c_long, [_vp]),
 }
@@ -404,6 +408,33 @@ class AlsSolver:
             self.close()
         except Exception:
             pass
+
+
+def load_csr_shard(data_file, indptr_file, indices_file, rows: int, row_begin: int, row_end: int):
+    """(ptr int64 rebased to 0, idx int32, val float32) of rows [row_begin, row_end) of a CSR (or columns of a CSC) .bin file
+    set, read with seeks (cumf_load_csr_shard_bin)."""
+    lib = load_library()
+    first, count = C.c_longlong(0), C.c_longlong(0)
+    if lib.cumf_bin_shard_extent(str(indptr_file).encode(), rows, row_begin, row_end, C.byref(first), C.byref(count)):
+        raise CumfError(f"cannot read rows [{row_begin}, {row_end}) of {indptr_file}")
+    ptr = np.empty(row_end - row_begin + 1, np.int64)
+    idx, val = np.empty(count.value, np.int32), np.empty(count.value, np.float32)
+    if lib.cumf_load_csr_shard_bin(str(data_file).encode(), str(indptr_file).encode(), str(indices_file).encode(), rows, row_begin,
+                                   row_end, _hp(ptr), _hp(idx), _hp(val)):
+        raise CumfError(f"cannot read the slice of {data_file} / {indices_file}")
+    return ptr, idx, val
+
+
+def csr_to_csc_device(rows: int, cols: int, rowptr, col, val, stream=None):
+    """CSR -> CSC on the device (cumf_csr_to_csc_device); torch CUDA tensors in (rowptr int64), tensors out."""
+    import torch
+    nnz = int(col.numel())
+    colptr = torch.empty(cols + 1, dtype=torch.int64, device=col.device)
+    row_out = torch.empty(max(nnz, 1), dtype=torch.int32, device=col.device)[:nnz]
+    val_out = torch.empty(max(nnz, 1), dtype=torch.float32, device=col.device)[:nnz]
+    _check(load_library().cumf_csr_to_csc_device(rows, cols, nnz, _dptr(rowptr), _dptr(col), _dptr(val), _dptr(colptr), _dptr(row_out),
+                                                 _dptr(val_out), _stream_ptr(stream)), "cumf_csr_to_csc_device")
+    return colptr, row_out, val_out
 
 
 class SynthShard:

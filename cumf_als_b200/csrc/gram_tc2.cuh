@@ -99,34 +99,53 @@ template <int F_> struct Geo {
     static_assert(2 * RB <= CR + 1 || RB == 1, "row block 1 of the hi region must start inside the region");
 };
 
+// CTA shapes.  Warp 3 issues the MMAs; stage workers are the other warps below kFirstEpiWarp, in order, the first kWorkers of
+// them (worker w owns ring slots w + kWorkers j); solver warpgroups follow.
+//   long rows (SYM):       20 warps  | 0-2 idle | 3 issuer | 4-8 five workers x 1 slot | 12-19 two solver warpgroups (2 systems)
+//   short rows, f <= 100:  16 warps  | 0-2 three workers x 2 slots | 3 issuer | 4-15 three solver warpgroups (3 systems)
+//                          (CUMF_TC2_W6S2: 0-2, 4-6 six workers x 1 slot | 3 issuer | 8-15 two solver warpgroups)
+//   f = 110, 120:          12 warps  | 0-2 workers x 2 slots | 3 issuer | 4-11 two solver warpgroups (2 systems, 224 registers)
+//   f >= 130 (RB = 2):     12 warps  | 0-2 workers x 2 slots | 3 issuer | 4-11 two warpgroups = ONE system
 template <int F, int MODE> struct Cfg {
     using G = Geo<F>;
     static constexpr bool kSym = (MODE == SYM);
     static_assert(!kSym || (G::RB == 1 && F <= 100), "the symmetric variant holds F + transposition temporaries in 152 registers");
+#ifdef CUMF_TC2_W6S2
+    static constexpr bool kSixWorkers = !kSym && G::RB == 1 && F <= 100;     // experiment: more gather-issuing warps, one system less
+#else
+    static constexpr bool kSixWorkers = false;
+#endif
     static constexpr int kSysWG = G::RB;                                          // warpgroups per system
-    static constexpr int kWG = kSym ? 2 : (G::RB == 2 ? 2 : (F <= 100 ? 3 : 2));  // solver warpgroups
+    static constexpr int kWG = kSym ? 2 : (G::RB == 2 ? 2 : ((F <= 100 && !kSixWorkers) ? 3 : 2));  // solver warpgroups
     static constexpr int kSys = kWG / kSysWG;                                     // systems in flight
     static constexpr int kFirstWorker = kSym ? 4 : 0;
-    static constexpr int kWorkers = kSym ? 5 : 3;
+    static constexpr int kWorkers = kSym ? 5 : (kSixWorkers ? 6 : 3);
 #ifdef CUMF_TC2_KROWS32
     static constexpr int kSlotsPerWorker = kSym ? 2 : (G::RB == 2 ? 2 : 4);
 #else
-    static constexpr int kSlotsPerWorker = kSym ? 1 : 2;
+    static constexpr int kSlotsPerWorker = (kSym || kSixWorkers) ? 1 : 2;
 #endif
     static constexpr int kSlots = kWorkers * kSlotsPerWorker;
-    static constexpr int kFirstEpiWarp = kSym ? 12 : 4;
+    static constexpr int kFirstEpiWarp = kSym ? 12 : (kSixWorkers ? 8 : 4);
     static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;               // 640 / 512 / 384
-    static constexpr int kRegsLaunch = kSym ? 96 : (kWG == 3 ? 128 : 168);
+    static constexpr int kRegsLaunch = kSym ? 96 : (kThreads == 512 ? 128 : 168);
     static constexpr int kRegsProd = kSym ? 80 : 56;
-    static constexpr int kRegsStage = 48;                                         // kSym: warpgroups 1, 2 (stage workers)
-    static constexpr int kRegsEpi = kSym ? 152 : (kWG == 3 ? 152 : 224);
+    static constexpr int kRegsStage = 48;                                         // warpgroups of workers only (warps 4 .. kFirstEpiWarp)
+    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 512 ? 152 : 224);
     static constexpr int kRing = kSlots * G::STAGE_BYTES;
     static constexpr int kTrRows = F / 2;                                         // kSym: rows of G exchanged per pass (2 passes)
     static constexpr int kScratch = kSym ? kSys * (kTrRows + 1) * F : 4;
     static constexpr int kSpN = 128 * G::RB;
-    static_assert(128 * (kRegsProd + (kSym ? 2 * kRegsStage : 0) + kWG * kRegsEpi) <= kThreads * kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
+    static constexpr int kStageWGs = (kFirstEpiWarp - 4) / 4;                     // warpgroups 1 .. that hold only workers / idle warps
+    static_assert(128 * (kRegsProd + kStageWGs * kRegsStage + kWG * kRegsEpi) <= kThreads * kRegsLaunch, "setmaxnreg budgets exceed the CTA register pool");
     static_assert(kThreads * kRegsLaunch <= 65536, "launch registers");
     static_assert(kSlots <= NBAR, "ring barriers");
+    // worker index of a warp (-1: not a worker): warps below kFirstEpiWarp except the issuer, counted from kFirstWorker
+    __host__ __device__ static constexpr int worker_of(int warp) {
+        return (warp == MMA_WARP || warp < kFirstWorker || warp >= kFirstEpiWarp) ? -1
+               : ((warp - kFirstWorker - ((warp > MMA_WARP && kFirstWorker <= MMA_WARP) ? 1 : 0)) < kWorkers
+                      ? (warp - kFirstWorker - ((warp > MMA_WARP && kFirstWorker <= MMA_WARP) ? 1 : 0)) : -1);
+    }
 };
 
 template <int F, int MODE> struct __align__(1024) Smem {
@@ -189,7 +208,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 // Waits park the warp (try_wait with a suspend-time hint -> NANOSLEEP.SYNCS).  Watchdog: a protocol error must fail the
 // launch instead of hanging the GPU -- after 2^18 unsuccessful polls (each parks for up to 100 us: 0.3 .. 26 s; a healthy wait
 // is microseconds) the CTA traps.  A poll counter, not a clock read: the wait loops are part of every role's hot path.
-constexpr uint32_t kWaitHintNs = 100000u;
+#ifndef CUMF_TC2_WAIT_NS
+#define CUMF_TC2_WAIT_NS 100000
+#endif
+constexpr uint32_t kWaitHintNs = CUMF_TC2_WAIT_NS;
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done, polls = 0;
@@ -458,12 +480,12 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 }
             }
         }
-    } else if (warp >= C::kFirstWorker && warp < C::kFirstWorker + C::kWorkers) {
+    } else if (C::worker_of(warp) >= 0) {
         if (n_chunks > 0) {
             // ============ stage workers: worker w owns stages w, w + W, ... and ring slots w + W j ===========
             constexpr int W = C::kWorkers, R = C::kSlotsPerWorker;
             constexpr int LPR = KROWS / 32;       // ratings per lane of a stage
-            const int sw = warp - C::kFirstWorker;
+            const int sw = C::worker_of(warp);
             const int own = (total_stages > sw) ? (total_stages - sw + W - 1) / W : 0;
             auto load_desc = [&](int t) -> StageDesc {
                 return (t < own) ? P.stage_tab[s_begin + sw + W * t] : StageDesc{0, 0u};

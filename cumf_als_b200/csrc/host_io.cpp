@@ -5,6 +5,7 @@
 // keep the reference's names and void signatures (host_utilities.h:31-40) so the
 // reference's unmodified main.cpp links against this library.
 #include <cstdio>
+#include <vector>
 #include <cstdlib>
 
 #include "../../include/cumf_als.h"
@@ -45,6 +46,46 @@ extern "C" int cumf_load_coo_bin(const char* dataFile, const char* rowFile, cons
     rc |= read_items(colFile, col, (size_t)nnz);
     rc |= read_items(dataFile, data, (size_t)nnz);
     return rc ? -1 : 0;
+}
+
+// ---- sharded loading: one rank reads only ITS rows of the CLI's .bin files (hugewiki.cu:2332-2340 keeps one file set per GPU
+// batch; here the reference's own single file set is sliced with seeks, so no process ever holds the whole matrix) ----------
+extern "C" int cumf_bin_shard_extent(const char* indptrFile, int rows, int row_begin, int row_end, long long* first, long long* count) {
+    if (!indptrFile || !first || !count || row_begin < 0 || row_begin > row_end || row_end > rows) return -1;
+    FILE* f = fopen(indptrFile, "rb");
+    if (!f) return -1;
+    int a = 0, b = 0;
+    int ok = fseek(f, (long)sizeof(int) * row_begin, SEEK_SET) == 0 && fread(&a, sizeof(int), 1, f) == 1 &&
+             fseek(f, (long)sizeof(int) * row_end, SEEK_SET) == 0 && fread(&b, sizeof(int), 1, f) == 1;
+    fclose(f);
+    if (!ok || b < a) return -1;
+    *first = a;
+    *count = (long long)b - a;
+    return 0;
+}
+// `count` items of `elem_size` bytes starting at item `first` of a headerless .bin file
+extern "C" int cumf_load_bin_slice(const char* file, int elem_size, long long first, long long count, void* dst) {
+    if (!file || !dst || elem_size <= 0 || first < 0 || count < 0) return -1;
+    FILE* f = fopen(file, "rb");
+    if (!f) return -1;
+    int ok = fseek(f, (long)(first * elem_size), SEEK_SET) == 0 && fread(dst, (size_t)elem_size, (size_t)count, f) == (size_t)count;
+    fclose(f);
+    return ok ? 0 : -1;
+}
+// rows [row_begin, row_end) of a CSR (or columns of a CSC) file set: ptr_out gets row_end - row_begin + 1 pointers rebased to
+// 0 (int64, what cumf_als_create_device / cumf_plan_create64 take), idx_out / val_out the slice (sized by cumf_bin_shard_extent)
+extern "C" int cumf_load_csr_shard_bin(const char* dataFile, const char* indptrFile, const char* indicesFile, int rows, int row_begin,
+                                       int row_end, long long* ptr_out, int* idx_out, float* val_out) {
+    long long first = 0, count = 0;
+    if (!ptr_out || cumf_bin_shard_extent(indptrFile, rows, row_begin, row_end, &first, &count)) return -1;
+    std::vector<int> ptr((size_t)(row_end - row_begin) + 1);
+    if (cumf_load_bin_slice(indptrFile, (int)sizeof(int), row_begin, (long long)ptr.size(), ptr.data())) return -1;
+    for (size_t i = 0; i < ptr.size(); ++i) ptr_out[i] = (long long)ptr[i] - first;
+    if (count == 0) return 0;
+    if (!idx_out || !val_out) return -1;
+    if (cumf_load_bin_slice(indicesFile, (int)sizeof(int), first, count, idx_out)) return -1;
+    if (cumf_load_bin_slice(dataFile, (int)sizeof(float), first, count, val_out)) return -1;
+    return 0;
 }
 
 // Factor initialisation loops of the reference's two front ends, on glibc rand() like they are.

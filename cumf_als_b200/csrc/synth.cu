@@ -297,6 +297,44 @@ extern "C" int cumf_synth_download_test(const cumf_synth_shard* sh, int* row_out
 
 namespace cumf {
 namespace {
+// one warp per row: key = column << 32 | row for every entry
+__global__ void csr_keys_kernel(const long long* __restrict__ ptr, const int* __restrict__ col, int rows, unsigned long long* __restrict__ keys) {
+    const int warp = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    for (long long k = ptr[warp] + lane; k < ptr[warp + 1]; k += 32) keys[k] = ((unsigned long long)(unsigned)col[k] << 32) | (unsigned long long)warp;
+}
+}  // namespace
+}  // namespace cumf
+
+// CSR -> CSC on the device (the reference ships both orientations as files, prepare_netflix_data.py:98-110):
+// one radix sort of (column, row) keys, rows ascending inside every column like scipy's tocsc.  All pointers are device
+// pointers; d_rowptr / d_colptr_out are int64 (rows + 1 / cols + 1 entries).  Synchronises `stream`.
+extern "C" int cumf_csr_to_csc_device(int rows, int cols, long long nnz, const long long* d_rowptr, const int* d_col, const float* d_val,
+                                      long long* d_colptr_out, int* d_row_out, float* d_val_out, void* stream) {
+    CUMF_REQUIRE(rows >= 0 && cols >= 0 && nnz >= 0 && d_rowptr && d_colptr_out, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    DevBuf keys_a, keys_b, tmp;
+    const size_t cap = (size_t)std::max<long long>(nnz, 1);
+    CUMF_TRY(keys_a.alloc(sizeof(unsigned long long) * cap));
+    CUMF_TRY(keys_b.alloc(sizeof(unsigned long long) * cap));
+    if (rows && nnz) csr_keys_kernel<<<(unsigned)(((size_t)rows * 32 + 255) / 256), 256, 0, st>>>(d_rowptr, d_col, rows, keys_a.as<unsigned long long>());
+    int col_bits = 1;
+    while ((1ll << col_bits) < std::max(cols, 2)) ++col_bits;
+    size_t bytes = 0;
+    CUMF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys_a.as<unsigned long long>(), keys_b.as<unsigned long long>(), d_val, d_val_out,
+                                                  nnz, 0, 32 + col_bits, st));
+    CUMF_TRY(tmp.alloc(bytes));
+    CUMF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys_a.as<unsigned long long>(), keys_b.as<unsigned long long>(), d_val, d_val_out,
+                                                  nnz, 0, 32 + col_bits, st));
+    if (nnz) split_keys_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(keys_b.as<unsigned long long>(), nnz, d_row_out);
+    col_ptr_kernel<<<(cols + 1 + 255) / 256, 256, 0, st>>>(keys_b.as<unsigned long long>(), nnz, cols, d_colptr_out);
+    CUMF_CUDA_TRY(cudaGetLastError());
+    CUMF_CUDA_TRY(cudaStreamSynchronize(st));
+    return CUMF_OK;
+}
+
+namespace cumf {
+namespace {
 __global__ void init_uniform_kernel(float* __restrict__ p, size_t n, unsigned long long seed, float scale) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = scale * u01(mix64(seed ^ (unsigned long long)i * 0x2545F4914F6CDD1Dull));

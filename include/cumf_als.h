@@ -85,6 +85,15 @@ int cumf_load_coo_row_bin(const char* rowFile, int* row, long nnz);
 int cumf_load_coo_bin(const char* dataFile, const char* rowFile, const char* colFile, float* data,
                       int* row, int* col, long nnz);
 
+/* Sharded loading: one rank reads only ITS rows (columns) of the CLI's .bin files with seeks -- no process holds the whole
+ * matrix (hugewiki.cu:2332-2340 keeps one file set per GPU batch instead).  cumf_bin_shard_extent: first entry and number
+ * of entries of rows [row_begin, row_end); cumf_load_csr_shard_bin: rebased int64 pointers (row_end - row_begin + 1) and the
+ * index / value slices, ready for cumf_plan_create64 / (after upload) cumf_als_create_device.  0 on success, -1 otherwise. */
+int cumf_bin_shard_extent(const char* indptrFile, int rows, int row_begin, int row_end, long long* first, long long* count);
+int cumf_load_bin_slice(const char* file, int elem_size, long long first, long long count, void* dst);
+int cumf_load_csr_shard_bin(const char* dataFile, const char* indptrFile, const char* indicesFile, int rows,
+                            int row_begin, int row_end, long long* ptr_out, int* idx_out, float* val_out);
+
 /* Factor initialisation of the reference's front ends (they do it inline, before doALS):
  *   thetaTHost[k] = scale * rand() / RAND_MAX  (glibc rand),  XTHost[k] = 0
  * main.cpp:72-78 uses srand(0) and scale 0.2; the TensorFlow op als_tf.cc:118-125 never
@@ -298,6 +307,10 @@ int cumf_synth_download(const cumf_synth_shard* sh, int what, int* idx_out, floa
 int cumf_synth_download_test(const cumf_synth_shard* sh, int* row_out, int* col_out, float* val_out);
 int cumf_synth_solver(cumf_synth_shard* sh, cumf_als_solver** out, int f, float lambda, long nnz_test_total,
                       int solver, int path);
+/* CSR -> CSC on the device: one radix sort of (column, row) keys, rows ascending inside every column (what scipy's
+ * tocsc gives prepare_netflix_data.py:98-110).  Device pointers; int64 pointer arrays.  Synchronises `stream`.        */
+int cumf_csr_to_csc_device(int rows, int cols, long long nnz, const long long* d_rowptr, const int* d_col,
+                           const float* d_val, long long* d_colptr_out, int* d_row_out, float* d_val_out, void* stream);
 /* theta <- scale * uniform[0,1) (same values on every replica), X <- 0, on the device (main.cpp:72-78's shape) */
 int cumf_als_init_factors_device(cumf_als_solver* s, unsigned long long seed, float scale);
 int cumf_group_create_synth(cumf_als_group** out, long long m, int n, float avg_deg, unsigned long long seed,

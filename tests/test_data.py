@@ -87,3 +87,24 @@ def test_nnz_balanced_ranges(ratings):
         assert sum(loads) == r.nnz
         if parts > 1:
             assert max(loads) <= r.nnz / parts + np.diff(r.csr_indptr).max()
+
+
+def test_sharded_bin_loader_reads_exactly_the_slice(tmp_path):
+    """cumf_load_csr_shard_bin: rows [b, e) of the CLI's file set, read with seeks (no whole-matrix pass)."""
+    import cumf_als_b200 as c
+    from cumf_als_b200.api import load_csr_shard
+    r = synth_ratings(200, 300, 5000, 400, seed=21)
+    write_bin_dir(tmp_path, r)
+    for b, e in ((0, 200), (0, 0), (17, 93), (199, 200), (50, 50)):
+        ptr, idx, val = load_csr_shard(tmp_path / "R_train_csr.data.bin", tmp_path / "R_train_csr.indptr.bin",
+                                       tmp_path / "R_train_csr.indices.bin", r.m, b, e)
+        lo, hi = int(r.csr_indptr[b]), int(r.csr_indptr[e])
+        assert ptr.dtype == np.int64 and np.array_equal(ptr, r.csr_indptr[b:e + 1].astype(np.int64) - lo)
+        assert np.array_equal(idx, r.csr_indices[lo:hi]) and np.array_equal(val, r.csr_data[lo:hi])
+    # the CSC files are sliced the same way (columns instead of rows)
+    ptr, idx, val = load_csr_shard(tmp_path / "R_train_csc.data.bin", tmp_path / "R_train_csc.indptr.bin",
+                                   tmp_path / "R_train_csc.indices.bin", r.n, 100, 250)
+    lo, hi = int(r.csc_indptr[100]), int(r.csc_indptr[250])
+    assert np.array_equal(idx, r.csc_indices[lo:hi]) and np.array_equal(val, r.csc_data[lo:hi])
+    with pytest.raises(c.CumfError):
+        load_csr_shard(tmp_path / "R_train_csr.data.bin", tmp_path / "nope.bin", tmp_path / "R_train_csr.indices.bin", r.m, 0, 10)

@@ -66,3 +66,23 @@ def test_hugewiki_replica_device_shards_equal_generic_host_path(cuda, monkeypatc
     print(f"1/64 replica: m={m} n={n} nnz={nnz}; rmse device-shards {hist_g[-1]} generic {hist_s[-1]}")
     assert np.abs(hist_g[:, 0] - hist_s[:, 0]).max() < 1e-4 * hist_s[:, 0].max()
     assert np.abs(hist_g[:, 1] - hist_s[:, 1]).max() < 2e-3 * hist_s[:, 1].max()     # the generic path drops the tail block of test samples (als.cu:1006)
+
+
+def test_csr_to_csc_device_equals_scipy(cuda):
+    """cumf_csr_to_csc_device (radix sort of (column, row) keys) against scipy's tocsc on a ragged matrix with empty rows and
+    columns, and shard loading from .bin files straight into a device-resident solver (no whole-matrix host arrays)."""
+    import scipy.sparse as sp
+    from cumf_als_b200.api import csr_to_csc_device
+    from cumf_als_b200.data import synth_ratings
+    rng = np.random.default_rng(5)
+    m, n = 700, 1100
+    dense = (rng.random((m, n)) < 0.02) * rng.integers(1, 6, (m, n))
+    dense[13] = 0
+    dense[:, 77] = 0
+    csr = sp.csr_matrix(dense.astype(np.float32))
+    dev = lambda a: cuda.from_numpy(np.ascontiguousarray(a)).cuda()
+    colptr, rows, vals = csr_to_csc_device(m, n, dev(csr.indptr.astype(np.int64)), dev(csr.indices.astype(np.int32)), dev(csr.data))
+    csc = csr.tocsc()
+    csc.sort_indices()
+    assert np.array_equal(colptr.cpu().numpy(), csc.indptr.astype(np.int64))
+    assert np.array_equal(rows.cpu().numpy(), csc.indices) and np.array_equal(vals.cpu().numpy(), csc.data)
