@@ -110,13 +110,17 @@ template <int F, int MODE> struct Cfg {
     using G = Geo<F>;
     static constexpr bool kSym = (MODE == SYM);
     static_assert(!kSym || (G::RB == 1 && F <= 100), "the symmetric variant holds F + transposition temporaries in 152 registers");
-#ifdef CUMF_TC2_W6S2
+#if defined(CUMF_TC2_W6S2) || defined(CUMF_TC2_W6S3)
     static constexpr bool kSixWorkers = !kSym && G::RB == 1 && F <= 100;     // experiment: more gather-issuing warps, one system less
 #else
     static constexpr bool kSixWorkers = false;
 #endif
     static constexpr int kSysWG = G::RB;                                          // warpgroups per system
+#ifdef CUMF_TC2_W6S3
+    static constexpr int kWG = kSym ? 2 : (G::RB == 2 ? 2 : (F <= 100 ? 3 : 2));  // experiment: six workers AND three systems (640 threads, 128-register solvers)
+#else
     static constexpr int kWG = kSym ? 2 : (G::RB == 2 ? 2 : ((F <= 100 && !kSixWorkers) ? 3 : 2));  // solver warpgroups
+#endif
     static constexpr int kSys = kWG / kSysWG;                                     // systems in flight
     static constexpr int kFirstWorker = kSym ? 4 : 0;
     static constexpr int kWorkers = kSym ? 5 : (kSixWorkers ? 6 : 3);
@@ -128,10 +132,10 @@ template <int F, int MODE> struct Cfg {
     static constexpr int kSlots = kWorkers * kSlotsPerWorker;
     static constexpr int kFirstEpiWarp = kSym ? 12 : (kSixWorkers ? 8 : 4);
     static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;               // 640 / 512 / 384
-    static constexpr int kRegsLaunch = kSym ? 96 : (kThreads == 512 ? 128 : 168);
-    static constexpr int kRegsProd = kSym ? 80 : 56;
-    static constexpr int kRegsStage = 48;                                         // warpgroups of workers only (warps 4 .. kFirstEpiWarp)
-    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 512 ? 152 : 224);
+    static constexpr int kRegsLaunch = (kSym || kThreads == 640) ? 96 : (kThreads == 512 ? 128 : 168);
+    static constexpr int kRegsProd = kSym ? 80 : (kThreads == 640 ? 48 : 56);
+    static constexpr int kRegsStage = (!kSym && kThreads == 640) ? 40 : 48;       // warpgroups of workers only (warps 4 .. kFirstEpiWarp)
+    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 640 ? 128 : (kThreads == 512 ? 152 : 224));
     static constexpr int kRing = kSlots * G::STAGE_BYTES;
     static constexpr int kTrRows = F / 2;                                         // kSym: rows of G exchanged per pass (2 passes)
     static constexpr int kScratch = kSym ? kSys * (kTrRows + 1) * F : 4;
