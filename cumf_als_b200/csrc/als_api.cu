@@ -1738,8 +1738,12 @@ static float doALS_multi(const int* csrRowIndexHostPtr, const int* csrColIndexHo
         }
     };
     for_each_shard_parallel(gpus, run);
-    for (int k = 0; k < gpus; ++k)
-        if (rcs[k] != CUMF_OK) { set_last_error("shard " + std::to_string(k) + ": " + errs[k]); die("multi-GPU iteration"); }
+    {
+        std::string all;
+        for (int k = 0; k < gpus; ++k)
+            if (rcs[k] != CUMF_OK) all += "shard " + std::to_string(k) + " (status " + std::to_string(rcs[k]) + "): " + errs[k] + "; ";
+        if (!all.empty()) { set_last_error(all); die("multi-GPU iteration"); }
+    }
     const double t_down = wall_seconds();
     if (cumf_group_get_factors(g, thetaTHost, XTHost) != CUMF_OK) die("cumf_group_get_factors");
     const double t_free = wall_seconds();

@@ -199,6 +199,11 @@ def test_cli_runs_and_logs_scrape_like_the_reference(need_ref, tmp_path):
         print(name, out[name])
         assert out[name]["done"] and out[name]["F"] == f and out[name]["runtime"] is not None
         assert out[name]["als"] > 0 and out[name]["hermitian"] > 0       # both timing scripts find their lines
-    ref = out["reference"]["rmse"]
+    # the reference's CG is not reproducible run to run (atomicAdd order): on this 3000 x 5000 problem two runs
+    # of ref_main_cg differ by ~1e-4 in the printed RMSE (0.666177 / 0.666102 on two B200 boxes), so the bar is its own spread
+    p2 = subprocess.run([str(ROOT / "oracle" / "_ref" / "ref_main_cg"), *argv], capture_output=True, text=True, timeout=600, env=env, cwd=tmp_path)
+    ref, ref2 = out["reference"]["rmse"], _scrape(p2.stdout)["rmse"]
+    tol = max(TOL * ref, 3 * abs(ref - ref2))
+    print(f"reference twice: {ref} {ref2}; tolerance {tol:.2e}")
     for name in ("reference main.cpp on this library", "cumf_als_main"):
-        assert abs(out[name]["rmse"] - ref) < TOL * ref, (name, out[name]["rmse"], ref)
+        assert min(abs(out[name]["rmse"] - ref), abs(out[name]["rmse"] - ref2)) < tol, (name, out[name]["rmse"], ref, ref2)

@@ -47,10 +47,11 @@ for impl in ("1", "2"):
     print(f"[group impl={impl}] {n_gpus} shards: factors equal {np.array_equal(X_g, X_w) and np.array_equal(th_g, th_w)}; "
           f"rmse single {want[-1]} group {got[-1]}; last iteration {ms:.3f} ms", flush=True)
 
-os.environ["CUMF_DEBUG"] = "1"
 os.environ.pop("CUMF_QUIET", None)
 out = {}
-for gpus in ("1", str(n_gpus)):
+for gpus in ("1", str(n_gpus), str(n_gpus) + " debug"):
+    os.environ["CUMF_DEBUG"] = "1" if gpus.endswith("debug") else "0"
+    gpus = gpus.split()[0]
     os.environ["CUMF_GPUS"] = gpus
     th, X = theta0.copy(), X0.copy()
     print(f"---- doALS CUMF_GPUS={gpus}", flush=True)
