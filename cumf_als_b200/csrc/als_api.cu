@@ -42,9 +42,54 @@ constexpr size_t kCacheMinBytes = 256;     // (the 16-byte scalars are not worth
 
 extern "C" int cumf_release_cached_memory(void);
 
+thread_local DevArena* t_arena = nullptr;
+
+int DevBuf::alloc_own(size_t n) {
+    DevArena* keep = t_arena;
+    t_arena = nullptr;
+    const int rc = alloc(n);
+    t_arena = keep;
+    return rc;
+}
+
+namespace {
+int* g_pinned_ints = nullptr;
+int g_pinned_next = 0;
+constexpr int kPinnedInts = 1024;
+}  // namespace
+int* DevBuf::pinned_int() {
+    std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
+    unsigned int flags = 0;
+    if (g_pinned_ints && cudaHostGetFlags(&flags, g_pinned_ints) != cudaSuccess) {      // the context was reset under us
+        cudaGetLastError();
+        g_pinned_ints = nullptr;
+    }
+    if (!g_pinned_ints) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&g_pinned_ints), sizeof(int) * kPinnedInts, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            g_pinned_ints = nullptr;
+            return nullptr;
+        }
+        g_pinned_next = 0;
+    }
+    int* p = g_pinned_ints + (g_pinned_next++ % kPinnedInts);
+    *p = 0;
+    return p;
+}
+
 int DevBuf::alloc(size_t n) {
     release();
     if (n == 0) n = 16;
+    if (t_arena && t_arena->base) {
+        const size_t off = (t_arena->used + 1023) & ~(size_t)1023;
+        if (off + n <= t_arena->cap) {
+            p = t_arena->base + off;
+            bytes = n;
+            in_arena = true;
+            t_arena->used = off + n;
+            return CUMF_OK;
+        }
+    }
     if (n >= kCacheMinBytes) {
         std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
         int dev = 0;
@@ -77,17 +122,18 @@ int DevBuf::alloc(size_t n) {
     return CUMF_OK;
 }
 void DevBuf::release() {
-    if (p && !borrowed) cudaFree(p);
+    if (p && !borrowed && !in_arena) cudaFree(p);
     p = nullptr;
     bytes = 0;
     borrowed = false;
+    in_arena = false;
 }
 // the caller guarantees that no work touching the buffer is in flight
 void DevBuf::release_to_cache() {
     const char* v = getenv("CUMF_CACHE_MB");
     const size_t cap = (size_t)((v && *v) ? std::max(0L, atol(v)) : 0) << 20;
     std::unique_lock<std::mutex> lock(g_buf_cache_mutex);
-    if (p && !borrowed && bytes >= kCacheMinBytes && g_buf_cache_bytes + bytes <= cap) {
+    if (p && !borrowed && !in_arena && bytes >= kCacheMinBytes && g_buf_cache_bytes + bytes <= cap) {
         int dev = 0;
         cudaGetDevice(&dev);
         g_buf_cache.push_back(CachedBuf{p, bytes, dev});
@@ -804,6 +850,8 @@ struct cumf_als_solver {
     unsigned long long epoch = 0;
     std::vector<void*> ipc_opened;
     cudaStream_t run_stream = nullptr;              // a group gives every shard its own stream (two shards may share a device in tests)
+    DevArena arena;                                 // everything sized at build time lives in ONE device allocation
+    DevBuf arena_block;
     // timers
     double ms_x = 0, ms_theta = 0;
     long launches = 0, iterations = 0;
@@ -827,6 +875,8 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     if (s->ev_csr) cudaEventDestroy(s->ev_csr);
     if (s->ev_csc) cudaEventDestroy(s->ev_csc);
     if (s->ev_rmse) cudaEventDestroy(s->ev_rmse);
+    s->flags.release();
+    s->arena_block.release_to_cache();      // one cudaFree for everything that was carved out of the arena
     delete s;
     return CUMF_OK;
 }
@@ -879,8 +929,27 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
     s->xb = x_begin; s->xe = x_end; s->tb = t_begin; s->te = t_end;
     s->device = device; s->solver = solver; s->path = path;
     int rc = CUMF_OK;
-    auto fail = [&](int code) { cumf_als_destroy(s); return code; };
     const long long xn = src.x_ptr.back() - src.x_ptr.front(), tn = src.t_ptr.back() - src.t_ptr.front();
+    // One device allocation for everything sized here (DevArena, common.cuh): rating slices, plans, stage tables, the split
+    // tables of both sides, RMSE scratch.  What does not fit (split-row scratch of unusual shapes) falls back to cudaMalloc;
+    // the factor replicas and the barrier flags stay allocations of their own (CUDA IPC exports whole allocations).
+    struct ArenaScope {
+        DevArena* prev;
+        explicit ArenaScope(DevArena* a) : prev(t_arena) { t_arena = a; }
+        ~ArenaScope() { t_arena = prev; }
+    };
+    if (env_long("CUMF_ARENA", 1) != 0) {
+        const size_t owned = (size_t)(x_end - x_begin) + (size_t)(t_end - t_begin);
+        size_t est = (size_t)64 << 20;
+        if (!src.on_device) est += (size_t)xn * 12 + (size_t)tn * 8 + (size_t)src.test_cnt * 12;
+        est += owned * 64 + ((size_t)(xn + tn) / 32 + owned) * 8;                 // chunks, meta, stage tables
+        est += ((size_t)m + (size_t)n + 2) * 512 * (f > 127 ? 2 : 1);              // pre-split fp16 tables of both sides
+        est += est / 16;
+        if (s->arena_block.alloc(est) == CUMF_OK) { s->arena.base = s->arena_block.as<unsigned char>(); s->arena.cap = est; s->arena.used = 0; }
+        else cudaGetLastError();                                                  // no arena: every buffer gets its own allocation
+    }
+    ArenaScope arena_scope(&s->arena);
+    auto fail = [&](int code) { t_arena = arena_scope.prev; cumf_als_destroy(s); return code; };
     CUMF_REQUIRE(xn == 0 || (src.csr_col && src.csr_val), "CSR slice");
     CUMF_REQUIRE(tn == 0 || (src.csc_row && src.csc_val), "CSC slice");
     // Order: what the first X half-step needs goes to the copy engine first (factors, CSR), the work plans are built on
@@ -899,8 +968,8 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
     // behind the uploads); the theta-side plan is built while factors + CSR are in flight
     if ((rc = plan_create_core(&s->px, src.x_ptr.data(), src.x_ptr.data() + 1, m, x_begin, x_end, f, path, true, false, x_begin)) != CUMF_OK)
         return fail(rc);
-    if ((rc = s->theta.alloc(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
-    if ((rc = s->x.alloc(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->theta.alloc_own(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
+    if ((rc = s->x.alloc_own(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
     // initial factors (optional here; cumf_als_set_factors otherwise) go first: the X half-step needs them
     if ((thetaTHost && cudaMemcpyAsync(s->theta.p, thetaTHost, sizeof(float) * (size_t)n * f, cudaMemcpyHostToDevice, up) != cudaSuccess) ||
         (XTHost && cudaMemcpyAsync(s->x.p, XTHost, sizeof(float) * (size_t)m * f, cudaMemcpyHostToDevice, up) != cudaSuccess)) {
@@ -1348,7 +1417,7 @@ extern "C" int cumf_als_ipc_blob_bytes(void) { return 3 * (int)sizeof(cudaIpcMem
 
 static int solver_alloc_flags(cumf_als_solver* s) {
     if (s->flags.p) return CUMF_OK;
-    CUMF_TRY(s->flags.alloc(8 * sizeof(unsigned long long)));
+    CUMF_TRY(s->flags.alloc_own(8 * sizeof(unsigned long long)));
     CUMF_CUDA_TRY(cudaMemset(s->flags.p, 0, 8 * sizeof(unsigned long long)));
     return CUMF_OK;
 }

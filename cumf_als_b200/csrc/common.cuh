@@ -63,22 +63,42 @@ struct SplitRow {
     int nnz;        // ratings in the whole row (for the lambda*n_u term)
 };
 
+// One device allocation per solver for everything whose size is known when the solver is built: a bump allocator that
+// DevBuf::alloc draws from while `t_arena` points at it (thread-local: the shards of a multi-GPU group are built by one
+// host thread each).  cudaMalloc / cudaFree take process-wide driver locks and cudaFree synchronises the device; with 8
+// shards x ~30 buffers in one process that was 250 ms of a 420 ms doALS call (round 2, 8 x B200).
+struct DevArena {
+    unsigned char* base = nullptr;
+    size_t cap = 0, used = 0;
+};
+extern thread_local DevArena* t_arena;
+
 // Owning device allocation (move-only; the destructor frees, so early returns do not leak).
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    bool in_arena = false;     // carved out of the solver's arena: released with it, never on its own
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), borrowed(o.borrowed) { o.p = nullptr; o.bytes = 0; o.borrowed = false; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes), in_arena(o.in_arena), borrowed(o.borrowed) {
+        o.p = nullptr; o.bytes = 0; o.borrowed = false; o.in_arena = false;
+    }
     DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; bytes = o.bytes; borrowed = o.borrowed; o.p = nullptr; o.bytes = 0; o.borrowed = false; }
+        if (this != &o) {
+            release();
+            p = o.p; bytes = o.bytes; borrowed = o.borrowed; in_arena = o.in_arena;
+            o.p = nullptr; o.bytes = 0; o.borrowed = false; o.in_arena = false;
+        }
         return *this;
     }
     ~DevBuf() { release(); }
     bool borrowed = false;     // points into memory the caller owns (device-resident shards): never freed or cached here
     void borrow(void* ptr, size_t n) { release(); p = ptr; bytes = n; borrowed = true; }
+    // a few ints of pinned host memory from a process-wide pool (asynchronous device -> host verdicts); never freed singly
+    static int* pinned_int();
     int alloc(size_t n);
+    int alloc_own(size_t n);   // always its own cudaMalloc (buffers exported through CUDA IPC must be whole allocations)
     void release();
     void release_to_cache();   // opt-in (CUMF_CACHE_MB > 0): keep the allocation for the next DevBuf::alloc of a similar size
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }

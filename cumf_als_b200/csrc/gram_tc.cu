@@ -1096,7 +1096,7 @@ void tc_plan_set_factor_rows(TcWork* w, int rows) {
             w->split_tab.release();          // the launch path reports the failure
     }
     if (!w->max_idx.p) w->max_idx.alloc(sizeof(int));
-    if (!w->h_max_idx) cudaHostAlloc(reinterpret_cast<void**>(&w->h_max_idx), sizeof(int), cudaHostAllocDefault);
+    if (!w->h_max_idx) w->h_max_idx = DevBuf::pinned_int();
     if (!w->max_idx_ready) cudaEventCreateWithFlags(&w->max_idx_ready, cudaEventDisableTiming);
     if (w->impl == 2) {
         if (!w->absmax.p) w->absmax.alloc(4 * sizeof(unsigned));
@@ -1260,7 +1260,6 @@ void tc_plan_destroy(TcWork* w, bool cache) {
     rel(w->absmax);
     rel(w->scales);
     if (w->max_idx_ready) cudaEventDestroy(w->max_idx_ready);
-    if (w->h_max_idx) cudaFreeHost(w->h_max_idx);
     delete w;
 }
 
@@ -1310,7 +1309,8 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
             if (rows > 0) {
                 // trust the hint for this launch, validate it behind the launch without synchronising
                 if (!w->max_idx.p) CUMF_TRY(w->max_idx.alloc(sizeof(int)));
-                if (!w->h_max_idx) CUMF_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&w->h_max_idx), sizeof(int), cudaHostAllocDefault));
+                if (!w->h_max_idx) w->h_max_idx = DevBuf::pinned_int();
+                CUMF_REQUIRE(w->h_max_idx != nullptr, "no pinned host memory for the index validation");
                 if (!w->max_idx_ready) CUMF_CUDA_TRY(cudaEventCreateWithFlags(&w->max_idx_ready, cudaEventDisableTiming));
                 CUMF_CUDA_TRY(cudaMemsetAsync(w->max_idx.p, 0, sizeof(int), st));
                 max_index_kernel<<<592, 256, 0, st>>>(d_colidx, w->idx_span, w->max_idx.as<int>());
