@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstring>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -809,6 +810,7 @@ extern "C" int cumf_rmse(const float* d_val, const int* d_row, const int* d_col,
 // ---------------------------------------------------------------------------------
 // resident solver handle
 // ---------------------------------------------------------------------------------
+namespace cumf_multi { struct SameDeviceSync; }
 struct cumf_als_solver {
     int m = 0, n = 0, f = 0;
     long nnz = 0, nnz_test = 0;
@@ -848,6 +850,7 @@ struct cumf_als_solver {
     DevBuf flags;                                   // [8] unsigned long long, written by the peers
     unsigned long long* peer_flags[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [r] = rank r's flags (own: local)
     unsigned long long epoch = 0;
+    cumf_multi::SameDeviceSync* same_dev = nullptr; // set when the shards of a group share one device (test mode): event barrier
     std::vector<void*> ipc_opened;
     cudaStream_t run_stream = nullptr;              // a group gives every shard its own stream (two shards may share a device in tests)
     DevArena arena;                                 // everything sized at build time lives in ONE device allocation
@@ -859,9 +862,12 @@ struct cumf_als_solver {
 
 extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     if (!s) return CUMF_OK;
+    const bool debug = env_long("CUMF_DEBUG", 0) != 0;
+    double t[5] = {wall_seconds(), 0, 0, 0, 0};
     cudaSetDevice(s->device);
     if (s->up_stream) cudaStreamSynchronize(s->up_stream);
     cudaDeviceSynchronize();            // what cudaFree would do implicitly: nothing may still use the buffers kept for reuse
+    t[1] = wall_seconds();
     for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     s->ipc_opened.clear();
     if (s->run_stream) { cudaStreamDestroy(s->run_stream); s->run_stream = nullptr; }
@@ -869,6 +875,7 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     s->coo_row.release_to_cache(); s->test_row.release_to_cache(); s->test_col.release_to_cache(); s->test_val.release_to_cache();
     s->theta.release_to_cache(); s->x.release_to_cache(); s->sse.release(); s->partials.release();
     s->prep.release(); s->prep_partials.release();
+    t[2] = wall_seconds();
     plan_free(s->px, true);
     plan_free(s->pt, true);
     if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
@@ -876,7 +883,13 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     if (s->ev_csc) cudaEventDestroy(s->ev_csc);
     if (s->ev_rmse) cudaEventDestroy(s->ev_rmse);
     s->flags.release();
+    t[3] = wall_seconds();
+    const size_t arena_bytes = s->arena_block.bytes;
     s->arena_block.release_to_cache();      // one cudaFree for everything that was carved out of the arena
+    t[4] = wall_seconds();
+    if (debug)
+        printf("\trelease: device idle after %.4f s, rating/factor buffers %.4f s, plans/streams/events %.4f s, arena (%.0f MB) %.4f s\n",
+               t[1] - t[0], t[2] - t[1], t[3] - t[2], arena_bytes / 1048576.0, t[4] - t[3]);
     delete s;
     return CUMF_OK;
 }
@@ -1331,12 +1344,19 @@ extern "C" int cumf_als_iterate(cumf_als_solver* s, int iters, float* ms_out, vo
     for (auto& e : ev) CUMF_CUDA_TRY(cudaEventCreate(&e));
     CUMF_CUDA_TRY(cudaEventRecord(ev[0], st));
     int rc = CUMF_OK;
-    for (int it = 0; it < iters && rc == CUMF_OK; ++it) {
-        rc = cumf_als_update_x(s, stream);
-        if (rc == CUMF_OK) rc = cumf_als_peer_barrier(s, stream);        // no-op for a single rank
+    // a shard of a same-device group keeps meeting its peers on the host after a failure (see SameDeviceSync)
+    auto barrier = [&]() {
+        if (rc != CUMF_OK && !s->same_dev) return;
+        const std::string first = rc != CUMF_OK ? cumf_last_error() : "";
+        const int b = cumf_als_peer_barrier(s, stream);                  // no-op for a single rank
+        if (rc == CUMF_OK) rc = b; else set_last_error(first);
+    };
+    for (int it = 0; it < iters && (rc == CUMF_OK || s->same_dev); ++it) {
+        if (rc == CUMF_OK) rc = cumf_als_update_x(s, stream);
+        barrier();
         if (rc == CUMF_OK && cudaEventRecord(ev[2 * it + 1], st) != cudaSuccess) rc = CUMF_ECUDA;
         if (rc == CUMF_OK) rc = cumf_als_update_theta(s, stream);
-        if (rc == CUMF_OK) rc = cumf_als_peer_barrier(s, stream);
+        barrier();
         if (rc == CUMF_OK && cudaEventRecord(ev[2 * it + 2], st) != cudaSuccess) rc = CUMF_ECUDA;
     }
     if (rc == CUMF_OK && cudaStreamSynchronize(st) != cudaSuccess) {
@@ -1381,6 +1401,38 @@ extern "C" int cumf_als_timers(cumf_als_solver* s, double* out6, int reset) {
 //   * cumf_als_ipc_export / _import        : one process per GPU (torchrun, MPI), CUDA IPC handles exchanged by the caller
 // ---------------------------------------------------------------------------------
 namespace cumf_multi {
+struct HostBarrier {
+    std::atomic<int> count{0}, sense{0};
+    int n = 1;
+    void wait() {
+        const int s = sense.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+            count.store(0, std::memory_order_relaxed);
+            sense.store(s ^ 1, std::memory_order_release);
+        } else {
+            while (sense.load(std::memory_order_acquire) == s) std::this_thread::yield();
+        }
+    }
+};
+// Test mode CUMF_GROUP_SAME_DEVICE=1 (every shard on one GPU): a spinning barrier kernel is not safe there -- streams of one
+// device share its few hardware queues, so shard A's spinning barrier can sit in FRONT of the very kernel of shard B it waits
+// for (seen when one host thread ran half a step ahead of the other).  Such a group orders its half-steps with events instead:
+// each shard records, the host threads meet, each shard's stream waits for the others' records.  Every shard thread must call
+// the barrier the same number of times, failed or not.
+struct SameDeviceSync {
+    HostBarrier hb;
+    cudaEvent_t ev[8][2] = {};
+    int n = 0;
+    explicit SameDeviceSync(int shards) : n(shards) {
+        hb.n = shards;
+        for (int r = 0; r < shards; ++r)
+            for (int p = 0; p < 2; ++p) cudaEventCreateWithFlags(&ev[r][p], cudaEventDisableTiming);
+    }
+    ~SameDeviceSync() {
+        for (int r = 0; r < n; ++r)
+            for (int p = 0; p < 2; ++p) if (ev[r][p]) cudaEventDestroy(ev[r][p]);
+    }
+};
 struct FlagPtrs { unsigned long long* p[8]; };
 // thread r of rank `me`: publish my epoch in rank r's flag word [me], then wait until rank r has published its own in mine
 __global__ void peer_barrier_kernel(FlagPtrs flags, int me, int nranks, unsigned long long epoch) {
@@ -1403,6 +1455,16 @@ __global__ void peer_barrier_kernel(FlagPtrs flags, int me, int nranks, unsigned
 extern "C" int cumf_als_peer_barrier(cumf_als_solver* s, void* stream) {
     CUMF_REQUIRE(s, "null pointer");
     if (s->nranks <= 1) return CUMF_OK;
+    if (s->same_dev) {
+        ++s->epoch;
+        const int par = (int)(s->epoch & 1);
+        const cudaError_t e = cudaEventRecord(s->same_dev->ev[s->rank][par], (cudaStream_t)stream);
+        s->same_dev->hb.wait();                                   // every shard's record of this epoch is enqueued
+        CUMF_CUDA_TRY(e);
+        for (int r = 0; r < s->nranks; ++r)
+            if (r != s->rank) CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->same_dev->ev[r][par], 0));
+        return CUMF_OK;
+    }
     cumf_multi::FlagPtrs fp;
     for (int r = 0; r < 8; ++r) fp.p[r] = s->peer_flags[r];
     ++s->epoch;
@@ -1475,6 +1537,7 @@ struct cumf_als_group {
     int m = 0, n = 0, f = 0;
     long nnz = 0, nnz_test = 0;
     std::vector<std::string> errors;        // per shard (g_last_error is thread-local)
+    std::unique_ptr<cumf_multi::SameDeviceSync> same_dev;
 };
 
 // contiguous row ranges with (nearly) equal numbers of ratings: the deterministic replacement of hugewiki's dynamic batch
@@ -1513,22 +1576,20 @@ extern "C" int cumf_group_destroy(cumf_als_group* g) {
     return CUMF_OK;
 }
 
-// Test mode CUMF_GROUP_SAME_DEVICE=1 puts every shard on one GPU.  There a spinning barrier CTA of one shard holds a few
-// registers of an SM, and the persistent half-step kernel of another shard (one CTA per SM, the whole register file) could
-// wait for that SM for ever: the plans of such a group leave one SM per shard free.  One shard per device needs none of this.
-static void same_device_leave_sms(int device, int shards) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    setenv("CUMF_TC_CTAS", std::to_string(std::max(1, sms - shards)).c_str(), 1);
-}
-
 // rank / peer tables of a fully created group (same process: plain device pointers, peer access enabled by the caller)
 static void group_connect(cumf_als_group* g) {
     const int n = (int)g->s.size();
+    bool one_device = n > 1;
+    for (int k = 1; k < n; ++k) one_device = one_device && g->s[k]->device == g->s[0]->device;
+    if (one_device) {
+        cudaSetDevice(g->s[0]->device);
+        g->same_dev.reset(new cumf_multi::SameDeviceSync(n));
+    }
     for (int k = 0; k < n; ++k) {
         cumf_als_solver* s = g->s[k];
         s->rank = k;
         s->nranks = n;
+        s->same_dev = g->same_dev.get();
         s->peer_x.n = s->peer_theta.n = 0;
         for (int j = 0; j < n; ++j) {
             s->peer_flags[j] = g->s[j]->flags.as<unsigned long long>();
@@ -1566,7 +1627,6 @@ extern "C" int cumf_group_create_synth(cumf_als_group** out, long long m, int n,
     CUMF_CUDA_TRY(cudaGetDeviceCount(&have));
     const bool same_device = env_long("CUMF_GROUP_SAME_DEVICE", 0) != 0;
     CUMF_REQUIRE(first_device >= 0 && first_device + (same_device ? 1 : n_devices) <= have, "not that many devices on this node");
-    if (same_device) same_device_leave_sms(first_device, n_devices);
     cumf_als_group* g = new cumf_als_group();
     g->m = (int)m; g->n = n; g->f = f; g->nnz_test = test_per_shard * n_devices;
     g->s.assign(n_devices, nullptr);
@@ -1612,7 +1672,6 @@ static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr
     const bool same_device = env_long("CUMF_GROUP_SAME_DEVICE", 0) != 0;
     CUMF_REQUIRE(first_device >= 0 && first_device + (same_device ? 1 : n_devices) <= have, "not that many devices on this node");
     auto device_of = [=](int k) { return same_device ? first_device : first_device + k; };
-    if (same_device) same_device_leave_sms(first_device, n_devices);
     cumf_als_group* g = new cumf_als_group();
     g->m = m; g->n = n; g->f = f; g->nnz = nnz; g->nnz_test = nnz_test;
     g->s.assign(n_devices, nullptr);
@@ -1729,21 +1788,6 @@ extern "C" int cumf_group_sse(cumf_als_group* g, double* train_sse, double* test
 
 // doALS over CUMF_GPUS devices of this node (DEVICEID = the first): one host thread per device runs the iteration loop of its
 // shard; the devices meet in the barrier kernels, the host threads only to add up the RMSE sums.  Same stdout contract.
-namespace cumf_multi {
-struct HostBarrier {
-    std::atomic<int> count{0}, sense{0};
-    int n = 1;
-    void wait() {
-        const int s = sense.load(std::memory_order_acquire);
-        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
-            count.store(0, std::memory_order_relaxed);
-            sense.store(s ^ 1, std::memory_order_release);
-        } else {
-            while (sense.load(std::memory_order_acquire) == s) std::this_thread::yield();
-        }
-    }
-};
-}  // namespace cumf_multi
 
 static float doALS_multi(const int* csrRowIndexHostPtr, const int* csrColIndexHostPtr, const float* csrValHostPtr,
                          const int* cscRowIndexHostPtr, const int* cscColIndexHostPtr, const float* cscValHostPtr,
@@ -1776,22 +1820,27 @@ static float doALS_multi(const int* csrRowIndexHostPtr, const int* csrColIndexHo
         step(cumf_als_peer_barrier(s, st));
         for (int iter = 0; iter < ITERS; ++iter) {
             double t0 = wall_seconds();
-            if (rcs[k] == CUMF_OK) {
-                step(cumf_als_update_x(s, st)) && step(cumf_als_peer_barrier(s, st));
+            // the barriers are taken by every shard, failed or not: the others are waiting in theirs
+            auto barrier = [&]() { const int b = cumf_als_peer_barrier(s, st); if (rcs[k] == CUMF_OK) step(b); };
+            {
+                if (rcs[k] == CUMF_OK) step(cumf_als_update_x(s, st));
+                barrier();
                 if (debug && k == 0) {
                     cudaStreamSynchronize(s->run_stream);
                     printf("---------------------------ALS iteration %d, update X.----------------------------------\n", iter);
                     printf("update X run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, m, f);
                     t0 = wall_seconds();
                 }
-                step(cumf_als_update_theta(s, st)) && step(cumf_als_peer_barrier(s, st));
+                if (rcs[k] == CUMF_OK) step(cumf_als_update_theta(s, st));
+                barrier();
                 if (debug && k == 0) {
                     cudaStreamSynchronize(s->run_stream);
                     printf("---------------------------------- ALS iteration %d, update theta ----------------------------------\n", iter);
                     printf("update theta run %f seconds, gridSize: %d, blockSize %d.\n", wall_seconds() - t0, n, f);
                     printf("Calculate RMSE.\n");
                 }
-                step(cumf_als_sse(s, cooRowIndexHostPtr ? &tr[(iter & 1) * gpus + k] : nullptr, &te[(iter & 1) * gpus + k], st));
+                if (rcs[k] == CUMF_OK)
+                    step(cumf_als_sse(s, cooRowIndexHostPtr ? &tr[(iter & 1) * gpus + k] : nullptr, &te[(iter & 1) * gpus + k], st));
             }
             hb.wait();          // every shard's sums of this iteration are in (a failed shard still takes part)
             if (k == 0) {

@@ -468,7 +468,13 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                                     const uint64_t a_hi = d_g + (uint64_t)((2 * rb * ATOM_BYTES) >> 4);
                                     const uint64_t a_lo = d_g + (uint64_t)(((CR + 2 * rb) * ATOM_BYTES) >> 4);
                                     const uint32_t dt = d_tmem + (uint32_t)(rb * NB);
+#ifdef CUMF_TC2_EXP_NOMMA
+                                    if (g != 0 || st != 0u) continue;      // experiment: one MMA per tile (defines the accumulator)
+#endif
                                     umma_f16(dt, a_hi, b_hi, idesc, (g == 0 && st == 0u) ? 0u : 1u);    // hi^T hi
+#ifdef CUMF_TC2_EXP_NOMMA
+                                    continue;
+#endif
                                     if (!P.hi_only) {
                                         umma_f16(dt, a_hi, b_lo, idesc, 1u);                            // hi^T lo   (kSym: hi^T 2 lo)
                                         if (!kSym) umma_f16(dt, a_lo, b_hi, idesc, 1u);                 // lo^T hi
@@ -516,15 +522,27 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 }
                 __syncwarp();
                 if (elect_one()) {
+#if defined(CUMF_TC2_EXP_NOGATHER)
+                    mbar_arrive(&sm.full_tma[slot]);                 // experiment: nothing is gathered
+#elif defined(CUMF_TC2_EXP_GATHER1)
+                    mbar_arrive_expect_tx(&sm.full_tma[slot], groups * (uint32_t)(G::KG_BYTES / NC));
+#else
                     mbar_arrive_expect_tx(&sm.full_tma[slot], groups * (uint32_t)(P.hi_only ? G::KG_BYTES / 2 : G::KG_BYTES));
+#endif
 #pragma unroll
                     for (int g = 0; g < KGROUPS; ++g) {
+#ifdef CUMF_TC2_EXP_NOGATHER
+                        if (g >= 0) break;
+#endif
                         if ((uint32_t)g < groups) {
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const int4 ix = *reinterpret_cast<const int4*>(&sm.stage_idx[slot][g * KT + q * 4]);
 #pragma unroll
                                 for (int c = 0; c < NC; ++c)
+#ifdef CUMF_TC2_EXP_GATHER1
+                                    if (c == 0)
+#endif
                                     if (c < CR || !P.hi_only)
                                         tma_gather4_col(sbase + g * G::KG_BYTES + (q >> 1) * G::SBO + c * ATOM_BYTES + (q & 1) * 512, &factor_map,
                                                     (c < CR ? c * CHUNK : NB + (c - CR) * CHUNK), ix.x, ix.y, ix.z, ix.w, &sm.full_tma[slot]);
@@ -662,6 +680,9 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                     }
                     continue;
                 }
+#ifdef CUMF_TC2_EXP_NOSOLVE
+                if (P.lambda > -1.f) continue;                       // experiment: drain only
+#endif
                 bi *= sB;
                 // ---- CG (cg.cu:47-230): row i of A in registers (still scaled by 2^2c: the power-of-two unscale sA is applied
                 // to the finished dot product, which is exact), p broadcast from shared memory, packed FMAs ----

@@ -1,7 +1,7 @@
 """Multi-GPU row sharding inside the library (include/cumf_als.h, "multi-GPU row sharding"), exercised on ONE GPU: with
 CUMF_GROUP_SAME_DEVICE=1 every shard of a cumf_als_group lives on device 0 with its own stream, so the peer stores of the
-solver epilogues, the device-side flag barrier, the per-shard by-product train RMSE and doALS under CUMF_GPUS are all run
-for real; on n GPUs only the addresses differ.  Sharded == unsharded bit for bit (every row's arithmetic is independent of
+solver epilogues, the per-shard by-product train RMSE and doALS under CUMF_GPUS are all run for real; on n GPUs the addresses
+differ and the half-steps are ordered by the device-side flag barrier instead of events (als_api.cu, SameDeviceSync).  Sharded == unsharded bit for bit (every row's arithmetic is independent of
 the partition).  The two-process CUDA IPC path needs two GPUs: tools/multi_gpu_check.py.  Run with -m gpu."""
 import numpy as np
 import pytest
