@@ -3,6 +3,8 @@
 //   split_factor2_kernel   fp32 factor -> fp16 table [hi 2^c | lo 2^c] (the TMA gather source) + the unscale factors
 //   fill_stage_table2      one descriptor per stage (32 / 64 ratings) with everything the MMA issuer needs
 //   update()               the launches of one half-step
+#include <vector>
+#include <cstdio>
 #include "gram_tc2.cuh"
 
 namespace cumf {
@@ -29,7 +31,7 @@ __device__ __forceinline__ int scale_exp(unsigned absmax_bits, int top) {
 }
 __device__ __forceinline__ float pow2f(int c) { return __uint_as_float((unsigned)(c + 127) << 23); }
 
-// out[row] = [ hi 2^c (f, zero padded to nb) | lo 2^c (f, zero padded) | zero to tab_cols ], row == rows is the all-zero row.
+// out[row] = [ hi 2^c (f, zero padded to nb = Geo::LO_COL) | lo 2^c (f, zero padded) | zero to tab_cols ], row == rows is the all-zero row.
 //   hi = v 2^c with the low 13 mantissa bits cleared (exact in fp16: 11 significant bits, max |v| 2^c < 2^15),
 //   lo = fp16(v 2^c - hi)   (sym: 2 lo -- the long-row variant forms hi^T (2 lo) only and halves G + G^T)
 __global__ void __launch_bounds__(256) split_factor2_kernel(const float* __restrict__ fac, int rows, int f, int nb, int tab_cols, int sym,
@@ -143,7 +145,7 @@ int tc2_update(const Tc2Launch& a, cudaStream_t st, int* launches) {
         *launches += 1;
     }
     const size_t pieces = (size_t)(a.factor_rows + 1) * (v.tab_cols / 8);
-    tc2::split_factor2_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a.d_factor, a.factor_rows, a.f, (a.f + 1 + 15) / 16 * 16,
+    tc2::split_factor2_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(a.d_factor, a.factor_rows, a.f, v.lo_col,
                                                                                v.tab_cols, a.sym ? 1 : 0, a.d_absmax,
                                                                                reinterpret_cast<uint4*>(a.d_table), a.d_scales);
     CUMF_CUDA_TRY(cudaGetLastError());
@@ -162,10 +164,41 @@ int tc2_update(const Tc2Launch& a, cudaStream_t st, int* launches) {
     p.tt = a.d_tt; p.rhs = a.d_rhs; p.tt_row_base = a.tt_row_base;
     p.scales = a.d_scales; p.sse_terms = a.d_sse_terms; p.zero_row = a.factor_rows;
     p.hi_only = a.hi_only ? 1 : 0;
+    p.prof = nullptr;
+#ifdef CUMF_TC2_PROFILE
+    // experiment builds only (tools/build_variant.sh prof -DCUMF_TC2_PROFILE): per-role cycle counters, printed per launch
+    static unsigned long long* d_prof = nullptr;
+    const bool prof = getenv("CUMF_TC2_PROF") != nullptr;
+    if (prof) {
+        if (!d_prof) cudaMalloc(&d_prof, 1024 * tc2::PROF_WORDS * sizeof(unsigned long long));
+        cudaMemsetAsync(d_prof, 0, 1024 * tc2::PROF_WORDS * sizeof(unsigned long long), st);
+        p.prof = d_prof;
+    }
+#endif
     CUMF_CUDA_TRY(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem));
     v.fn<<<a.grid, v.threads, v.smem, st>>>(*reinterpret_cast<const CUtensorMap*>(a.tensor_map), p);
     CUMF_CUDA_TRY(cudaGetLastError());
     *launches += 1;
+#ifdef CUMF_TC2_PROFILE
+    if (prof) {
+        std::vector<unsigned long long> h((size_t)a.grid * tc2::PROF_WORDS);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        double s[tc2::PROF_WORDS] = {};
+        for (int c = 0; c < a.grid; ++c)
+            for (int k = 0; k < tc2::PROF_WORDS; ++k) s[k] += (double)h[(size_t)c * tc2::PROF_WORDS + k] / a.grid;
+        printf("[tc2 prof f=%d sym=%d grid=%d] per-CTA mean kilocycles\n", a.f, (int)a.sym, a.grid);
+        printf("  issuer : loop %.0f  wait landed %.0f  wait tmem-buffer %.0f  stages %.0f\n", s[3] / 1e3, s[1] / 1e3, s[2] / 1e3, s[4]);
+        for (int w = 0; w < 3; ++w)
+            printf("  worker%d: loop %.0f  wait slot-free %.0f  issue %.0f\n", w, s[7 + 3 * w] / 1e3, s[5 + 3 * w] / 1e3, s[6 + 3 * w] / 1e3);
+        for (int g = 0; g < 3; ++g)
+            printf("  solver%d: loop %.0f  wait accumulator %.0f  drain %.0f  solve+store %.0f  chunk head %.0f  systems %.0f\n", g,
+                   s[17 + 6 * g] / 1e3, s[14 + 6 * g] / 1e3, s[15 + 6 * g] / 1e3, s[16 + 6 * g] / 1e3, s[19 + 6 * g] / 1e3, s[18 + 6 * g]);
+        printf("  solver0 detail: before the loop %.0f  CG steps %.0f: publish+mat-vec %.0f  p.Ap sum+update %.0f  r.r sum %.0f  (cycles per step: %.0f / %.0f / %.0f)\n",
+               s[32] / 1e3, s[36], s[33] / 1e3, s[34] / 1e3, s[35] / 1e3, s[33] / s[36], s[34] / s[36], s[35] / s[36]);
+        fflush(stdout);
+    }
+#endif
     return CUMF_OK;
 }
 

@@ -53,6 +53,11 @@ constexpr int MAX_SYS = 3;                // systems in flight per CTA
 constexpr int MAX_BUF = 4;                // TMEM accumulator buffers
 constexpr int NBAR = 16;
 constexpr int MAX_ROWS = 64;              // ratings per stage, at most
+#ifndef CUMF_TC2_PROD_REGS
+#define CUMF_TC2_PROD_REGS 56             // setmaxnreg of warps 0-3 / 4-15 of the 512-thread shape (128 * (prod + 3 * epi) <= 65536)
+#define CUMF_TC2_EPI_REGS 152
+#endif
+constexpr int ROP_KG_BYTES = 512;         // rating operand of one k-group: 16 (N) x 16 (K) fp16, 8 x 16-byte core matrices
 constexpr int SYM = 1, WIDE = 0;
 
 // cg.cu:31,195: `rsnew < 1e-4` compares in double; for a float rsnew that is rsnew < nextafterf(1e-4f, +inf)
@@ -80,7 +85,17 @@ template <int F_> struct Geo {
     static constexpr int CR = (NB + CHUNK - 1) / CHUNK;            // chunks per region (hi / lo)
     static constexpr int NC = 2 * CR;                              // chunks per gathered row in shared memory
     static constexpr int ROW_BYTES = NC * 128;                     // one gathered row in shared memory
-    static constexpr int TAB_COLS = (2 * NB < CHUNK) ? CHUNK : 2 * NB;   // table row in HBM (halfs; at least one TMA box wide)
+    // Table row in HBM (halfs): [hi | lo], each region padded so that every 64-half box the gathers fetch is ONE aligned
+    // 128-byte line (2 NB <= 64: both regions share the one line of a 128-byte row).  Round 2 first packed the regions to
+    // 2 NB halfs (448-byte rows at f = 100): half of the boxes then straddled two lines, and the gather rate of the short-row
+    // launch -- requests, not bytes -- dropped by a third (-DCUMF_TC2_PACKED_TABLE rebuilds that layout for A/B runs).
+#ifdef CUMF_TC2_PACKED_TABLE
+    static constexpr int LO_COL = NB;
+    static constexpr int TAB_COLS = (2 * NB < CHUNK) ? CHUNK : 2 * NB;
+#else
+    static constexpr int LO_COL = (2 * NB <= CHUNK) ? NB : CR * CHUNK;
+    static constexpr int TAB_COLS = (2 * NB <= CHUNK) ? CHUNK : 2 * CR * CHUNK;
+#endif
     static constexpr int RB = (F + 1 > 128) ? 2 : 1;               // 128-lane row blocks of the accumulator
     static constexpr int TILE_COLS = RB * NB;
     static constexpr int NBUF = (TMEM_COLS / TILE_COLS >= 4) ? 4 : (TMEM_COLS / TILE_COLS >= 2 ? 2 : 1);
@@ -133,10 +148,22 @@ template <int F, int MODE> struct Cfg {
     static constexpr int kFirstEpiWarp = kSym ? 12 : (kSixWorkers ? 8 : 4);
     static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;               // 640 / 512 / 384
     static constexpr int kRegsLaunch = (kSym || kThreads == 640) ? 96 : (kThreads == 512 ? 128 : 168);
-    static constexpr int kRegsProd = kSym ? 80 : (kThreads == 640 ? 48 : 56);
+    static constexpr int kRegsProd = kSym ? 80 : (kThreads == 640 ? 48 : (kThreads == 512 ? CUMF_TC2_PROD_REGS : 56));
     static constexpr int kRegsStage = (!kSym && kThreads == 640) ? 40 : 48;       // warpgroups of workers only (warps 4 .. kFirstEpiWarp)
-    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 640 ? 128 : (kThreads == 512 ? 152 : 224));
+    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 640 ? 128 : (kThreads == 512 ? CUMF_TC2_EPI_REGS : 224));
     static constexpr int kRing = kSlots * G::STAGE_BYTES;
+    // -DCUMF_TC2_RATING_OPERAND (experiment, off): the ratings of a stage as a SECOND B operand (K-major, no swizzle, N = 16: 512
+    // bytes per k-group) that the stage's worker writes when it issues the gathers; two small MMAs per k-group add hi^T r and
+    // lo^T r into columns F, F + 1 of the tile, and nobody patches the landed rows.  Correct for every f (tests green), but
+    // slower: each extra MMA re-reads the 4 KB A tile from shared memory, and shared-memory bandwidth -- MMA operand fetches
+    // (7.5 KB per 128x112x16 MMA = 134 B per tensor-pipe cycle, above the 128 B/cycle the SM delivers) plus the TMA writes --
+    // is what bounds this kernel (profiles/README.md, round 2 "what bounds the short-row launch").
+#ifdef CUMF_TC2_RATING_OPERAND
+    static constexpr bool kRatingOperand = !kSym;
+#else
+    static constexpr bool kRatingOperand = false;      // measured: theta side 10.3-10.6 ms with the operand, 9.7 ms with the patch
+#endif
+    static constexpr int kRopBytes = kRatingOperand ? kSlots * G::KGROUPS * ROP_KG_BYTES : 16;
     static constexpr int kTrRows = F / 2;                                         // kSym: rows of G exchanged per pass (2 passes)
     static constexpr int kScratch = kSym ? kSys * (kTrRows + 1) * F : 4;
     static constexpr int kSpN = 128 * G::RB;
@@ -156,6 +183,7 @@ template <int F, int MODE> struct __align__(1024) Smem {
     using C = Cfg<F, MODE>;
     unsigned char ring[C::kRing];                 // kSlots stages, TMA destination == UMMA operand
     unsigned char ring_guard[2 * ATOM_BYTES];     // A-operand windows of the last stage may read one atom past the ring
+    __align__(128) unsigned char rop[C::kRopBytes];   // rating operands [slot][k-group][512] (kRatingOperand)
     float stage_vals[NBAR][MAX_ROWS];
     __align__(16) int stage_idx[NBAR][MAX_ROWS];
     float solver_scratch[C::kScratch];
@@ -196,7 +224,14 @@ struct Params {
     double* sse_terms;
     int zero_row;
     int hi_only;                  // reduced-precision mode: gather and multiply only the fp16 hi halves
+    unsigned long long* prof;     // -DCUMF_TC2_PROFILE builds: [cta][PROF_WORDS] cycle counters per role (tools/theta_probe.py)
 };
+constexpr int PROF_WORDS = 40;
+#ifdef CUMF_TC2_PROFILE
+#define CUMF_PROF(stmt) stmt
+#else
+#define CUMF_PROF(stmt)
+#endif
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -227,6 +262,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "=r"(done) : "r"(addr), "r"(parity), "r"(kWaitHintNs) : "memory");
         if (!done && ++polls > (1u << 18)) __trap();
     } while (!done);
+}
+// the issuer's wait for a landed stage: plain polling (no suspend hint) in -DCUMF_TC2_ISSUER_SPIN builds
+__device__ __forceinline__ void mbar_wait_hot(unsigned long long* bar, uint32_t parity) {
+#ifdef CUMF_TC2_ISSUER_SPIN
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done, polls = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && ++polls > (1u << 28)) __trap();
+    } while (!done);
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ void tma_gather4_col(void* smem_dst, const CUtensorMap* tmap, int col, int r0, int r1, int r2, int r3,
                                                 unsigned long long* bar) {
@@ -303,6 +355,19 @@ __host__ __device__ constexpr uint64_t desc_template(int lbo_bytes, int sbo_byte
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// A MN-major (the gathered rows), B K-major (the rating operand)
+__host__ __device__ constexpr uint32_t make_idesc_rating(int M, int N) {
+    return (1u << 4) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// K-major, no-swizzle descriptor (layout type 0; the layout of round 1's fp32-ring operands, gram_tc.cu smem_desc_template):
+// element (n, k) of a 16-deep k-group at (n / 8) * 256 + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2; leading offset = distance of
+// the two K core matrices (128), stride offset = distance of 8-row groups (256)
+__host__ __device__ constexpr uint64_t desc_template_rating() {
+    return ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr int rating_operand_offset(int n, int k) {
+    return (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+}
 
 // sum over the 4 * kSysWG warps of a system; every thread gets the same value, fixed order (deterministic)
 template <int NW>
@@ -324,21 +389,31 @@ __device__ __forceinline__ float sys_sum(float v, float* red, int warp_in_sys, i
 template <int KROWS> __device__ __forceinline__ int chunk_steps(const Chunk& ck) { return max(1, (ck.end - ck.begin + KROWS - 1) / KROWS); }
 
 // drain this thread's TMEM lane of one tile: columns [0, F) -> a[], column F -> b (raw accumulator values, scale 2^2c / 2^(c+cr))
-template <int F, bool kFirst>
+// kTwoB: column F + 1 holds the rest of b (rating operand: hi and lo halves of the ratings land in two columns)
+template <int F, bool kFirst, bool kTwoB>
 __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[Geo<F>::FA], float& b) {
     constexpr int NB = Geo<F>::NB;
+    static_assert(!kTwoB || (F % 16 != 15 && F + 1 < NB), "column F + 1 must lie in the 16-column block of column F");
     if constexpr (kFirst) {
-        // the first tile of a chunk lands straight in a[] (16-register blocks, no copies)
+        // the first tile of a chunk lands straight in a[] (16-register blocks, no copies); all loads are in flight before the
+        // one wait (-DCUMF_TC2_DRAIN_SERIAL: a wait per block, the round-2 form)
+        uint32_t v[NB / 16][16];
 #pragma unroll
         for (int cc = 0; cc < NB; cc += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + cc, v);
+            tmem_ld16(taddr + cc, v[cc / 16]);
+#ifdef CUMF_TC2_DRAIN_SERIAL
             tmem_ld_wait();
+#endif
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < NB; cc += 16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float x = __uint_as_float(v[j]);
+                const float x = __uint_as_float(v[cc / 16][j]);
                 if (cc + j < F) a[cc + j] = x;
                 else if (cc + j == F) b = x;
+                else if (kTwoB && cc + j == F + 1) b += x;
             }
         }
     } else {
@@ -354,9 +429,9 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float (&a)[Geo<F>::FA
             for (int j = 0; j < 8; ++j) {
                 const float x = __uint_as_float(v[j]), y = __uint_as_float(w[j]);
                 if (cc + j < F) a[cc + j] += x;
-                else if (cc + j == F) b += x;
+                else if (cc + j == F || (kTwoB && cc + j == F + 1)) b += x;
                 if (cc + 8 + j < F) a[cc + 8 + j] += y;
-                else if (cc + 8 + j == F) b += y;
+                else if (cc + 8 + j == F || (kTwoB && cc + 8 + j == F + 1)) b += y;
             }
         }
     }
@@ -392,6 +467,9 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
     }
     // padding entries of the CG direction vector stay zero for ever (the mat-vec reads FA >= F of them)
     for (int k = tid; k < C::kSys * 2 * C::kSpN; k += C::kThreads) (&sm.sp[0][0][0])[k] = 0.f;
+    // rating operands: only rows F % 16 and F % 16 + 1 are ever written, the other fourteen stay zero
+    if constexpr (C::kRatingOperand)
+        for (int k = tid; k < C::kRopBytes / 16; k += C::kThreads) reinterpret_cast<uint4*>(sm.rop)[k] = make_uint4(0u, 0u, 0u, 0u);
     if (warp == MMA_WARP) tmem_alloc(&sm.tmem_base, TMEM_COLS);
     fence_proxy_async();
     tc_fence_before();
@@ -407,6 +485,8 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             constexpr uint32_t idesc = make_idesc(128, NB);
             constexpr uint64_t tmpl = desc_template(ATOM_BYTES, G::SBO);
             const uint64_t dbase = tmpl | (uint64_t)((smem_u32(sm.ring) & 0x3FFFFu) >> 4);
+            constexpr uint32_t idesc_r = make_idesc_rating(128, 16);
+            const uint64_t rbase = desc_template_rating() | (uint64_t)((smem_u32(sm.rop) & 0x3FFFFu) >> 4);
             const uint32_t tmem_base = *reinterpret_cast<const volatile uint32_t*>(&sm.tmem_base);
             const uint32_t empty_bar0 = smem_u32(&sm.empty_op[0]);
             const uint32_t acc_full_bar0 = smem_u32(&sm.acc_full[0][0]);      // [sys][buf], 8 bytes each
@@ -415,6 +495,7 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             int S = s_begin;
             const int s_end = s_begin + total_stages;
             uint32_t info_next = P.stage_tab[S].info;
+            CUMF_PROF(long long pf_full = 0; long long pf_acc = 0; long long pf_n = 0; const long long pf_t0 = clock64();)
             while (S < s_end) {
                 const uint32_t info = info_next;
                 const uint32_t stages = (info >> TILE_STAGES_SHIFT) & 31u;
@@ -426,11 +507,15 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 const uint32_t d_tmem = tmem_base + buf * (uint32_t)G::TILE_COLS;
                 const uint32_t full_bar = acc_full_bar0 + (sys * MAX_BUF + buf) * 8u;
                 const uint32_t last_groups = ((info >> TILE_LAST_GROUPS_SHIFT) & 3u) + 1u;
+                CUMF_PROF(long long pf_a = clock64();)
                 mbar_wait(&sm.acc_empty[buf], (m >> FLAG_EMPTY_PARITY_SHIFT) & 1u);
+                CUMF_PROF(pf_acc += clock64() - pf_a;)
                 for (uint32_t st = 0; st < stages; ++st) {
                     const uint32_t groups = (st + 1u < stages) ? (uint32_t)KGROUPS : last_groups;
-                    mbar_wait(&sm.full_tma[slot], ph);          // the gathered rows have landed (TMA complete_tx)
-                    {
+                    CUMF_PROF(pf_a = clock64();)
+                    mbar_wait_hot(&sm.full_tma[slot], ph);      // the gathered rows have landed (TMA complete_tx)
+                    CUMF_PROF(pf_full += clock64() - pf_a; ++pf_n;)
+                    if constexpr (!C::kRatingOperand) {
                         // The rating rides along as feature F of gathered row kk: hi part in the hi region, lo part in the lo region.
                         // This warp drops them in itself -- the slot's worker is free to refill other slots, and a landed stage
                         // never waits for a worker that is busy issuing gathers (round 2: 40 % of the workers' time was spent
@@ -479,6 +564,13 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                                         umma_f16(dt, a_hi, b_lo, idesc, 1u);                            // hi^T lo   (kSym: hi^T 2 lo)
                                         if (!kSym) umma_f16(dt, a_lo, b_hi, idesc, 1u);                 // lo^T hi
                                     }
+                                    if constexpr (C::kRatingOperand) {
+                                        // columns F, F + 1 += hi^T (r_hi, r_lo) [+ lo^T (r_hi, r_lo)]; the other 14 rows of the
+                                        // operand are zero, so the neighbouring Gram columns get + 0
+                                        const uint64_t b_r = rbase + (uint64_t)((slot * (uint32_t)(KGROUPS * ROP_KG_BYTES) + g * ROP_KG_BYTES) >> 4);
+                                        umma_f16(dt + (uint32_t)(F / 16 * 16), a_hi, b_r, idesc_r, 1u);
+                                        if (!P.hi_only) umma_f16(dt + (uint32_t)(F / 16 * 16), a_lo, b_r, idesc_r, 1u);
+                                    }
                                 }
                             }
                         }
@@ -489,6 +581,8 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                     if (++slot == (uint32_t)C::kSlots) { slot = 0; ph ^= 1u; }
                 }
             }
+            CUMF_PROF(if (lane == 0 && P.prof) { unsigned long long* q = P.prof + (size_t)blockIdx.x * PROF_WORDS;
+                                                 q[1] = pf_full; q[2] = pf_acc; q[3] = clock64() - pf_t0; q[4] = pf_n; })
         }
     } else if (C::worker_of(warp) >= 0) {
         if (n_chunks > 0) {
@@ -500,6 +594,7 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             auto load_desc = [&](int t) -> StageDesc {
                 return (t < own) ? P.stage_tab[s_begin + sw + W * t] : StageDesc{0, 0u};
             };
+            const float rscale = __ldg(P.scales + 2);
             struct Rat { int idx[LPR]; float val[LPR]; };
             auto load_rat = [&](const StageDesc& d) -> Rat {
                 Rat r;
@@ -517,8 +612,22 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 unsigned char* sbase = sm.dstage(slot);
 #pragma unroll
                 for (int e = 0; e < LPR; ++e) {
-                    sm.stage_vals[slot][lane + 32 * e] = rat.val[e];
+                    if constexpr (!C::kRatingOperand) sm.stage_vals[slot][lane + 32 * e] = rat.val[e];
                     sm.stage_idx[slot][lane + 32 * e] = rat.idx[e];
+                }
+                if constexpr (C::kRatingOperand) {
+                    // r * 2^cr = hi + lo, both fp16 (hi: the top 11 bits, exact), as rows F % 16 and F % 16 + 1 of the operand
+                    unsigned char* rop = sm.rop + slot * (KGROUPS * ROP_KG_BYTES);
+#pragma unroll
+                    for (int e = 0; e < LPR; ++e) {
+                        const int kk = lane + 32 * e;
+                        const float r0 = rat.val[e] * rscale;
+                        const float h0 = __uint_as_float(__float_as_uint(r0) & 0xFFFFE000u);
+                        unsigned char* dst = rop + (kk >> 4) * ROP_KG_BYTES + rating_operand_offset(F % 16, kk & 15);
+                        *reinterpret_cast<__half*>(dst) = __float2half_rn(h0);
+                        *reinterpret_cast<__half*>(dst + 16) = __float2half_rn(r0 - h0);
+                    }
+                    fence_proxy_async();                        // generic-proxy writes ordered before the tensor core's reads
                 }
                 __syncwarp();
                 if (elect_one()) {
@@ -545,7 +654,7 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
 #endif
                                     if (c < CR || !P.hi_only)
                                         tma_gather4_col(sbase + g * G::KG_BYTES + (q >> 1) * G::SBO + c * ATOM_BYTES + (q & 1) * 512, &factor_map,
-                                                    (c < CR ? c * CHUNK : NB + (c - CR) * CHUNK), ix.x, ix.y, ix.z, ix.w, &sm.full_tma[slot]);
+                                                    (c < CR ? c * CHUNK : G::LO_COL + (c - CR) * CHUNK), ix.x, ix.y, ix.z, ix.w, &sm.full_tma[slot]);
                             }
                         }
                     }
@@ -562,20 +671,29 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             }
             // refills: own-stage t goes into slot sw + W (t mod R) once the MMAs of own-stage t - R (use number t / R - 1 of that
             // slot) have retired (tcgen05.commit -> empty_op); descriptor and ratings of the next refill are prefetched
+            // (descriptors two refills ahead, ratings one: the rating loads never wait for the descriptor they depend on)
+            CUMF_PROF(long long pf_wait = 0; long long pf_issue = 0; const long long pf_t0 = clock64();)
             StageDesc dcur = load_desc(R);
+            StageDesc dnext = load_desc(R + 1);
             Rat rat = load_rat(dcur);
             int slot_j = 0;
             uint32_t par = 0;
             for (int t = R; t < own; ++t) {
-                const StageDesc dnext = load_desc(t + 1);
+                const StageDesc dnext2 = load_desc(t + 2);
                 const Rat nrat = load_rat(dnext);
                 const int slot = sw + W * slot_j;
+                CUMF_PROF(const long long pf_a = clock64();)
                 mbar_wait(&sm.empty_op[slot], par);
+                CUMF_PROF(const long long pf_b = clock64();)
                 issue(slot, dcur.info >> 8, rat);
+                CUMF_PROF(pf_wait += pf_b - pf_a; pf_issue += clock64() - pf_b;)
                 dcur = dnext;
+                dnext = dnext2;
                 rat = nrat;
                 if (++slot_j == R) { slot_j = 0; par ^= 1u; }
             }
+            CUMF_PROF(if (lane == 0 && P.prof) { unsigned long long* q = P.prof + (size_t)blockIdx.x * PROF_WORDS + 5 + 3 * sw;
+                                                 q[0] = pf_wait; q[1] = pf_issue; q[2] = clock64() - pf_t0; })
         }
     } else if (warp >= C::kFirstEpiWarp) {
         reg_inc<C::kRegsEpi>();
@@ -597,9 +715,25 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
             uint32_t seen = 0;                             // bit b: phase parity of acc_full[sys][b] this system waits for next
             uint32_t spb = 0;
             double sse_acc = 0.0;
+            CUMF_PROF(long long pf_wait = 0; long long pf_drain = 0; long long pf_solve = 0; long long pf_n = 0; long long pf_head = 0;
+                      long long pf_pre = 0; long long pf_mv = 0; long long pf_red1 = 0; long long pf_red2 = 0; long long pf_iters = 0;
+                      const long long pf_t0 = clock64();)
+            // the head of the next chunk is loaded a chunk ahead: its latency hides behind this chunk's solve
+            int4 ck_raw = make_int4(0, 0, 0, -1);
+            int meta_raw = 0;
+            if (c_begin + sys < c_end) {
+                ck_raw = __ldg(reinterpret_cast<const int4*>(P.chunks + c_begin + sys));
+                meta_raw = __ldg(P.chunk_meta + c_begin + sys);
+            }
             for (int c = c_begin + sys; c < c_end; c += C::kSys) {
-                const Chunk ck = P.chunks[c];
-                const int tile0 = P.chunk_meta[c] >> 2;
+                CUMF_PROF(const long long pf_h = clock64();)
+                Chunk ck;
+                ck.row = ck_raw.x; ck.begin = ck_raw.y; ck.end = ck_raw.z; ck.slot = ck_raw.w;
+                const int tile0 = meta_raw >> 2;
+                if (c + C::kSys < c_end) {
+                    ck_raw = __ldg(reinterpret_cast<const int4*>(P.chunks + c + C::kSys));
+                    meta_raw = __ldg(P.chunk_meta + c + C::kSys);
+                }
                 const int tiles = (chunk_steps<KROWS>(ck) + G::SUB - 1) / G::SUB;
                 float a[FA];
                 float bi = 0.f;
@@ -610,18 +744,23 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 // bounds the length of the tensor core's own (truncating) chain.  The first tile lands straight in a[].
                 auto take_tile = [&](int tile, auto first) {
                     const uint32_t buf = (uint32_t)(tile0 + tile) & (uint32_t)(NBUF - 1);
+                    CUMF_PROF(const long long pf_a = clock64();)
                     mbar_wait(&sm.acc_full[sys][buf], (seen >> buf) & 1u);
+                    CUMF_PROF(const long long pf_b = clock64(); pf_wait += pf_b - pf_a;)
                     seen ^= 1u << buf;
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)G::TILE_COLS + (uint32_t)(rb * NB);
-                    drain_tile<F, decltype(first)::value>(taddr, a, bi);
+                    drain_tile<F, decltype(first)::value, C::kRatingOperand>(taddr, a, bi);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);
+                    CUMF_PROF(pf_drain += clock64() - pf_b;)
                 };
+                CUMF_PROF(pf_head += clock64() - pf_h;)
                 take_tile(0, std::true_type{});
 #pragma unroll 1
                 for (int tile = 1; tile < tiles; ++tile) take_tile(tile, std::false_type{});
+                CUMF_PROF(const long long pf_s = clock64(); ++pf_n;)
                 if constexpr (kSym) {
                     // [A | b] = (G + G^T) / 2 (the 1/2 lives in sA / sB): rows of G go through shared memory, kTrRows at a time.
                     // Thread i adds G[j][i] to its G[i][j]; where row j was symmetrised in an earlier pass (i < base) the buffer
@@ -687,6 +826,22 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 // ---- CG (cg.cu:47-230): row i of A in registers (still scaled by 2^2c: the power-of-two unscale sA is applied
                 // to the finished dot product, which is exact), p broadcast from shared memory, packed FMAs ----
                 auto spmv = [&](const float* sp, float self) -> float {
+#if defined(CUMF_TC2_LDS_BATCH)
+                    // experiment: CUMF_TC2_LDS_BATCH loads of p in flight before the first FMA needs one
+                    constexpr int NQ = FA / 4, B = CUMF_TC2_LDS_BATCH;
+                    float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+                    float4 q[B];
+#pragma unroll
+                    for (int k = 0; k < B; ++k) if (k < NQ) q[k] = *reinterpret_cast<const float4*>(sp + 4 * k);
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) {
+                        const float4 pv = q[k % B];
+                        if (k + B < NQ) q[k % B] = *reinterpret_cast<const float4*>(sp + 4 * (k + B));
+                        ffma2(y0, y1, a[4 * k], a[4 * k + 1], pv.x, pv.y);
+                        ffma2(y2, y3, a[4 * k + 2], a[4 * k + 3], pv.z, pv.w);
+                    }
+                    return fmaf(reg, self, sA * ((y0 + y1) + (y2 + y3)));
+#elif defined(CUMF_TC2_SPMV4)
                     float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
 #pragma unroll
                     for (int j = 0; j < FA; j += 4) {
@@ -695,6 +850,18 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                         ffma2(y2, y3, a[j + 2], a[j + 3], pv.z, pv.w);
                     }
                     return fmaf(reg, self, sA * ((y0 + y1) + (y2 + y3)));
+#else
+                    // four independent FFMA2 chains (eight partial sums): the chain, not the issue rate, sets the mat-vec time
+                    float y[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int j = 0; j < FA; j += 4) {
+                        const float4 pv = *reinterpret_cast<const float4*>(sp + j);
+                        const int h = (j >> 2) & 1;
+                        ffma2(y[4 * h], y[4 * h + 1], a[j], a[j + 1], pv.x, pv.y);
+                        ffma2(y[4 * h + 2], y[4 * h + 3], a[j + 2], a[j + 3], pv.z, pv.w);
+                    }
+                    return fmaf(reg, self, sA * (((y[0] + y[1]) + (y[2] + y[3])) + ((y[4] + y[5]) + (y[6] + y[7]))));
+#endif
                 };
                 const float own = active ? 1.f : 0.f;
                 float* sp = sm.sp[sys][spb]; spb ^= 1u;
@@ -703,16 +870,21 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 float r = active ? bi - spmv(sp, xi) : 0.f;        // r = b - A x
                 float p = r;
                 float rsold = sys_sum<NW>(own * r * r, sm.red[sys][0], warp_in_sys, lane, bar_id);
+                CUMF_PROF(pf_pre += clock64() - pf_s;)
                 for (int it = 0; (float)it < P.cg_iter; ++it) {
+                    CUMF_PROF(const long long pf_i0 = clock64(); ++pf_iters;)
                     sp = sm.sp[sys][spb]; spb ^= 1u;
                     if (active) sp[i] = p;
                     named_bar_sync(bar_id, NW * 32);
                     const float ap = active ? spmv(sp, p) : 0.f;
+                    CUMF_PROF(const long long pf_i1 = clock64() + (long long)(ap != ap); pf_mv += pf_i1 - pf_i0;)
                     const float pap = sys_sum<NW>(own * p * ap, sm.red[sys][1], warp_in_sys, lane, bar_id);
                     const float alpha = rsold / pap;               // cg.cu:128 (no guard)
                     xi = fmaf(alpha, p, xi);
                     r = fmaf(-alpha, ap, r);
+                    CUMF_PROF(const long long pf_i2 = clock64() + (long long)(r != r && alpha == 0.5f); pf_red1 += pf_i2 - pf_i1;)
                     const float rsnew = sys_sum<NW>(own * r * r, sm.red[sys][2], warp_in_sys, lane, bar_id);
+                    CUMF_PROF(pf_red2 += clock64() + (long long)(rsnew != rsnew) - pf_i2;)
                     if (rsnew < kCgErrorF) break;                  // cg.cu:195
                     const float beta = rsnew / rsold;
                     rsold = rsnew;
@@ -727,7 +899,12 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                     const float srow = sys_sum<NW>(own * xi * (bi + r + reg * xi), sm.red[sys][1], warp_in_sys, lane, bar_id);
                     if (ck.end > ck.begin) sse_acc += (double)srow;
                 }
+                CUMF_PROF(pf_solve += clock64() - pf_s;)
             }
+            CUMF_PROF(if (i == 0 && P.prof) { unsigned long long* q = P.prof + (size_t)blockIdx.x * PROF_WORDS + 14 + 6 * sys;
+                                              q[0] = pf_wait; q[1] = pf_drain; q[2] = pf_solve; q[3] = clock64() - pf_t0; q[4] = pf_n; q[5] = pf_head;
+                                              if (sys == 0) { unsigned long long* e = P.prof + (size_t)blockIdx.x * PROF_WORDS + 32;
+                                                              e[0] = pf_pre; e[1] = pf_mv; e[2] = pf_red1; e[3] = pf_red2; e[4] = pf_iters; } })
             if (P.sse_terms != nullptr && i == 0) P.sse_terms[blockIdx.x * MAX_SYS + sys] = sse_acc;
         }
     }
@@ -745,13 +922,13 @@ struct Variant {
     void (*fn)(const CUtensorMap, const Params);
     int threads;
     size_t smem;
-    int krows, sub, nbuf, nsys, tab_cols;
+    int krows, sub, nbuf, nsys, tab_cols, lo_col;
 };
 template <int F, int MODE> Variant make_variant() {
     using C = Cfg<F, MODE>;
     static_assert(SmemCheck<F, MODE>::ok, "shared memory");
     return Variant{als_fused2_kernel<F, MODE>, C::kThreads, sizeof(Smem<F, MODE>), Geo<F>::KROWS, Geo<F>::SUB, Geo<F>::NBUF, C::kSys,
-                   Geo<F>::TAB_COLS};
+                   Geo<F>::TAB_COLS, Geo<F>::LO_COL};
 }
 bool variant_a(int f, bool sym, Variant* out);   // f = 10 .. 50
 bool variant_b(int f, bool sym, Variant* out);   // f = 60 .. 100
