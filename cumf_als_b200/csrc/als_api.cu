@@ -1681,14 +1681,18 @@ static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr
     std::vector<int> rcs(n_devices, CUMF_OK);
     // one host thread per device: work plans, allocations and the (asynchronous) uploads of all shards proceed in parallel,
     // every GPU pulls its slice over its own PCIe link
+    const bool debug = env_long("CUMF_DEBUG", 0) != 0;
     for_each_shard_parallel(n_devices, [&](int k) {
+        const double t0 = wall_seconds();
         rcs[k] = als_create_impl(&g->s[k], csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
                                  cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
                                  cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, xr[k].first,
                                  xr[k].second, tr[k].first, tr[k].second, device_of(k), solver, path, wait_uploads,
                                  thetaTHost, XTHost);
+        const double t1 = wall_seconds();
         if (rcs[k] == CUMF_OK) rcs[k] = shard_runtime_setup(g->s[k], first_device, n_devices, same_device);
         if (rcs[k] != CUMF_OK) g->errors[k] = cumf_last_error();
+        if (debug) printf("\tshard %d: solver %.4f s, stream + peer access %.4f s\n", k, t1 - t0, wall_seconds() - t1);
     });
     for (int k = 0; k < n_devices; ++k)
         if (rcs[k] != CUMF_OK) {
