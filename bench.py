@@ -80,14 +80,48 @@ def make_inputs(w, scale: float, device: str):
 
 
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU DURING the timed region.  NVML from a thread of this process (a sample
+    every 2 ms: an 8-GPU run times 45 ms, less than nvidia-smi needs to start); `nvidia-smi -lms` only if pynvml is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    _nvml = None
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.tmp = gpu_index, None, None
+        self.handle, self.thread, self.stop, self.samples = None, None, None, []
+        try:
+            import pynvml
+            if ClockSampler._nvml is None:
+                pynvml.nvmlInit()
+                ClockSampler._nvml = pynvml
+            try:        # CUDA_VISIBLE_DEVICES may renumber: go by UUID
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.handle = None
+
+    def _poll(self):
+        nv = ClockSampler._nvml
+        while not self.stop.is_set():
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0,
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
+            except Exception:
+                pass
+            self.stop.wait(0.002)
 
     def __enter__(self):
+        if self.handle is not None:
+            import threading
+            self.stop = threading.Event()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
@@ -97,6 +131,9 @@ class ClockSampler:
         return self
 
     def __exit__(self, *exc):
+        if self.thread is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -106,6 +143,29 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.handle is not None:
+            nv = ClockSampler._nvml
+            if not self.samples:
+                return out
+            out["samples"] = len(self.samples)
+            out["sm_mhz"] = float(np.median([x[0] for x in self.samples]))
+            try:
+                out["sm_max_mhz"] = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            except Exception:
+                pass
+            out["power_w_max"] = max(x[1] for x in self.samples)
+            bits = 0
+            for x in self.samples:
+                bits |= int(x[2])
+            for nm, const in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                              ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+                mask = getattr(nv, const, None)
+                if mask is None:
+                    mask = getattr(nv, const.replace("ClocksEventReason", "ClocksThrottleReason"), 0)
+                if bits & int(mask):
+                    out["reasons"].append(nm)
+            out["source"] = "nvml"
+            return out
         if self.tmp is None:
             return out
         try:
@@ -125,6 +185,7 @@ class ClockSampler:
         for i, nm in enumerate(names):
             if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows if len(r) >= 9):
                 out["reasons"].append(nm)
+        out["source"] = "nvidia-smi"
         return out
 
 
