@@ -79,49 +79,65 @@ def make_inputs(w, scale: float, device: str):
     return r, theta0, X0
 
 
+_CLOCK_HELPER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+sel, path = sys.argv[1], sys.argv[2]
+try:
+    h = nv.nvmlDeviceGetHandleByUUID(sel) if sel.startswith("GPU-") else nv.nvmlDeviceGetHandleByIndex(int(sel))
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[3]))
+mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+with open(path, "w", buffering=1) as f:
+    while True:
+        try:
+            f.write("%.6f,%d,%d,%.1f,%d\n" % (time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx,
+                                              nv.nvmlDeviceGetPowerUsage(h) / 1000.0, nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
+        except Exception:
+            pass
+        time.sleep(0.004)
+"""
+
+
 class ClockSampler:
-    """SM clock, power and throttle reasons of one GPU DURING the timed region.  NVML from a thread of this process (a sample
-    every 2 ms: an 8-GPU run times 45 ms, less than nvidia-smi needs to start); `nvidia-smi -lms` only if pynvml is missing."""
+    """SM clock, power and throttle reasons of one GPU DURING the timed region.  A helper PROCESS polls NVML every few ms from
+    the moment the sampler is first constructed (process start-up and nvmlInit take longer than an 8-GPU timed region of
+    45 ms; polling from a thread of this process was measured to slow the launches down); `with` only brackets the region by
+    wall-clock time stamps, summary() keeps the samples inside it.  Falls back to `nvidia-smi -lms` without pynvml."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-    _nvml = None
+    _helpers = {}       # gpu index -> (Popen, path)
 
     def __init__(self, gpu_index: int):
         self.gpu, self.proc, self.tmp = gpu_index, None, None
-        self.handle, self.thread, self.stop, self.samples = None, None, None, []
-        try:
-            import pynvml
-            if ClockSampler._nvml is None:
-                pynvml.nvmlInit()
-                ClockSampler._nvml = pynvml
-            try:        # CUDA_VISIBLE_DEVICES may renumber: go by UUID
-                import torch
-                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
-                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
-            except Exception:
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-        except Exception:
-            self.handle = None
-
-    def _poll(self):
-        nv = ClockSampler._nvml
-        while not self.stop.is_set():
+        self.t0 = self.t1 = None
+        self.helper = ClockSampler._helpers.get(gpu_index)
+        if self.helper is None:
             try:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0,
-                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)))
+                import pynvml  # noqa: F401  (only: is it there?)
+                sel = str(gpu_index)
+                try:
+                    import torch
+                    sel = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                except Exception:
+                    pass
+                tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+                tmp.close()
+                proc = subprocess.Popen([sys.executable, "-c", _CLOCK_HELPER, sel, tmp.name, str(gpu_index)],
+                                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                import atexit
+                atexit.register(lambda: (proc.terminate(), os.path.exists(tmp.name) and os.unlink(tmp.name)))
+                self.helper = ClockSampler._helpers[gpu_index] = (proc, tmp.name)
             except Exception:
-                pass
-            self.stop.wait(0.002)
+                self.helper = None
 
     def __enter__(self):
-        if self.handle is not None:
-            import threading
-            self.stop = threading.Event()
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
+        self.t0 = time.time()
+        if self.helper is not None and self.helper[0].poll() is None:
             return self
+        self.helper = None                 # the helper died (no NVML): nvidia-smi
         try:
             self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
@@ -131,9 +147,7 @@ class ClockSampler:
         return self
 
     def __exit__(self, *exc):
-        if self.thread is not None:
-            self.stop.set()
-            self.thread.join(timeout=2)
+        self.t1 = time.time()
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -143,28 +157,27 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.handle is not None:
-            nv = ClockSampler._nvml
-            if not self.samples:
-                return out
-            out["samples"] = len(self.samples)
-            out["sm_mhz"] = float(np.median([x[0] for x in self.samples]))
+        if self.helper is not None:
             try:
-                out["sm_max_mhz"] = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                rows = [l.split(",") for l in open(self.helper[1]).read().strip().splitlines() if l.count(",") == 4]
+                rows = [(float(a), float(b), float(c), float(d), int(e)) for a, b, c, d, e in rows]
             except Exception:
-                pass
-            out["power_w_max"] = max(x[1] for x in self.samples)
+                rows = []
+            inside = [x for x in rows if self.t0 <= x[0] <= self.t1]
+            if not inside:
+                return out
+            out["samples"] = len(inside)
+            out["sm_mhz"] = float(np.median([x[1] for x in inside]))
+            out["sm_max_mhz"] = inside[0][2]
+            out["power_w_max"] = max(x[3] for x in inside)
             bits = 0
-            for x in self.samples:
-                bits |= int(x[2])
-            for nm, const in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
-                              ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
-                mask = getattr(nv, const, None)
-                if mask is None:
-                    mask = getattr(nv, const.replace("ClocksEventReason", "ClocksThrottleReason"), 0)
-                if bits & int(mask):
+            for x in inside:
+                bits |= x[4]
+            # nvml.h nvmlClocksEventReason*: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+            for nm, mask in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)):
+                if bits & mask:
                     out["reasons"].append(nm)
-            out["source"] = "nvml"
+            out["source"] = "nvml helper process, samples inside the timed region"
             return out
         if self.tmp is None:
             return out
@@ -359,6 +372,7 @@ def run_ours(args, w):
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    ClockSampler(local_rank)        # starts the NVML helper process now: it is polling long before the timed region
     host_pg = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -486,6 +500,7 @@ def run_ours_partial_gram(args, w):
 
     rank, local_rank, world = dist_env()
     torch.cuda.set_device(local_rank)
+    ClockSampler(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     r, theta0, X0 = make_inputs(w, args.scale, "cuda")
@@ -597,6 +612,7 @@ def run_reference(args, w):
     from oracle import oracle as O
     sys.path.insert(0, str(ROOT / "tests" / "golden"))
     torch.cuda.set_device(local_rank)
+    ClockSampler(local_rank)
     r, theta0, X0 = make_inputs(w, args.scale, "cuda")
     f, lam = w["f"], w["lam"]
     xb, tb = w["ref_batches"]
