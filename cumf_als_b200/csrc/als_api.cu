@@ -44,6 +44,9 @@ constexpr size_t kCacheMinBytes = 256;     // (the 16-byte scalars are not worth
 extern "C" int cumf_release_cached_memory(void);
 
 thread_local DevArena* t_arena = nullptr;
+// set by cumf_group_create* around the creation of its shards: their factor replicas and barrier flags are carved out of the
+// shard's arena too (a stand-alone solver keeps them as allocations of their own: cumf_als_ipc_export hands them to peers)
+static thread_local bool t_group_member = false;
 
 int DevBuf::alloc_own(size_t n) {
     DevArena* keep = t_arena;
@@ -951,9 +954,11 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
         explicit ArenaScope(DevArena* a) : prev(t_arena) { t_arena = a; }
         ~ArenaScope() { t_arena = prev; }
     };
+    const bool member = t_group_member;      // shard of a one-process group: nothing of it is ever exported over CUDA IPC
     if (env_long("CUMF_ARENA", 1) != 0) {
         const size_t owned = (size_t)(x_end - x_begin) + (size_t)(t_end - t_begin);
         size_t est = (size_t)64 << 20;
+        if (member) est += ((size_t)m + (size_t)n) * f * sizeof(float) + 4096;    // the factor replicas and the flags live here too
         if (!src.on_device) est += (size_t)xn * 12 + (size_t)tn * 8 + (size_t)src.test_cnt * 12;
         est += owned * 64 + ((size_t)(xn + tn) / 32 + owned) * 8;                 // chunks, meta, stage tables
         est += ((size_t)m + (size_t)n + 2) * 512 * (f > 127 ? 2 : 1);              // pre-split fp16 tables of both sides
@@ -963,6 +968,12 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
     }
     ArenaScope arena_scope(&s->arena);
     auto fail = [&](int code) { t_arena = arena_scope.prev; cumf_als_destroy(s); return code; };
+    if (member && s->arena.base) {
+        // barrier flags: zeroed now, synchronously, while nothing is queued on this device (a peer may write them as soon as
+        // ITS uploads are done)
+        if ((rc = s->flags.alloc(8 * sizeof(unsigned long long))) != CUMF_OK) return fail(rc);
+        if (cudaMemset(s->flags.p, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) { set_last_error("cumf_als_create: flags"); return fail(CUMF_ECUDA); }
+    }
     CUMF_REQUIRE(xn == 0 || (src.csr_col && src.csr_val), "CSR slice");
     CUMF_REQUIRE(tn == 0 || (src.csc_row && src.csc_val), "CSC slice");
     // Order: what the first X half-step needs goes to the copy engine first (factors, CSR), the work plans are built on
@@ -981,8 +992,8 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
     // behind the uploads); the theta-side plan is built while factors + CSR are in flight
     if ((rc = plan_create_core(&s->px, src.x_ptr.data(), src.x_ptr.data() + 1, m, x_begin, x_end, f, path, true, false, x_begin)) != CUMF_OK)
         return fail(rc);
-    if ((rc = s->theta.alloc_own(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
-    if ((rc = s->x.alloc_own(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
+    if ((rc = member ? s->theta.alloc(sizeof(float) * (size_t)n * f) : s->theta.alloc_own(sizeof(float) * (size_t)n * f)) != CUMF_OK) return fail(rc);
+    if ((rc = member ? s->x.alloc(sizeof(float) * (size_t)m * f) : s->x.alloc_own(sizeof(float) * (size_t)m * f)) != CUMF_OK) return fail(rc);
     // initial factors (optional here; cumf_als_set_factors otherwise) go first: the X half-step needs them
     if ((thetaTHost && cudaMemcpyAsync(s->theta.p, thetaTHost, sizeof(float) * (size_t)n * f, cudaMemcpyHostToDevice, up) != cudaSuccess) ||
         (XTHost && cudaMemcpyAsync(s->x.p, XTHost, sizeof(float) * (size_t)m * f, cudaMemcpyHostToDevice, up) != cudaSuccess)) {
@@ -1487,6 +1498,7 @@ static int solver_alloc_flags(cumf_als_solver* s) {
 extern "C" int cumf_als_ipc_export(cumf_als_solver* s, void* blob) {
     CUMF_REQUIRE(s && blob, "null pointer");
     CUMF_CUDA_TRY(cudaSetDevice(s->device));
+    CUMF_REQUIRE(!s->x.in_arena && !s->theta.in_arena, "a shard of a one-process group cannot be exported (its replicas are part of a larger allocation)");
     CUMF_TRY(solver_alloc_flags(s));
     cudaIpcMemHandle_t* h = reinterpret_cast<cudaIpcMemHandle_t*>(blob);
     CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[0], s->x.p));
@@ -1684,6 +1696,8 @@ static int group_create_impl(cumf_als_group** out, const int* csrRowIndexHostPtr
     const bool debug = env_long("CUMF_DEBUG", 0) != 0;
     for_each_shard_parallel(n_devices, [&](int k) {
         const double t0 = wall_seconds();
+        t_group_member = true;
+        struct Reset { ~Reset() { t_group_member = false; } } reset_member;
         rcs[k] = als_create_impl(&g->s[k], csrRowIndexHostPtr, csrColIndexHostPtr, csrValHostPtr, cscRowIndexHostPtr,
                                  cscColIndexHostPtr, cscValHostPtr, cooRowIndexHostPtr, cooRowIndexTestHostPtr,
                                  cooColIndexTestHostPtr, cooValHostTestPtr, m, n, f, nnz, nnz_test, lambda, xr[k].first,

@@ -561,8 +561,13 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                                     continue;
 #endif
                                     if (!P.hi_only) {
+#ifdef CUMF_TC2_MMA_ORDER_B
+                                        if (!kSym) umma_f16(dt, a_lo, b_hi, idesc, 1u);                 // experiment: consecutive MMAs share B
+                                        umma_f16(dt, a_hi, b_lo, idesc, 1u);
+#else
                                         umma_f16(dt, a_hi, b_lo, idesc, 1u);                            // hi^T lo   (kSym: hi^T 2 lo)
                                         if (!kSym) umma_f16(dt, a_lo, b_hi, idesc, 1u);                 // lo^T hi
+#endif
                                     }
                                     if constexpr (C::kRatingOperand) {
                                         // columns F, F + 1 += hi^T (r_hi, r_lo) [+ lo^T (r_hi, r_lo)]; the other 14 rows of the
