@@ -149,47 +149,62 @@ void DevBuf::release_to_cache() {
     lock.unlock();
     release();
 }
-// ---- pinned staging arena + copy kernel (see common.cuh) ---------------------------------------------
+// ---- pinned staging arenas + copy kernel (see common.cuh) --------------------------------------------
 namespace {
-unsigned char* g_stage = nullptr;
-size_t g_stage_bytes = 0, g_stage_used = 0;
-std::vector<unsigned char*> g_stage_retired;     // arenas outgrown while copies from them may still be queued
+constexpr int kMaxStageDevices = 16;
+struct Stage {
+    unsigned char* p = nullptr;
+    size_t bytes = 0, used = 0;
+    std::vector<unsigned char*> retired;     // arenas outgrown while copies from them may still be queued
+    std::mutex mutex;
+};
+Stage g_stages[kMaxStageDevices];            // one per device: the shards of a group build and upload their plans in parallel
+thread_local Stage* t_stage = nullptr;       // the arena of the StagingSection this thread holds
 __global__ void copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t words) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+Stage& stage_of_current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_stages[(dev >= 0 && dev < kMaxStageDevices) ? dev : 0];
 }
 }  // namespace
 
 // A cudaDeviceReset by the caller (the reference CLI ends with one, main.cpp:168; die() below) invalidates the arena:
 // probe it before reuse and drop a dangling pointer instead of writing through it.
-static bool stage_alive() {
-    if (!g_stage) return false;
+static bool stage_alive(Stage& g) {
+    if (!g.p) return false;
     unsigned int flags = 0;
-    if (cudaHostGetFlags(&flags, g_stage) == cudaSuccess) return true;
+    if (cudaHostGetFlags(&flags, g.p) == cudaSuccess) return true;
     cudaGetLastError();
-    g_stage = nullptr;
-    g_stage_bytes = g_stage_used = 0;
-    g_stage_retired.clear();
+    g.p = nullptr;
+    g.bytes = g.used = 0;
+    g.retired.clear();
     return false;
 }
 
-void staging_reset() {
-    g_stage_used = 0;
-    if (!stage_alive()) return;
-    for (unsigned char* p : g_stage_retired) cudaFreeHost(p);
-    g_stage_retired.clear();
+static void stage_reset(Stage& g) {
+    g.used = 0;
+    if (!stage_alive(g)) return;
+    for (unsigned char* p : g.retired) cudaFreeHost(p);
+    g.retired.clear();
 }
+void staging_reset() { stage_reset(t_stage ? *t_stage : stage_of_current_device()); }
 
-static std::mutex g_stage_mutex;
 StagingSection::StagingSection() {
-    g_stage_mutex.lock();
+    Stage& g = stage_of_current_device();
+    g.mutex.lock();
+    t_stage = &g;
     held = true;
-    staging_reset();
+    stage_reset(g);
 }
 int StagingSection::finish(cudaStream_t st) {
     if (!held) return CUMF_OK;
     const cudaError_t e = cudaStreamSynchronize(st);
     held = false;
-    g_stage_mutex.unlock();
+    Stage* g = t_stage;
+    t_stage = nullptr;
+    if (g) g->mutex.unlock();
     if (e != cudaSuccess) {
         set_last_error(std::string("plan upload: ") + cudaGetErrorString(e));
         return CUMF_ECUDA;
@@ -199,26 +214,32 @@ int StagingSection::finish(cudaStream_t st) {
 StagingSection::~StagingSection() {
     if (held) {
         cudaStreamSynchronize(last);
-        g_stage_mutex.unlock();
+        Stage* g = t_stage;
+        t_stage = nullptr;
+        if (g) g->mutex.unlock();
     }
 }
 
 static void staging_release() {
-    if (stage_alive()) {
-        for (unsigned char* p : g_stage_retired) cudaFreeHost(p);
-        cudaFreeHost(g_stage);
+    for (Stage& g : g_stages) {
+        std::lock_guard<std::mutex> lock(g.mutex);
+        if (stage_alive(g)) {
+            for (unsigned char* p : g.retired) cudaFreeHost(p);
+            cudaFreeHost(g.p);
+        }
+        g.retired.clear();
+        g.p = nullptr;
+        g.bytes = g.used = 0;
     }
-    g_stage_retired.clear();
-    g_stage = nullptr;
-    g_stage_bytes = g_stage_used = 0;
 }
 
 int upload_via_kernel(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
     if (bytes == 0) return CUMF_OK;
     CUMF_REQUIRE((bytes & 3u) == 0, "upload_via_kernel: size must be a multiple of 4");
+    Stage& g = t_stage ? *t_stage : stage_of_current_device();
     const size_t need = (bytes + 255) & ~(size_t)255;
-    if (!stage_alive() || g_stage_used + need > g_stage_bytes) {
-        const size_t grow = std::max<size_t>(std::max<size_t>(g_stage_bytes * 2, (size_t)16 << 20), g_stage_used + need);
+    if (!stage_alive(g) || g.used + need > g.bytes) {
+        const size_t grow = std::max<size_t>(std::max<size_t>(g.bytes * 2, (size_t)16 << 20), g.used + need);
         unsigned char* fresh = nullptr;
         if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), grow, cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
@@ -226,13 +247,13 @@ int upload_via_kernel(void* d_dst, const void* h_src, size_t bytes, cudaStream_t
             CUMF_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
             return CUMF_OK;
         }
-        if (g_stage) g_stage_retired.push_back(g_stage);     // queued copies may still read it: freed at the next reset
-        g_stage = fresh;
-        g_stage_bytes = grow;
-        g_stage_used = 0;
+        if (g.p) g.retired.push_back(g.p);     // queued copies may still read it: freed at the next reset
+        g.p = fresh;
+        g.bytes = grow;
+        g.used = 0;
     }
-    unsigned char* slot = g_stage + g_stage_used;
-    g_stage_used += need;
+    unsigned char* slot = g.p + g.used;
+    g.used += need;
     memcpy(slot, h_src, bytes);
     const size_t words = bytes / 4;
     const int blocks = (int)std::min<size_t>((words + 255) / 256, 592);

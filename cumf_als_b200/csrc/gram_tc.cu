@@ -1221,7 +1221,7 @@ int tc_plan_create(TcWork** out, const std::vector<Chunk>& chunks, const Chunk* 
     if (rc == CUMF_OK) rc = w->stage_tab.alloc(sizeof(StageDesc) * (size_t)std::max(1, stage_base[n]));
     if (rc == CUMF_OK) rc = d_base.alloc(sizeof(int) * (n + 1));
     if (rc == CUMF_OK) rc = w->chunk_meta.alloc(sizeof(int) * std::max(n, 1));
-    StagingSection sec;      // the process-wide pinned arena, until the fill kernel below has read it
+    StagingSection sec;      // the device's pinned staging arena, until the fill kernel below has read it
     if (rc == CUMF_OK &&
         (upload_via_kernel(w->cta_ptr.p, ptr.data(), sizeof(int) * (grid + 1), 0) != CUMF_OK ||
          upload_via_kernel(w->chunk_meta.p, chunk_meta.data(), sizeof(int) * std::max(n, 1), 0) != CUMF_OK ||

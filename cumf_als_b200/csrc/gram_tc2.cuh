@@ -54,8 +54,11 @@ constexpr int MAX_BUF = 4;                // TMEM accumulator buffers
 constexpr int NBAR = 16;
 constexpr int MAX_ROWS = 64;              // ratings per stage, at most
 #ifndef CUMF_TC2_PROD_REGS
-#define CUMF_TC2_PROD_REGS 56             // setmaxnreg of warps 0-3 / 4-15 of the 512-thread shape (128 * (prod + 3 * epi) <= 65536)
-#define CUMF_TC2_EPI_REGS 152
+// setmaxnreg of warps 0-3 / 4-15 of the 512-thread shape at f > 90 (128 * (prod + 3 * epi) <= 65536; smaller f: 56 / 152).  56 / 152 until round 2's last A/B:
+// with 160 registers the solver keeps six or seven LDS.128 of the mat-vec in flight instead of five (theta side 9.2 -> 8.8 ms),
+// and the stage workers / the issuer fit 32 without spills
+#define CUMF_TC2_PROD_REGS 32
+#define CUMF_TC2_EPI_REGS 160
 #endif
 constexpr int ROP_KG_BYTES = 512;         // rating operand of one k-group: 16 (N) x 16 (K) fp16, 8 x 16-byte core matrices
 constexpr int SYM = 1, WIDE = 0;
@@ -148,9 +151,9 @@ template <int F, int MODE> struct Cfg {
     static constexpr int kFirstEpiWarp = kSym ? 12 : (kSixWorkers ? 8 : 4);
     static constexpr int kThreads = (kFirstEpiWarp + 4 * kWG) * 32;               // 640 / 512 / 384
     static constexpr int kRegsLaunch = (kSym || kThreads == 640) ? 96 : (kThreads == 512 ? 128 : 168);
-    static constexpr int kRegsProd = kSym ? 80 : (kThreads == 640 ? 48 : (kThreads == 512 ? CUMF_TC2_PROD_REGS : 56));
+    static constexpr int kRegsProd = kSym ? 80 : (kThreads == 640 ? 48 : (kThreads == 512 ? (F > 90 ? CUMF_TC2_PROD_REGS : 56) : 56));
     static constexpr int kRegsStage = (!kSym && kThreads == 640) ? 40 : 48;       // warpgroups of workers only (warps 4 .. kFirstEpiWarp)
-    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 640 ? 128 : (kThreads == 512 ? CUMF_TC2_EPI_REGS : 224));
+    static constexpr int kRegsEpi = kSym ? 152 : (kThreads == 640 ? 128 : (kThreads == 512 ? (F > 90 ? CUMF_TC2_EPI_REGS : 152) : 224));
     static constexpr int kRing = kSlots * G::STAGE_BYTES;
     // -DCUMF_TC2_RATING_OPERAND (experiment, off): the ratings of a stage as a SECOND B operand (K-major, no swizzle, N = 16: 512
     // bytes per k-group) that the stage's worker writes when it issues the gathers; two small MMAs per k-group add hi^T r and
