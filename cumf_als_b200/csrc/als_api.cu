@@ -642,7 +642,8 @@ static int solve_batch(float* tt, float* x, float* rhs, int batch, int f, int so
 }
 
 static int update_factor_impl(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
-                              float* d_out, float lambda, int solver, float cgIter, void* stream, const PeerOut* peers);
+                              float* d_out, float lambda, int solver, float cgIter, void* stream, const PeerOut* peers,
+                              const SplitOut* split_out = nullptr, bool table_current = false, bool* wrote_split = nullptr);
 
 extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
                                   float* d_out, float lambda, int solver, float cgIter, void* stream) {
@@ -651,10 +652,15 @@ extern "C" int cumf_update_factor(cumf_plan* p, const int* d_colidx, const float
 
 // peers (optional): replicas of d_out on other GPUs that receive every updated row (the row-block exchange of the sharded
 // half-step, done by the solver epilogues themselves)
+// split_out (optional): f = 100 gather tables that receive the split form of every row this half-step solves; *wrote_split says
+// whether every row went there (fused generic kernel + CG tail); table_current: this plan's own gather table is up to date
 static int update_factor_impl(cumf_plan* p, const int* d_colidx, const float* d_val, const float* d_factor,
-                              float* d_out, float lambda, int solver, float cgIter, void* stream, const PeerOut* peers) {
+                              float* d_out, float lambda, int solver, float cgIter, void* stream, const PeerOut* peers,
+                              const SplitOut* split_out, bool table_current, bool* wrote_split) {
     CUMF_REQUIRE(p && d_colidx && d_val && d_factor && d_out, "null pointer");
     if (peers && peers->n == 0) peers = nullptr;
+    if (split_out && split_out->n == 0) split_out = nullptr;
+    if (wrote_split) *wrote_split = false;
     CUMF_REQUIRE(solver == CUMF_SOLVER_CG || solver == CUMF_SOLVER_LU, "unknown solver");
     cudaStream_t st = (cudaStream_t)stream;
     const int f = p->f;
@@ -678,19 +684,21 @@ static int update_factor_impl(cumf_plan* p, const int* d_colidx, const float* d_
         }
         cudaEvent_t e0, e1;
         plan_time_begin(p, st, &e0, &e1);
-        const TcExtra extra = tc_extra_from(peers);
+        if (split_out && !(f == 100 && tc_plan_impl(p->tc) == 2)) split_out = nullptr;     // only the generic kernel writes split rows
+        const TcExtra extra = tc_extra_from(peers, split_out, table_current);
         CUMF_TRY(tc_update_factor(p->tc, d_chunks, (int)p->chunks.size(), d_colidx, d_val, d_factor, d_out,
                                   f, lambda, cgIter, p->scratchA.as<float>(), p->scratchB.as<float>(), st, &launches, terms,
-                                  peers ? &extra : nullptr));
+                                  (peers || split_out || table_current) ? &extra : nullptr));
         plan_time_end(p, st, e0, e1);
         // rows that were split across CTAs: reduce their partials into a compact batch, solve it
         if (ns > 0) {
             CUMF_TRY(launch_split_reduce(d_splits, 0, ns, f, lambda, /*compact=*/1, 0, p->tt.as<float>(),
                                          p->rhs.as<float>(), p->scratchA.as<float>(), p->scratchB.as<float>(), st));
             CUMF_TRY(launch_cg(p->tt.as<float>(), d_out, p->rhs.as<float>(), ns, f, cgIter, d_splits, st, lambda,
-                               terms ? terms + tc_sse_terms_per_cta() * tc_plan_grid(p->tc) : nullptr, peers));
+                               terms ? terms + tc_sse_terms_per_cta() * tc_plan_grid(p->tc) : nullptr, peers, 0, split_out));
             launches += 2;
         }
+        if (wrote_split) *wrote_split = (split_out != nullptr);
         p->sse_terms_valid = (terms != nullptr);
         p->last_launches = launches;
         return CUMF_OK;
@@ -874,6 +882,9 @@ struct cumf_als_solver {
     DevBuf flags;                                   // [8] unsigned long long, written by the peers
     unsigned long long* peer_flags[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [r] = rank r's flags (own: local)
     unsigned long long epoch = 0;
+    SplitOut theta_split_out{};                     // X-side gather tables (own + peers') that theta half-steps keep up to date
+    bool theta_table_current = false;               // ... and whether the last theta half-step did (any other write to theta resets it)
+    bool theta_ptr_exposed = false;                 // cumf_als_theta_ptr was handed out: never trust the table
     cumf_multi::SameDeviceSync* same_dev = nullptr; // set when the shards of a group share one device (test mode): event barrier
     std::vector<void*> ipc_opened;
     cudaStream_t run_stream = nullptr;              // a group gives every shard its own stream (two shards may share a device in tests)
@@ -883,6 +894,12 @@ struct cumf_als_solver {
     double ms_x = 0, ms_theta = 0;
     long launches = 0, iterations = 0;
 };
+
+// CUMF_FUSED_SPLIT=0: theta half-steps do not write split rows, every X half-step re-splits all of theta (round 1 behaviour)
+static bool fused_split_enabled() { return env_long("CUMF_FUSED_SPLIT", 1) != 0; }
+static unsigned short* own_gather_table(cumf_als_solver* s) {
+    return (s && s->px && s->px->tc && fused_split_enabled()) ? tc_plan_split_table_f100(s->px->tc) : nullptr;
+}
 
 extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     if (!s) return CUMF_OK;
@@ -1079,6 +1096,7 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
         set_last_error(std::string("cumf_als_create: upload failed: ") + cudaGetErrorString(cudaGetLastError()));
         return fail(CUMF_ECUDA);
     }
+    if (unsigned short* tab = own_gather_table(s)) { s->theta_split_out.p[0] = tab; s->theta_split_out.n = 1; }
     *out = s;
     return CUMF_OK;
 }
@@ -1211,6 +1229,7 @@ extern "C" int cumf_als_set_factors(cumf_als_solver* s, const float* thetaTHost,
     CUMF_CUDA_TRY(cudaMemcpy(s->theta.p, thetaTHost, sizeof(float) * (size_t)s->n * s->f, cudaMemcpyHostToDevice));
     CUMF_CUDA_TRY(cudaMemcpy(s->x.p, XTHost, sizeof(float) * (size_t)s->m * s->f, cudaMemcpyHostToDevice));
     s->theta_fresh = false;
+    s->theta_table_current = false;
     return CUMF_OK;
 }
 extern "C" int cumf_als_get_factors(cumf_als_solver* s, float* thetaTHost, float* XTHost) {
@@ -1227,7 +1246,21 @@ extern "C" int cumf_als_shape(const cumf_als_solver* s, int* m, int* n, int* f) 
     if (f) *f = s->f;
     return CUMF_OK;
 }
-extern "C" float* cumf_als_theta_ptr(cumf_als_solver* s) { return s ? s->theta.as<float>() : nullptr; }
+// (a caller that holds the raw pointer may rewrite theta behind the solver's back: the X side's gather table is then rebuilt by
+// a full split pass before every X half-step, as in round 1)
+extern "C" float* cumf_als_theta_ptr(cumf_als_solver* s) {
+    if (!s) return nullptr;
+    s->theta_ptr_exposed = true;
+    s->theta_table_current = false;
+    return s->theta.as<float>();
+}
+// library-internal (synth.cu): both replicas for an in-library rewrite; the caller does not keep the pointers
+extern "C" void cumf_als_internal_rewrite_factors(cumf_als_solver* s, float** theta, float** x) {
+    s->theta_fresh = false;
+    s->theta_table_current = false;
+    *theta = s->theta.as<float>();
+    *x = s->x.as<float>();
+}
 extern "C" float* cumf_als_x_ptr(cumf_als_solver* s) { return s ? s->x.as<float>() : nullptr; }
 
 extern "C" int cumf_als_update_x(cumf_als_solver* s, void* stream) {
@@ -1235,15 +1268,22 @@ extern "C" int cumf_als_update_x(cumf_als_solver* s, void* stream) {
     CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_csr, 0));
     s->theta_fresh = false;
     CUMF_TRY(update_factor_impl(s->px, s->csr_col.as<int>(), s->csr_val.as<float>(), s->theta.as<float>(),
-                                s->x.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_x));
+                                s->x.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_x, nullptr,
+                                /*table_current=*/s->theta_table_current));
     s->launches += s->px->last_launches;
     return CUMF_OK;
 }
 extern "C" int cumf_als_update_theta(cumf_als_solver* s, void* stream) {
     CUMF_REQUIRE(s, "null pointer");
     CUMF_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_csc, 0));
+    // the X side's gather table (f = 100 long-row kernel) gets the split form of every theta row from this half-step's solver
+    // epilogues, on every replica: the next X half-step skips its split pass over all of theta
+    s->theta_table_current = false;
+    bool wrote = false;
     CUMF_TRY(update_factor_impl(s->pt, s->csc_row.as<int>(), s->csc_val.as<float>(), s->x.as<float>(),
-                                s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_theta));
+                                s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_theta,
+                                s->theta_split_out.n > 0 ? &s->theta_split_out : nullptr, false, &wrote));
+    s->theta_table_current = wrote && !s->theta_ptr_exposed;
     s->launches += s->pt->last_launches;
     s->theta_fresh = s->pt->sse_terms_valid;
     return CUMF_OK;
@@ -1506,8 +1546,11 @@ extern "C" int cumf_als_peer_barrier(cumf_als_solver* s, void* stream) {
     return CUMF_OK;
 }
 
-// blob = 3 CUDA IPC handles (X replica, theta replica, barrier flags), 64 bytes each
-extern "C" int cumf_als_ipc_blob_bytes(void) { return 3 * (int)sizeof(cudaIpcMemHandle_t); }
+// blob = 4 CUDA IPC handles of 64 bytes (X replica, theta replica, barrier flags, the allocation that holds the X side's gather
+// table) + two 8-byte words (offset of the table in that allocation; 1 if there is such a table, else the 4th handle is unused)
+namespace { constexpr int kIpcHandles = 4; }
+extern "C" int cumf_als_ipc_blob_bytes(void) { return kIpcHandles * (int)sizeof(cudaIpcMemHandle_t) + 16; }
+
 
 static int solver_alloc_flags(cumf_als_solver* s) {
     if (s->flags.p) return CUMF_OK;
@@ -1525,6 +1568,20 @@ extern "C" int cumf_als_ipc_export(cumf_als_solver* s, void* blob) {
     CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[0], s->x.p));
     CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[1], s->theta.p));
     CUMF_CUDA_TRY(cudaIpcGetMemHandle(&h[2], s->flags.p));
+    unsigned long long* words = reinterpret_cast<unsigned long long*>(h + kIpcHandles);
+    words[0] = words[1] = 0;
+    memset(&h[3], 0, sizeof(h[3]));
+    if (unsigned short* tab = own_gather_table(s)) {
+        // the table is usually carved out of the solver's arena: export the whole allocation and say where the table starts
+        unsigned char* base = reinterpret_cast<unsigned char*>(tab);
+        if (s->arena.base && base >= s->arena.base && base < s->arena.base + s->arena.cap) base = s->arena.base;
+        if (cudaIpcGetMemHandle(&h[3], base) == cudaSuccess) {
+            words[0] = (unsigned long long)(reinterpret_cast<unsigned char*>(tab) - base);
+            words[1] = 1;
+        } else {
+            cudaGetLastError();
+        }
+    }
     return CUMF_OK;
 }
 
@@ -1540,18 +1597,33 @@ extern "C" int cumf_als_ipc_import(cumf_als_solver* s, const void* blobs, int nr
     s->nranks = nranks;
     s->peer_x.n = s->peer_theta.n = 0;
     s->peer_flags[my_rank] = s->flags.as<unsigned long long>();
-    const cudaIpcMemHandle_t* h = reinterpret_cast<const cudaIpcMemHandle_t*>(blobs);
+    const size_t stride = (size_t)cumf_als_ipc_blob_bytes();
+    auto blob_of = [&](int r) { return reinterpret_cast<const cudaIpcMemHandle_t*>(static_cast<const unsigned char*>(blobs) + stride * r); };
+    auto words_of = [&](int r) { return reinterpret_cast<const unsigned long long*>(blob_of(r) + kIpcHandles); };
+    // split rows are pushed only if EVERY rank has a gather table to receive them (all ranks see the same blobs, so they agree)
+    bool tables = own_gather_table(s) != nullptr;
+    for (int r = 0; r < nranks; ++r) tables = tables && (r == my_rank || words_of(r)[1] == 1);
+    s->theta_split_out.n = 0;
+    if (tables) s->theta_split_out.p[s->theta_split_out.n++] = own_gather_table(s);
     for (int r = 0; r < nranks; ++r) {
         if (r == my_rank) continue;
+        const cudaIpcMemHandle_t* h = blob_of(r);
         void* p[3] = {nullptr, nullptr, nullptr};
         for (int k = 0; k < 3; ++k) {
-            CUMF_CUDA_TRY(cudaIpcOpenMemHandle(&p[k], h[3 * r + k], cudaIpcMemLazyEnablePeerAccess));
+            CUMF_CUDA_TRY(cudaIpcOpenMemHandle(&p[k], h[k], cudaIpcMemLazyEnablePeerAccess));
             s->ipc_opened.push_back(p[k]);
         }
         s->peer_x.p[s->peer_x.n++] = reinterpret_cast<float*>(p[0]);
         s->peer_theta.p[s->peer_theta.n++] = reinterpret_cast<float*>(p[1]);
         s->peer_flags[r] = reinterpret_cast<unsigned long long*>(p[2]);
+        if (tables) {
+            void* base = nullptr;
+            CUMF_CUDA_TRY(cudaIpcOpenMemHandle(&base, h[3], cudaIpcMemLazyEnablePeerAccess));
+            s->ipc_opened.push_back(base);
+            s->theta_split_out.p[s->theta_split_out.n++] = reinterpret_cast<unsigned short*>(static_cast<unsigned char*>(base) + words_of(r)[0]);
+        }
     }
+    s->theta_table_current = false;
     return CUMF_OK;
 }
 
@@ -1618,17 +1690,23 @@ static void group_connect(cumf_als_group* g) {
         cudaSetDevice(g->s[0]->device);
         g->same_dev.reset(new cumf_multi::SameDeviceSync(n));
     }
+    bool all_tables = true;       // split rows are pushed only if every shard has a gather table to receive them
+    for (int k = 0; k < n; ++k) all_tables = all_tables && own_gather_table(g->s[k]) != nullptr;
     for (int k = 0; k < n; ++k) {
         cumf_als_solver* s = g->s[k];
         s->rank = k;
         s->nranks = n;
         s->same_dev = g->same_dev.get();
         s->peer_x.n = s->peer_theta.n = 0;
+        s->theta_split_out.n = 0;
+        s->theta_table_current = false;
+        if (all_tables) s->theta_split_out.p[s->theta_split_out.n++] = own_gather_table(s);
         for (int j = 0; j < n; ++j) {
             s->peer_flags[j] = g->s[j]->flags.as<unsigned long long>();
             if (j == k) continue;
             s->peer_x.p[s->peer_x.n++] = g->s[j]->x.as<float>();
             s->peer_theta.p[s->peer_theta.n++] = g->s[j]->theta.as<float>();
+            if (all_tables) s->theta_split_out.p[s->theta_split_out.n++] = own_gather_table(g->s[j]);
         }
     }
 }

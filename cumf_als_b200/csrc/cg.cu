@@ -43,7 +43,8 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[NT/32]*/, int 
 template <int F, int S>
 __global__ void __launch_bounds__(((F * S + 31) / 32) * 32)
 cg_kernel(const float* __restrict__ A, float* __restrict__ x, const float* __restrict__ b, float cg_iter,
-          const SplitRow* __restrict__ sys_rows, float lambda, double* __restrict__ sse_rows, PeerOut peers, int x_row_offset) {
+          const SplitRow* __restrict__ sys_rows, float lambda, double* __restrict__ sse_rows, PeerOut peers, int x_row_offset,
+          SplitOut split_out) {
     constexpr int SEG = F / S;
     constexpr int NT = ((F * S + 31) / 32) * 32;
     __shared__ __align__(16) float sp[F];
@@ -117,6 +118,7 @@ cg_kernel(const float* __restrict__ A, float* __restrict__ x, const float* __res
     if (active && h == 0) {
         x[xrow * F + i] = xi;                            // cg.cu:230
         for (int k = 0; k < peers.n; ++k) peers.p[k][prow * F + i] = xi;      // the same row of every peer replica
+        if (split_out.n > 0) split_row_store(split_out, prow, i, xi);         // and its split form (common.cuh, SplitOut)
     }
     if (sse_rows != nullptr) {
         // x^T b + x^T r + reg x^T x: with sum r_j^2 it gives the row's squared error (see gram_tc.cu); only used
@@ -130,10 +132,10 @@ cg_kernel(const float* __restrict__ A, float* __restrict__ x, const float* __res
 
 template <int F>
 int launch_one(const float* A, float* x, const float* b, int batch, float cg_iter, const SplitRow* rows,
-               cudaStream_t st, float lambda, double* sse_rows, const PeerOut& peers, int x_row_offset) {
+               cudaStream_t st, float lambda, double* sse_rows, const PeerOut& peers, int x_row_offset, const SplitOut& split_out) {
     constexpr int S = (F > 128) ? 2 : 1;
     constexpr int NT = ((F * S + 31) / 32) * 32;
-    cg_kernel<F, S><<<batch, NT, 0, st>>>(A, x, b, cg_iter, rows, lambda, sse_rows, peers, x_row_offset);
+    cg_kernel<F, S><<<batch, NT, 0, st>>>(A, x, b, cg_iter, rows, lambda, sse_rows, peers, x_row_offset, split_out);
     CUMF_CUDA_TRY(cudaGetLastError());
     return CUMF_OK;
 }
@@ -141,12 +143,15 @@ int launch_one(const float* A, float* x, const float* b, int batch, float cg_ite
 }  // namespace
 
 int launch_cg(const float* d_A, float* d_x, const float* d_b, int batch, int f, float cg_iter,
-              const SplitRow* d_sys_rows, cudaStream_t st, float lambda, double* d_sse_rows, const PeerOut* peers_in, int x_row_offset) {
+              const SplitRow* d_sys_rows, cudaStream_t st, float lambda, double* d_sse_rows, const PeerOut* peers_in, int x_row_offset,
+              const SplitOut* split_in) {
     if (batch <= 0) return CUMF_OK;
     PeerOut peers{};
     if (peers_in) peers = *peers_in;
+    SplitOut split_out{};
+    if (split_in && f == 100) split_out = *split_in;      // the table format belongs to the f = 100 kernel
     switch (f) {
-#define CUMF_CG_CASE(F) case F: return launch_one<F>(d_A, d_x, d_b, batch, cg_iter, d_sys_rows, st, lambda, d_sse_rows, peers, x_row_offset);
+#define CUMF_CG_CASE(F) case F: return launch_one<F>(d_A, d_x, d_b, batch, cg_iter, d_sys_rows, st, lambda, d_sse_rows, peers, x_row_offset, split_out);
         CUMF_CG_CASE(10) CUMF_CG_CASE(20) CUMF_CG_CASE(30) CUMF_CG_CASE(40) CUMF_CG_CASE(50)
         CUMF_CG_CASE(60) CUMF_CG_CASE(70) CUMF_CG_CASE(80) CUMF_CG_CASE(90) CUMF_CG_CASE(100)
         CUMF_CG_CASE(110) CUMF_CG_CASE(120) CUMF_CG_CASE(130) CUMF_CG_CASE(140) CUMF_CG_CASE(150)

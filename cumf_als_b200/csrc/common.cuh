@@ -1,6 +1,7 @@
 // common.cuh -- shared declarations of the B200 ALS hot path (internal header).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -112,6 +113,33 @@ struct PeerOut {
     int n;
 };
 
+// Pre-split fp16 tables (the f = 100 long-row kernel's gather source: [hi (128 halfs) | lo' = (v - hi) * 2048 (128 halfs)] per
+// row, gram_tc.cu split_factor_kernel) that receive the split form of every row a half-step solves, next to the fp32 row: the
+// NEXT half-step then finds its gather table up to date and skips its split pass over the whole factor -- which every rank of a
+// sharded run would otherwise repeat in full (round-1 verdict: 246 MB written per rank per half-step regardless
+// of the number of ranks).  p[0] is the local table, the others live on peer GPUs.
+struct SplitOut {
+    unsigned short* p[8];     // fp16 bit patterns
+    int n;
+};
+constexpr int kSplitRowHalfs = 256, kSplitLoOffset = 128;
+constexpr float kSplitLoScale = 2048.f;
+#ifdef __CUDACC__
+// hi = the top 11 significant bits (exact in fp16), lo' = fp16((v - hi) * 2048): the arithmetic of split_factor_kernel
+__device__ __forceinline__ void split_row_store(const SplitOut& so, size_t row, int col, float v) {
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const unsigned short hh = __half_as_ushort(__float2half_rn(h));
+    const unsigned short hl = __half_as_ushort(__float2half_rn((v - h) * kSplitLoScale));
+#pragma unroll 1
+    for (int k = 0; k < so.n; ++k) {
+        unsigned short* t = so.p[k] + row * kSplitRowHalfs + col;
+        t[0] = hh;
+        t[kSplitLoOffset] = hl;
+    }
+}
+#endif
+
+
 // Small host -> device uploads of plan metadata that must not queue on the copy engine behind gigabytes of rating
 // uploads: the bytes go through a pinned staging arena (one per device, grown on demand, kept) and are copied by a kernel
 // reading the arena over PCIe.  Asynchronous on `st`; the arena is recycled by staging_reset(), which the caller may
@@ -147,7 +175,7 @@ int launch_split_reduce(const SplitRow* d_rows, int r0, int r1, int f, float lam
 // (used for the compact batch of split rows).
 int launch_cg(const float* d_A, float* d_x, const float* d_b, int batch, int f, float cg_iter,
               const SplitRow* d_sys_rows, cudaStream_t st, float lambda = 0.f, double* d_sse_rows = nullptr,
-              const PeerOut* peers = nullptr, int x_row_offset = 0);
+              const PeerOut* peers = nullptr, int x_row_offset = 0, const SplitOut* split_out = nullptr);
 // cuBLAS batched LU oracle.
 int launch_lu(float* d_A, float* d_x, float* d_b, int batch, int f, cudaStream_t st);
 // RMSE partial sums.
@@ -176,12 +204,18 @@ int tc_sse_terms_per_cta();
 struct TcExtra {
     float* d_tt = nullptr; float* d_rhs = nullptr; int tt_row_base = 0;
     float* const* peer_out = nullptr; int n_peer_out = 0;
+    const SplitOut* split_out = nullptr;      // generic kernel at f = 100: also write every solved row's split form there
+    bool table_current = false;               // f = 100 kernel: the gather table already holds d_factor's split form
 };
-inline TcExtra tc_extra_from(const PeerOut* peers) {
+inline TcExtra tc_extra_from(const PeerOut* peers, const SplitOut* split_out = nullptr, bool table_current = false) {
     TcExtra e;
     if (peers) { e.peer_out = peers->p; e.n_peer_out = peers->n; }
+    e.split_out = split_out;
+    e.table_current = table_current;
     return e;
 }
+// the f = 100 kernel's gather table of a plan (nullptr: this plan gathers from a table of another format)
+unsigned short* tc_plan_split_table_f100(TcWork* w);
 int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks,
                      const int* d_colidx, const float* d_val, const float* d_factor, float* d_out,
                      int f, float lambda, float cg_iter, float* d_scratchA, float* d_scratchB,
@@ -204,6 +238,7 @@ struct Tc2Launch {
     void* d_table = nullptr; const void* tensor_map = nullptr;      // fp16 split table [factor_rows + 1][tab_cols] and its CUtensorMap
     unsigned* d_absmax = nullptr; float* d_scales = nullptr;        // 2 words / 4 floats of per-launch scale state
     float* d_out = nullptr; float* const* peer_out = nullptr; int n_peer_out = 0;
+    const SplitOut* split_out = nullptr;
     float lambda = 0.f, cg_iter = 0.f;
     float* d_scratchA = nullptr; float* d_scratchB = nullptr;
     float* d_tt = nullptr; float* d_rhs = nullptr; int tt_row_base = 0;

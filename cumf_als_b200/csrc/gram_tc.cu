@@ -1000,6 +1000,7 @@ struct TcWork {
     int hint_rows = 0;                  // rows of the opposing factor as told by the caller (0: scan the indices)
     int factor_rows = 0;                // largest column id + 1 found in scanned_colidx[0, idx_span)
     DevBuf split_tab;                   // [factor_rows + 1][256] fp16, last row zero
+    const void* table_filled = nullptr; // == split_tab.p once a full split pass has written padding and zero row of this allocation
     DevBuf max_idx;
     // with a row-count hint the index scan runs asynchronously (no stream synchronisation on the hot path): its result
     // lands in pinned host memory and is checked by the next launch of this plan
@@ -1073,6 +1074,10 @@ static int encode_factor_map(CUtensorMap* map, const float* d_factor) {
 void tc_plan_destroy(TcWork* w, bool cache);
 
 int tc_plan_grid(const TcWork* w) { return w ? w->grid : 0; }
+unsigned short* tc_plan_split_table_f100(TcWork* w) {
+    return (w && w->impl == 1 && w->direct && w->f == 100) ? w->split_tab.as<unsigned short>() : nullptr;
+}
+
 int tc_plan_impl(const TcWork* w) { return w ? w->impl : 0; }
 // rows of the opposing factor, when the caller knows them: saves the index scan (and its stream synchronisation) of
 // the first direct-staging launch
@@ -1089,6 +1094,7 @@ void tc_plan_set_factor_rows(TcWork* w, int rows) {
     if (rows != w->factor_rows || !w->split_tab.p) {
         const int cols = w->impl == 2 ? w->info2.tab_cols : SPLIT_COLS;
         w->split_tab.release();
+        w->table_filled = nullptr;
         if (w->split_tab.alloc((size_t)(rows + 1) * cols * 2) == CUMF_OK &&
             encode_split_map(&w->split_map, w->split_tab.p, (long long)rows + 1, cols) == CUMF_OK)
             w->factor_rows = rows;
@@ -1332,6 +1338,7 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
             if (rows != w->factor_rows || !w->split_tab.p) {
                 const int cols = w->impl == 2 ? w->info2.tab_cols : SPLIT_COLS;
                 w->split_tab.release();
+                w->table_filled = nullptr;
                 CUMF_TRY(w->split_tab.alloc((size_t)(rows + 1) * cols * 2));
                 CUMF_TRY(encode_split_map(&w->split_map, w->split_tab.p, (long long)rows + 1, cols));
                 w->factor_rows = rows;
@@ -1365,13 +1372,20 @@ int tc_update_factor(TcWork* w, const Chunk* d_chunks, int nchunks, const int* d
             if (extra) {
                 a.d_tt = extra->d_tt; a.d_rhs = extra->d_rhs; a.tt_row_base = extra->tt_row_base;
                 a.peer_out = extra->peer_out; a.n_peer_out = extra->n_peer_out;
+                a.split_out = extra->split_out;
             }
             return tc2_update(a, st, launches);
         }
-        const size_t pieces = (size_t)(w->factor_rows + 1) * 32;
-        split_factor_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(d_factor, w->factor_rows, w->split_tab.as<uint4>());
-        CUMF_CUDA_TRY(cudaGetLastError());
-        *launches += 1;
+        // the split pass over the whole opposing factor -- unless the half-step that produced that factor already wrote the
+        // split form of every row into this table (TcExtra::table_current; the table's padding and zero row come from the
+        // first full pass)
+        if (!(extra && extra->table_current && w->table_filled == w->split_tab.p)) {
+            const size_t pieces = (size_t)(w->factor_rows + 1) * 32;
+            split_factor_kernel<<<(unsigned)((pieces + 255) / 256), 256, 0, st>>>(d_factor, w->factor_rows, w->split_tab.as<uint4>());
+            CUMF_CUDA_TRY(cudaGetLastError());
+            *launches += 1;
+            w->table_filled = w->split_tab.p;
+        }
         const uint64_t desc_tmpl = smem_desc_template_direct(D_CHUNK_STRIDE, D_KG_STRIDE);
         v.fn<<<w->grid, v.threads, v.smem, st>>>(d_chunks, w->cta_ptr.as<int>(), w->stage_tab.as<StageDesc>(), w->cta_stage_ptr.as<int>(),
                                                d_colidx, d_val, w->split_map, d_out, lambda, cg_iter, d_scratchA, d_scratchB,

@@ -164,6 +164,9 @@ int tc2_update(const Tc2Launch& a, cudaStream_t st, int* launches) {
     p.tt = a.d_tt; p.rhs = a.d_rhs; p.tt_row_base = a.tt_row_base;
     p.scales = a.d_scales; p.sse_terms = a.d_sse_terms; p.zero_row = a.factor_rows;
     p.hi_only = a.hi_only ? 1 : 0;
+    p.split_out.n = 0;
+    for (int k = 0; k < 8; ++k) p.split_out.p[k] = nullptr;
+    if (a.split_out && a.f == 100 && !a.d_tt) p.split_out = *a.split_out;
     p.prof = nullptr;
 #ifdef CUMF_TC2_PROFILE
     // experiment builds only (tools/build_variant.sh prof -DCUMF_TC2_PROFILE): per-role cycle counters, printed per launch

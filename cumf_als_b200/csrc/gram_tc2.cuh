@@ -227,6 +227,7 @@ struct Params {
     double* sse_terms;
     int zero_row;
     int hi_only;                  // reduced-precision mode: gather and multiply only the fp16 hi halves
+    SplitOut split_out;           // F == 100: tables that receive every solved row's split form (common.cuh)
     unsigned long long* prof;     // -DCUMF_TC2_PROFILE builds: [cta][PROF_WORDS] cycle counters per role (tools/theta_probe.py)
 };
 constexpr int PROF_WORDS = 40;
@@ -901,6 +902,9 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 if (active) {
 #pragma unroll 1
                     for (int k = 0; k < P.out.n; ++k) P.out.p[k][(size_t)ck.row * F + i] = xi;
+                    if constexpr (F == 100) {
+                        if (P.split_out.n > 0) split_row_store(P.split_out, (size_t)ck.row, i, xi);
+                    }
                 }
                 if (P.sse_terms != nullptr) {
                     // sum_j (r_j - x.theta_j)^2 = sum r_j^2 - (x^T b + x^T r + reg x^T x) with r the CG residual (see gram_tc.cu)

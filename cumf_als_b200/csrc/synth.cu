@@ -344,10 +344,12 @@ __global__ void init_uniform_kernel(float* __restrict__ p, size_t n, unsigned lo
 
 // theta <- scale * uniform[0,1) (a pure function of seed and position: every replica gets the same values), X <- 0: the shape
 // of the front ends' initialisation (main.cpp:72-78) without a host copy of the factors (20 GB of X at Hugewiki scale)
+extern "C" void cumf_als_internal_rewrite_factors(cumf_als_solver* s, float** theta, float** x);
 extern "C" int cumf_als_init_factors_device(cumf_als_solver* s, unsigned long long seed, float scale) {
     CUMF_REQUIRE(s, "null pointer");
-    float* th = cumf_als_theta_ptr(s);
-    float* x = cumf_als_x_ptr(s);
+    float* th = nullptr;
+    float* x = nullptr;
+    cumf_als_internal_rewrite_factors(s, &th, &x);
     int m = 0, n = 0, f = 0;
     cumf_als_shape(s, &m, &n, &f);
     init_uniform_kernel<<<1184, 256>>>(th, (size_t)n * f, seed, scale);

@@ -257,11 +257,13 @@ int cumf_als_timers(cumf_als_solver* s, double* out6, int reset);
  * ranges of X and theta and full replicas of both factors; the solver epilogue of its half-step
  * stores every updated row into ALL replicas (peer-mapped pointers over NVLink), so the
  * exchange overlaps the kernel, and one tiny barrier kernel (epoch flags in peer memory) ends
- * the half-step.  No NCCL call on this path.
+ * the half-step.  No NCCL call on this path.  At f = 100 with long X rows the theta half-step's epilogues also
+ * store each solved row's fp16 split form into every rank's X-side gather table, so no rank re-splits all of theta
+ * before its X half-step (CUMF_FUSED_SPLIT=0 turns that off; taking cumf_als_theta_ptr does too).
  *
  * (a) one process per GPU (torchrun / MPI): create the solver with this rank's ranges, exchange
- *     the blobs of cumf_als_ipc_export (CUDA IPC handles of the two replicas and the flag
- *     words; cumf_als_ipc_blob_bytes() each) with any transport, hand all of them, in rank
+ *     the blobs of cumf_als_ipc_export (CUDA IPC handles of the two replicas, the flag
+ *     words and the allocation holding the gather table; cumf_als_ipc_blob_bytes() each) with any transport, hand all of them, in rank
  *     order, to cumf_als_ipc_import on every rank, synchronise the ranks once on the host, then
  *     cumf_als_iterate (which ends each half-step with cumf_als_peer_barrier) or
  *     update_x / peer_barrier / update_theta / peer_barrier by hand.                          */

@@ -64,3 +64,57 @@ def test_doals_cumf_gpus_equals_single(cuda):
     assert p.returncode == 0
     assert "[doALS] CUMF_GPUS=2 vs 1: factors equal True" in p.stdout
     assert p.stdout.count("factors equal True") == 3          # group with both kernels, then doALS
+
+
+@pytest.mark.parametrize("shards", [1, 2, 3])
+def test_theta_half_step_keeps_the_x_side_gather_table_current(cuda, monkeypatch, shards):
+    """f = 100, long X rows (round-1 kernel, 512-byte [hi | lo'] gather table of theta) and short theta rows (generic kernel): the
+    theta half-step's solver epilogues write the split form of every row they solve into that table -- on every shard -- and the
+    next X half-step skips its split pass over all of theta.  Same table bits, so the factors equal those of
+    CUMF_FUSED_SPLIT=0 (every X half-step re-splits) bit for bit, with one launch less per iteration and shard."""
+    monkeypatch.setenv("CUMF_GROUP_SAME_DEVICE", "1")
+    monkeypatch.delenv("CUMF_TC_IMPL", raising=False)
+    monkeypatch.setenv("CUMF_SPLIT_NNZ", "4000")           # some X rows split across CTAs, a few theta rows too (CG tail writes split rows)
+    f, lam, iters = 100, 0.048, 3
+    r = synth_ratings(900, 14000, 1400000, 20000, seed=123)
+    theta0, X0 = init_factors(r.m, r.n, f, seed=5)
+
+    def run(fused):
+        monkeypatch.setenv("CUMF_FUSED_SPLIT", "1" if fused else "0")
+        if shards == 1:
+            s = c.AlsSolver(*_solver_args(r, f, lam))
+        else:
+            s = c.AlsGroup(*_solver_args(r, f, lam), n_devices=shards)
+        s.set_factors(theta0, X0)
+        s.iterate(iters)
+        out = s.get_factors()
+        n_launch = int(s.timers()["launches"]) if shards == 1 else None
+        s.close()
+        return out, n_launch
+
+    (th_a, X_a), la = run(False)
+    (th_b, X_b), lb = run(True)
+    assert np.array_equal(th_a, th_b) and np.array_equal(X_a, X_b)
+    if shards == 1:
+        print(f"launches: re-split every X half-step {la}, fused {lb}")
+        assert lb == la - (iters - 1)
+
+
+def test_raw_theta_pointer_disables_the_table_shortcut(cuda, monkeypatch):
+    """A caller that took cumf_als_theta_ptr may rewrite theta behind the solver's back: after that the X side re-splits."""
+    monkeypatch.delenv("CUMF_TC_IMPL", raising=False)
+    f, lam = 100, 0.048
+    r = synth_ratings(900, 14000, 1400000, 20000, seed=124)
+    theta0, X0 = init_factors(r.m, r.n, f, seed=6)
+    s = c.AlsSolver(*_solver_args(r, f, lam))
+    s.set_factors(theta0, X0)
+    launches = lambda: int(s.timers()["launches"])
+    s.iterate(1)
+    l0 = launches()
+    s.iterate(1)
+    per_iter_fused = launches() - l0
+    assert s.theta_ptr != 0
+    l1 = launches()
+    s.iterate(1)
+    assert launches() - l1 == per_iter_fused + 1
+    s.close()
