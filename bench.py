@@ -423,6 +423,13 @@ def run_ours(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     tm = solver.timers()
+    rank_kernel_ms = None
+    if world > 1:      # dominant-kernel time of every rank (the slowest one sets the step: the others wait in the barrier kernel)
+        it = max(tm["iterations"], 1)
+        mine = torch.tensor([tm["gram_x_ms"] / it, tm["gram_theta_ms"] / it], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_kernel_ms = [[round(float(v), 4) for v in t.cpu()] for t in allr]
     train_rmse, test_rmse = rmse()
     iters_per_s = args.steps / (ms / 1e3)
 
@@ -454,6 +461,10 @@ def run_ours(args, w):
             "train_rmse": train_rmse, "test_rmse": test_rmse,
             "gpu_launches": int(tm["launches"]),
             "clocks": clocks.summary(),
+            **({"rank_kernel_ms": {"x_side_theta_side_per_rank": rank_kernel_ms,
+                                   "slowest_sum": max(a + b for a, b in rank_kernel_ms),
+                                   "sum_of_per_side_maxima": max(a for a, _ in rank_kernel_ms) + max(b for _, b in rank_kernel_ms)}}
+               if rank_kernel_ms else {}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": (sum(v.get("dram_bytes", 0) for v in ncu.values() if isinstance(v, dict)) or None) if ncu else None,
