@@ -89,30 +89,41 @@ try:
 except Exception:
     h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[3]))
 mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+gate = path + ".gate"
+import os
 with open(path, "w", buffering=1) as f:
     while True:
+        if not os.path.exists(gate):      # NVML is only queried inside a timed region (its queries contend with the driver
+            time.sleep(0.001)             # calls of everything else on the box: allocation, peer access, IPC)
+            continue
+        try:
+            period = float(open(gate).read() or 4) / 1000.0
+        except Exception:
+            period = 0.004
         try:
             f.write("%.6f,%d,%d,%.1f,%d\n" % (time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), mx,
                                               nv.nvmlDeviceGetPowerUsage(h) / 1000.0, nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
         except Exception:
             pass
-        time.sleep(0.004)
+        time.sleep(period)
 """
 
 
 class ClockSampler:
-    """SM clock, power and throttle reasons of one GPU DURING the timed region.  A helper PROCESS polls NVML every few ms from
-    the moment the sampler is first constructed (process start-up and nvmlInit take longer than an 8-GPU timed region of
-    45 ms; polling from a thread of this process was measured to slow the launches down); `with` only brackets the region by
-    wall-clock time stamps, summary() keeps the samples inside it.  Falls back to `nvidia-smi -lms` without pynvml."""
+    """SM clock, power and throttle reasons of one GPU DURING the timed region.  A helper PROCESS is started when the sampler
+    is first constructed (process start-up and nvmlInit take longer than an 8-GPU timed region of 45 ms) and polls NVML every
+    4 ms while a `with` block holds its gate file -- only then: polled all the time, it slowed the driver calls of the e2e
+    leg (allocation, peer access) several-fold.  summary() keeps the samples between the block's wall-clock time stamps.
+    Falls back to `nvidia-smi -lms` without pynvml."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     _helpers = {}       # gpu index -> (Popen, path)
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_ms: float = 4.0):
         self.gpu, self.proc, self.tmp = gpu_index, None, None
         self.t0 = self.t1 = None
+        self.period_ms = period_ms
         self.helper = ClockSampler._helpers.get(gpu_index)
         if self.helper is None:
             try:
@@ -128,7 +139,7 @@ class ClockSampler:
                 proc = subprocess.Popen([sys.executable, "-c", _CLOCK_HELPER, sel, tmp.name, str(gpu_index)],
                                         stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 import atexit
-                atexit.register(lambda: (proc.terminate(), os.path.exists(tmp.name) and os.unlink(tmp.name)))
+                atexit.register(lambda: (proc.terminate(), [os.path.exists(q) and os.unlink(q) for q in (tmp.name, tmp.name + ".gate")]))
                 self.helper = ClockSampler._helpers[gpu_index] = (proc, tmp.name)
             except Exception:
                 self.helper = None
@@ -136,6 +147,8 @@ class ClockSampler:
     def __enter__(self):
         self.t0 = time.time()
         if self.helper is not None and self.helper[0].poll() is None:
+            with open(self.helper[1] + ".gate", "w") as g:     # the helper polls NVML while this file exists
+                g.write(str(self.period_ms))
             return self
         self.helper = None                 # the helper died (no NVML): nvidia-smi
         try:
@@ -148,6 +161,11 @@ class ClockSampler:
 
     def __exit__(self, *exc):
         self.t1 = time.time()
+        if self.helper is not None:
+            try:
+                os.unlink(self.helper[1] + ".gate")
+            except OSError:
+                pass
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -644,7 +662,7 @@ def run_reference(args, w):
             O.ref_do_als(r, theta0.copy(), X0.copy(), f, lam, args.warmup, xb, tb, variant, local_rank)
     th, X = pin(theta0), pin(X0)
     iters = args.steps
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank, period_ms=20.0) as clocks:      # (the reference makes driver calls inside its timed call)
         t0 = time.perf_counter()
         with CaptureStdout() as cap:
             fin = O.ref_do_als(r, th, X, f, lam, iters, xb, tb, variant, local_rank)
