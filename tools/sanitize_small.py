@@ -28,3 +28,17 @@ for f in fs:
     s.close()
     print(f"sanitize_small: f={f} 2 iterations {ms:.1f} ms, rmse {tr:.5f} / {te:.5f}", flush=True)
     assert np.isfinite(tr) and np.isfinite(te)
+
+if 100 in fs:
+    # long X rows at f = 100: round-1 kernel on the X side, generic kernel on the theta side writing split rows into its table
+    os.environ["CUMF_SPLIT_NNZ"] = "2200"
+    r = synth_ratings(16, 900, 32000, 1000, seed=4)
+    theta0, X0 = init_factors(r.m, r.n, 100, seed=2)
+    s = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
+                    r.test_row, r.test_col, r.test_val, r.m, r.n, 100, 0.05)
+    s.set_factors(theta0, X0)
+    ms = s.iterate(3)
+    tr, te = s.rmse()
+    s.close()
+    print(f"sanitize_small: f=100 long X rows, 3 iterations {ms:.1f} ms, rmse {tr:.5f} / {te:.5f}", flush=True)
+    assert np.isfinite(tr) and np.isfinite(te)
