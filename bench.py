@@ -249,10 +249,16 @@ def launch_roofline(rows, nnz, f, fused, ms, ncu):
     out = {"ms": ms, "algorithmic_bytes": b, "algorithmic_gbs": b / 1e9 / (ms / 1e3), "frac_hbm": b / 1e9 / (ms / 1e3) / hbm,
            "useful_tflops": flops / 1e12 / (ms / 1e3), "frac_tensor": flops / 1e12 / (ms / 1e3) / tf}
     if ncu:
-        out.update({k: ncu[k] for k in ("dram_bytes", "tensor_pipe_pct", "l2_hit_pct") if k in ncu})
+        out.update({k: ncu[k] for k in ("dram_bytes", "tensor_pipe_pct", "l2_hit_pct", "smem_data_pipe_pct") if k in ncu})
         if "dram_bytes" in ncu:
             out["dram_gbs"] = ncu["dram_bytes"] / 1e9 / (ms / 1e3)
-            out["bound"] = "hbm" if ncu["dram_bytes"] > 0.25 * b else "tensor+l2 (gather source is L2-resident)"
+            if ncu["dram_bytes"] > 0.25 * b:
+                out["bound"] = "hbm"
+            elif sum((ncu.get("smem_data_pipe_pct") or {}).values()) > 80:
+                out["bound"] = ("shared-memory data pipe (tensor-core operand reads + the CG's p broadcasts); the gather source is "
+                                "L2-resident, so neither the HBM nor the tensor fraction is this launch's roof")
+            else:
+                out["bound"] = "tensor+l2 (gather source is L2-resident)"
     return out
 
 

@@ -193,6 +193,9 @@ template <int F, int MODE> struct __align__(1024) Smem {
     __align__(16) float sp[C::kSys][2][C::kSpN];  // CG direction vector per system, double buffered
     float red[C::kSys][3][8];                     // cross-warp partial sums
     unsigned long long full_tma[NBAR], empty_op[NBAR];
+#ifdef CUMF_TC2_EXPLICIT_HANDOFF
+    unsigned long long vals_ready[NBAR];          // sanitizer build: see the issuer's wait
+#endif
     unsigned long long acc_full[MAX_SYS][MAX_BUF], acc_empty[MAX_BUF];
     uint32_t tmem_base;
     __device__ __forceinline__ unsigned char* dstage(int slot) { return ring + slot * C::G::STAGE_BYTES; }
@@ -463,6 +466,9 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();      // SWIZZLE_128B atoms need 1024-byte alignment
     if (tid == 0) {
         for (int s = 0; s < NBAR; ++s) { mbar_init(&sm.full_tma[s], 1); mbar_init(&sm.empty_op[s], 1); }
+#ifdef CUMF_TC2_EXPLICIT_HANDOFF
+        for (int s = 0; s < NBAR; ++s) mbar_init(&sm.vals_ready[s], 1);
+#endif
         for (int b = 0; b < MAX_BUF; ++b) {
             for (int g = 0; g < MAX_SYS; ++g) mbar_init(&sm.acc_full[g][b], 1);
             mbar_init(&sm.acc_empty[b], 4 * RB);
@@ -519,6 +525,13 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                     CUMF_PROF(pf_a = clock64();)
                     mbar_wait_hot(&sm.full_tma[slot], ph);      // the gathered rows have landed (TMA complete_tx)
                     CUMF_PROF(pf_full += clock64() - pf_a; ++pf_n;)
+#ifdef CUMF_TC2_EXPLICIT_HANDOFF
+                    // compute-sanitizer racecheck build only.  The stage worker's stage_vals[] reach this warp through full_tma[slot]:
+                    // the worker's arrive.expect_tx (release) is one of the two things that complete the phase this warp acquired
+                    // above -- the other is the TMA's complete_tx, and racecheck does not follow transaction counts, so it reports
+                    // the handoff as a hazard.  This redundant thread-to-thread barrier makes the same ordering visible to the tool.
+                    mbar_wait(&sm.vals_ready[slot], ph);
+#endif
                     if constexpr (!C::kRatingOperand) {
                         // The rating rides along as feature F of gathered row kk: hi part in the hi region, lo part in the lo region.
                         // This warp drops them in itself -- the slot's worker is free to refill other slots, and a landed stage
@@ -640,6 +653,9 @@ als_fused2_kernel(const __grid_constant__ CUtensorMap factor_map, const __grid_c
                 }
                 __syncwarp();
                 if (elect_one()) {
+#ifdef CUMF_TC2_EXPLICIT_HANDOFF
+                    mbar_arrive(&sm.vals_ready[slot]);
+#endif
 #if defined(CUMF_TC2_EXP_NOGATHER)
                     mbar_arrive(&sm.full_tma[slot]);                 // experiment: nothing is gathered
 #elif defined(CUMF_TC2_EXP_GATHER1)

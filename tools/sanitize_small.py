@@ -32,7 +32,7 @@ for f in fs:
 if 100 in fs:
     # long X rows at f = 100: round-1 kernel on the X side, generic kernel on the theta side writing split rows into its table
     os.environ["CUMF_SPLIT_NNZ"] = "2200"
-    r = synth_ratings(16, 900, 32000, 1000, seed=4)
+    r = synth_ratings(16, 4000, 32000, 1000, seed=4)
     theta0, X0 = init_factors(r.m, r.n, 100, seed=2)
     s = c.AlsSolver(r.csr_indptr, r.csr_indices, r.csr_data, r.csc_indices, r.csc_indptr, r.csc_data, r.coo_row,
                     r.test_row, r.test_col, r.test_val, r.m, r.n, 100, 0.05)
