@@ -914,9 +914,14 @@ extern "C" int cumf_als_destroy(cumf_als_solver* s) {
     if (s->run_stream) { cudaStreamDestroy(s->run_stream); s->run_stream = nullptr; }
     s->csr_col.release_to_cache(); s->csr_val.release_to_cache(); s->csc_row.release_to_cache(); s->csc_val.release_to_cache();
     s->coo_row.release_to_cache(); s->test_row.release_to_cache(); s->test_col.release_to_cache(); s->test_val.release_to_cache();
-    s->theta.release_to_cache(); s->x.release_to_cache(); s->sse.release(); s->partials.release();
+    const double t_theta0 = wall_seconds();
+    s->theta.release_to_cache();
+    const double t_theta1 = wall_seconds();
+    s->x.release_to_cache(); s->sse.release(); s->partials.release();
     s->prep.release(); s->prep_partials.release();
     t[2] = wall_seconds();
+    if (debug && t[2] - t[1] > 0.005)
+        printf("\trelease: of which theta replica %.4f s, X replica and scalars %.4f s\n", t_theta1 - t_theta0, t[2] - t_theta1);
     plan_free(s->px, true);
     plan_free(s->pt, true);
     if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }

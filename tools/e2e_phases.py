@@ -18,7 +18,7 @@ import torch  # noqa: E402
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()   # like main.cpp:50-69 / bench.py
 for name in ("csr_indptr", "csr_indices", "csr_data", "csc_indptr", "csc_indices", "csc_data", "coo_row", "test_row", "test_col", "test_val"):
     setattr(r, name, pin(getattr(r, name)))
-for rep, iters in enumerate((1, 3, 10)):
+for rep, iters in enumerate(tuple(int(a) for a in os.environ.get("E2E_ITERS", "1,3,10").split(","))):
     th, X = pin(theta0), pin(X0)
     t0 = time.perf_counter()
     fin = c.do_als(*r.doals_args(), th, X, r.test_row, r.test_col, r.test_val, r.m, r.n, w["f"], r.nnz, r.nnz_test, w["lam"], iters, 1, 1, 0)
