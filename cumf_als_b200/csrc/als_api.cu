@@ -93,6 +93,8 @@ int DevBuf::alloc(size_t n) {
             t_arena->used = off + n;
             return CUMF_OK;
         }
+        t_arena->overflow_bytes += n;
+        t_arena->overflow_count += 1;
     }
     if (n >= kCacheMinBytes) {
         std::lock_guard<std::mutex> lock(g_buf_cache_mutex);
@@ -1005,6 +1007,20 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
         if (!src.on_device) est += (size_t)xn * 12 + (size_t)tn * 8 + (size_t)src.test_cnt * 12;
         est += owned * 64 + ((size_t)(xn + tn) / 32 + owned) * 8;                 // chunks, meta, stage tables
         est += ((size_t)m + (size_t)n + 2) * 512 * (f > 127 ? 2 : 1);              // pre-split fp16 tables of both sides
+        // partial [A | b] slots of rows that are cut into several chunks (plan_create_core: more than CUMF_SPLIT_NNZ ratings), and
+        // the compact batch their sums are solved from: ~0.5 GB on the Netflix X side, so it must be part of the estimate
+        if (path != CUMF_PATH_SIMT) {
+            const long long max_chunk = env_long("CUMF_SPLIT_NNZ", 8192);
+            auto scratch = [&](const std::vector<long long>& ptr) {
+                size_t slots = 0, rows_split = 0;
+                for (size_t r = 0; r + 1 < ptr.size(); ++r) {
+                    const long long cnt = ptr[r + 1] - ptr[r];
+                    if (cnt > max_chunk) { slots += (size_t)((cnt + max_chunk - 1) / max_chunk); rows_split += 1; }
+                }
+                return (slots + rows_split) * ((size_t)f * f + f) * sizeof(float) + (slots + rows_split) * 2048;
+            };
+            est += scratch(src.x_ptr) + scratch(src.t_ptr);
+        }
         est += est / 16;
         if (s->arena_block.alloc(est) == CUMF_OK) { s->arena.base = s->arena_block.as<unsigned char>(); s->arena.cap = est; s->arena.used = 0; }
         else cudaGetLastError();                                                  // no arena: every buffer gets its own allocation
@@ -1093,9 +1109,12 @@ static int als_create_core(cumf_als_solver** out, const ShardSource& src, int m,
                                    reinterpret_cast<int*>(s->prep.p), up)) != CUMF_OK) return fail(rc);
         s->prep_coo = true;
     }
-    if (debug)
+    if (debug) {
         printf("\tsetup: X plan + factor/CSR/CSC uploads enqueued %.4f s, theta plan %.4f s, rest %.4f s\n", t_plans - t_begin_wall,
                t_plans_end - t_plans, wall_seconds() - t_plans_end);
+        printf("\tsetup: arena %.0f of %.0f MB used, %d requests (%.0f MB) did not fit and are allocations of their own\n",
+               s->arena.used / 1048576.0, s->arena.cap / 1048576.0, s->arena.overflow_count, s->arena.overflow_bytes / 1048576.0);
+    }
     cudaEventRecord(s->ev_rmse, up);
     if (wait_uploads && cudaStreamSynchronize(s->up_stream) != cudaSuccess) {
         set_last_error(std::string("cumf_als_create: upload failed: ") + cudaGetErrorString(cudaGetLastError()));

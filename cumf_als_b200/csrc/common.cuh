@@ -71,6 +71,8 @@ struct SplitRow {
 struct DevArena {
     unsigned char* base = nullptr;
     size_t cap = 0, used = 0;
+    size_t overflow_bytes = 0;     // requests that did not fit and became allocations of their own (the estimate was short)
+    int overflow_count = 0;
 };
 extern thread_local DevArena* t_arena;
 
