@@ -87,3 +87,19 @@ def test_round2_two_gpu_line():
     assert d["n_gpus"] == 2 and d["config"] == one["config"] and d["scaling"] == "strong"
     assert 1.8 * one["value"] < d["value"] < 2.2 * one["value"]
     assert d["e2e"]["gpus"] == 2 and d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] * d["steps"] == (d["config"]["m"] + d["config"]["n"]) * d["config"]["f"] * 4
+
+
+def test_round2_final_lines():
+    """The last both-arms run of round 2 (tools/gpu_r2_z.sh): same contract, and the theta-side launch is labelled with the unit
+    the ncu capture shows saturated (profiles/traffic.json: shared-memory data pipe 97 %)."""
+    ours, ref = _line("r2z_bench_ours.json"), _line("r2z_bench_reference.json")
+    assert ref["impl"] == "reference" and "impl" not in ours and ours["config"] == ref["config"]
+    assert ours["steps"] == ref["steps"] and ours["warmup"] == ref["warmup"] >= 3
+    r = ours["roofline"]
+    assert r["bound"] == "hbm" and r["frac"] == pytest.approx(r["achieved"] / r["peak"], rel=1e-9) and r["traffic"]
+    th, x = r["launches"]["theta_side"], r["launches"]["x_side"]
+    assert th["bound"].startswith("shared-memory data pipe") and sum(th["smem_data_pipe_pct"].values()) > 90
+    assert x["bound"] == "hbm" and x["dram_bytes"] > 10 * th["dram_bytes"]
+    assert ours["clocks"]["samples"] > 0 and ours["clocks"]["sm_mhz"] > 0
+    assert ours["e2e"]["value"] < ours["value"] and ours["gpu_launches"] > 0
+    assert ref["cpu_baseline"]["kind"] == "reference" and ref["e2e"]["h2d_bytes_per_step"] == 0
