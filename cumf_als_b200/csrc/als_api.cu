@@ -1304,6 +1304,9 @@ extern "C" int cumf_als_update_theta(cumf_als_solver* s, void* stream) {
     // epilogues, on every replica: the next X half-step skips its split pass over all of theta
     s->theta_table_current = false;
     bool wrote = false;
+    // (the table is allocated with the plan and never moves while the row hint holds; if it ever did, the peers would be
+    // writing into the old one: stop pushing split rows rather than trust stale pointers)
+    if (s->theta_split_out.n > 0 && s->theta_split_out.p[0] != own_gather_table(s)) s->theta_split_out.n = 0;
     CUMF_TRY(update_factor_impl(s->pt, s->csc_row.as<int>(), s->csc_val.as<float>(), s->x.as<float>(),
                                 s->theta.as<float>(), s->lambda, s->solver, s->cg_iter, stream, &s->peer_theta,
                                 s->theta_split_out.n > 0 ? &s->theta_split_out : nullptr, false, &wrote));
