@@ -91,8 +91,11 @@ except Exception:
 mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
 gate = path + ".gate"
 import os
+parent = os.getppid()
 with open(path, "w", buffering=1) as f:
     while True:
+        if os.getppid() != parent:        # the bench process is gone (killed before its atexit hook): do not linger
+            break
         if not os.path.exists(gate):      # NVML is only queried inside a timed region (its queries contend with the driver
             time.sleep(0.001)             # calls of everything else on the box: allocation, peer access, IPC)
             continue
